@@ -1,0 +1,406 @@
+/*
+ * wurblpt_b200.h -- C ABI of the B200-native WurblPT path-tracing core.
+ *
+ * This is the drop-in boundary for the one hot path this repository replaces:
+ *   mcpt() -> tracePath() -> BVH::hit()      (reference libwurblpt/wurblpt.hpp:108-436,
+ *                                              libwurblpt/bvh.hpp:277-311)
+ * together with Scene::updateBVH() (reference libwurblpt/scene.hpp:151-169) which
+ * prepares the acceleration structure that path reads.
+ *
+ * The reference is a header-only C++ library with a *source* API (no binary plugin
+ * ABI). The inline C++ API mirror in include/wurblpt/ flattens its Scene / Camera /
+ * Sensor / Parameters objects into the plain structs below and calls these entry
+ * points; nothing else crosses the boundary. Only plain pointers and sizes appear
+ * here -- no C++ types, no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative WPT_E_* code on failure;
+ *     wpt_last_error() returns a thread-local human-readable message. The C++
+ *     wrapper turns failures into fprintf(stderr)+abort(), matching the reference's
+ *     only error convention (bvh.hpp:260-263, mpi.hpp:191-194).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with WPT_E_NO_DEVICE.
+ *   - vec4 colour channels are (r, g, b, nir) as in the reference
+ *     (material_lambertian.hpp:53-59); quaternions are stored (x, y, z, w)
+ *     (gvm.hpp quaternion); matrices are column-major (gvm.hpp matrix).
+ *   - frames are w*h*3 float32, pixel index = y*w + x, row 0 = bottom of the image
+ *     (wurblpt.hpp:339-341, camera.hpp:148).
+ */
+#ifndef WURBLPT_B200_H
+#define WURBLPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WPT_ABI_VERSION 1u
+
+/* error codes */
+#define WPT_OK              0
+#define WPT_E_INVALID      -1   /* invalid argument / malformed scene description */
+#define WPT_E_NO_DEVICE    -2   /* no usable CUDA device (there is no CPU fallback) */
+#define WPT_E_CUDA         -3   /* a CUDA runtime call or kernel failed */
+#define WPT_E_UNSUPPORTED  -4   /* scene uses a feature outside the device's closed set */
+#define WPT_E_STATE        -5   /* call order violated, e.g. render before update_bvh */
+
+/* ---------------------------------------------------------------- animations */
+
+/* One key frame: time + Transformation (reference animation_keyframes.hpp:70-78,
+ * transformation.hpp:47-62). */
+typedef struct wpt_keyframe {
+    float t;
+    float translation[3];
+    float rotation[4];          /* x, y, z, w */
+    float scaling[3];
+} wpt_keyframe;
+
+/* AnimationKeyframes (animation_keyframes.hpp:191-215): a sorted run of key frames. */
+typedef struct wpt_animation {
+    uint32_t first_keyframe;
+    uint32_t keyframe_count;
+} wpt_animation;
+
+/* ------------------------------------------------------------------ textures */
+
+enum {
+    WPT_TEX_CONSTANT    = 0,    /* TextureConstant    texture.hpp:160-180 */
+    WPT_TEX_CHECKER     = 1,    /* TextureChecker     texture.hpp:182-205 */
+    WPT_TEX_IMAGE       = 2,    /* TextureImage       texture_image.hpp:37-233 */
+    WPT_TEX_TRANSFORMER = 3     /* TextureTransformer texture.hpp:207-246 */
+};
+
+enum { WPT_TEXEL_U8 = 0, WPT_TEXEL_U16 = 1, WPT_TEXEL_F32 = 2 };
+
+typedef struct wpt_texture {
+    int32_t type;
+    int32_t src_texture;        /* TRANSFORMER: index of the wrapped texture */
+    int32_t width, height;      /* IMAGE */
+    int32_t components;         /* IMAGE: 1..4 as stored */
+    int32_t texel_type;         /* IMAGE: WPT_TEXEL_* */
+    int32_t linearize_srgb;     /* IMAGE: decode sRGB on rgb channels (texture_image.hpp:235-262) */
+    int32_t horiz, vert;        /* CHECKER */
+    int32_t _pad;
+    uint64_t texel_offset;      /* IMAGE: byte offset into wpt_scene_desc.texels, x fastest, row 0 first */
+    float color0[4];            /* CONSTANT colour / CHECKER colour 0 */
+    float color1[4];            /* CHECKER colour 1 */
+    float coord_factor[2];      /* IMAGE, TRANSFORMER */
+    float coord_offset[2];
+    float val_factor[4];
+    float val_offset[4];
+} wpt_texture;
+
+/* ----------------------------------------------------------------- materials */
+
+enum {
+    WPT_MAT_NONE            = 0,    /* base Material: no scatter, no emission (material.hpp:158-191) */
+    WPT_MAT_LAMBERTIAN      = 1,    /* material_lambertian.hpp:61-102 */
+    WPT_MAT_MIRROR          = 2,    /* material_mirror.hpp:53-62 */
+    WPT_MAT_GLASS           = 3,    /* material_glass.hpp:91-152 */
+    WPT_MAT_GGX             = 4,    /* material_ggx.hpp:173-257 */
+    WPT_MAT_MODPHONG        = 5,    /* material_modphong.hpp:183-327 */
+    WPT_MAT_PHASE_ISOTROPIC = 6,    /* material_phase_function_isotropic.hpp:51-59 */
+    WPT_MAT_LIGHT_DIFFUSE   = 7,    /* light_diffuse.hpp:50-61 */
+    WPT_MAT_LIGHT_SPOT      = 8,    /* light_spot.hpp:45-60 */
+    WPT_MAT_LIGHT_TOF       = 9,    /* light_tof.hpp:55-74 */
+    WPT_MAT_TWOSIDED        = 10    /* material.hpp:273-334 */
+};
+
+#define WPT_MATF_HAVE_NIR            1u  /* 4th channel given explicitly (vec4 ctor), else mean(rgb) */
+#define WPT_MATF_CHROMATIC           2u  /* GLASS: chromaticDispersion (material_glass.hpp:66-69) */
+#define WPT_MATF_DIFFUSE_TEX_ALPHA   4u  /* MODPHONG: diffuseTexHasAlpha */
+#define WPT_MATF_SPECULAR_TEX_ALPHA  8u  /* MODPHONG: specularTexHasAlpha */
+
+/*
+ * Parameter slots per type (unused slots are ignored):
+ *   LAMBERTIAN      v0 albedo                               tex0 albedo
+ *   MIRROR          v0 color                                tex0 color
+ *   GLASS           v0 absorption, v1 ior material, v2 ior surrounding
+ *   GGX             v0 albedo, f0 f1 roughness x y          tex0 albedo, tex1 roughness
+ *   MODPHONG        v0 diffuse, v1 specular, v2 transmissive, v3 emissive,
+ *                   f0 shininess, f1 opacity, f2 index of refraction
+ *                   tex0 diffuse, tex1 specular, tex2 shininess, tex3 opacity, tex4 emissive
+ *   PHASE_ISOTROPIC v0 albedo
+ *   LIGHT_DIFFUSE   v0 emission                             tex0
+ *   LIGHT_SPOT      v0 emission, f0 cos(half opening angle) tex0
+ *   LIGHT_TOF       f0 radiance, f1 cos(half opening angle) tex0
+ *   TWOSIDED        front, back (material indices, -1 = null pointer)
+ */
+typedef struct wpt_material {
+    int32_t type;
+    int32_t normal_tex;         /* Material::normalTex, -1 = none (material.hpp:132) */
+    int32_t tex[5];             /* texture indices, -1 = none */
+    uint32_t flags;
+    int32_t front, back;
+    int32_t _pad[2];
+    float v0[4], v1[4], v2[4], v3[4];
+    float f[4];
+} wpt_material;
+
+/* ------------------------------------------------------------------ geometry */
+
+#define WPT_MESHF_TEXCOORDS 1u
+#define WPT_MESHF_TANGENTS  2u
+
+/* Mesh (mesh.hpp:38-153): interleaved vertices pos(3) nrm(3) [tc(2)] [tng(3)]. */
+typedef struct wpt_mesh {
+    uint64_t vertex_offset;     /* in floats, into wpt_scene_desc.vertices */
+    uint64_t index_offset;      /* in uint32, into wpt_scene_desc.indices */
+    uint32_t vertex_count;
+    uint32_t vertex_stride;     /* 6, 8 or 11 floats */
+    uint32_t triangle_count;
+    uint32_t flags;             /* WPT_MESHF_* */
+} wpt_mesh;
+
+/* MeshInstance (mesh.hpp:159-189). */
+typedef struct wpt_instance {
+    int32_t mesh;
+    int32_t material;           /* -1 = nullptr (e.g. medium boundaries) */
+    int32_t animation;          /* -1 = none */
+    int32_t has_transform;      /* !transformation.isIdentity() */
+    float M[16];                /* transformationM, column-major */
+    float N[9];                 /* transformationN, column-major */
+    float _pad[3];
+} wpt_instance;
+
+/* HitableSphere (hitable_sphere.hpp:33-86). */
+typedef struct wpt_sphere {
+    float center[3];
+    float radius;
+    float rotation[4];
+    int32_t material;
+    int32_t animation;
+    int32_t _pad[2];
+} wpt_sphere;
+
+/* HitableMedium (hitable_medium.hpp:36-98). The boundary is a run of global hitable
+ * ids (see wpt_component) in wpt_scene_desc.boundary_hitables. */
+typedef struct wpt_medium {
+    float density;
+    int32_t material;           /* phase function */
+    uint32_t first_boundary;
+    uint32_t boundary_count;
+} wpt_medium;
+
+enum { WPT_COMP_MESH_INSTANCE = 0, WPT_COMP_SPHERE = 1, WPT_COMP_MEDIUM = 2 };
+
+#define WPT_COMPF_HITABLE 1u    /* Scene::take (in the BVH); unset = Scene::takeUnhitable (scene.hpp:127-135) */
+#define WPT_COMPF_HOTSPOT 2u    /* HotSpotType::HotSpot (scene.hpp:48-52,113-125) */
+
+/*
+ * One Scene::take(SceneComponent*) call. Components expand, in order, into the
+ * scene's hitables: a mesh instance into one hitable per triangle, a sphere or a
+ * medium into one. The position of a hitable in that expansion (over ALL components,
+ * hitable or not) is its *global hitable id*: the id wpt_primary_hits() reports and
+ * medium boundaries refer to.
+ */
+typedef struct wpt_component {
+    int32_t type;               /* WPT_COMP_* */
+    int32_t ref;                /* index into instances / spheres / media */
+    uint32_t flags;             /* WPT_COMPF_* */
+    uint32_t _pad;
+} wpt_component;
+
+/* ------------------------------------------------------------ environment map */
+
+enum { WPT_ENV_NONE = 0, WPT_ENV_EQUIRECT = 1, WPT_ENV_CUBE = 2 };
+enum { WPT_ENV_COMPAT_MITSUBA = 0, WPT_ENV_COMPAT_SURROUND_VIDEO = 1 };
+
+/* EnvironmentMap (envmap.hpp:44-285). The importance tables are those built by
+ * initializeImportanceSampling(N) (envmap.hpp:121-158); is_n = 0 means it was not called. */
+typedef struct wpt_envmap {
+    int32_t type;
+    int32_t compat;             /* EQUIRECT */
+    int32_t tex[6];             /* EQUIRECT: tex[0]; CUBE: posx negx posy negy posz negz */
+    int32_t is_n;
+    int32_t _pad;
+    const float* M;             /* is_n*is_n */
+    const int32_t* Ms;
+    const float* Mcs;
+} wpt_envmap;
+
+/* --------------------------------------------------------------------- scene */
+
+typedef struct wpt_scene_desc {
+    uint32_t abi_version;       /* WPT_ABI_VERSION */
+    uint32_t n_animations;
+    const wpt_animation* animations;
+    uint32_t n_keyframes;
+    uint32_t n_textures;
+    const wpt_keyframe* keyframes;
+    const wpt_texture* textures;
+    uint64_t texel_bytes;
+    const uint8_t* texels;
+    uint32_t n_materials;
+    uint32_t n_meshes;
+    const wpt_material* materials;
+    const wpt_mesh* meshes;
+    uint64_t n_vertex_floats;
+    const float* vertices;
+    uint64_t n_indices;
+    const uint32_t* indices;
+    uint32_t n_instances;
+    uint32_t n_spheres;
+    const wpt_instance* instances;
+    const wpt_sphere* spheres;
+    uint32_t n_media;
+    uint32_t n_boundary;
+    const wpt_medium* media;
+    const uint32_t* boundary_hitables;
+    uint32_t n_components;
+    uint32_t _pad;
+    const wpt_component* components;
+    wpt_envmap envmap;
+} wpt_scene_desc;
+
+/* -------------------------------------------------------------------- camera */
+
+enum { WPT_SURROUND_OFF = 0, WPT_SURROUND_180 = 1, WPT_SURROUND_360 = 2 };
+enum { WPT_DISTORTION_NONE = 0, WPT_DISTORTION_RADIAL_AND_PLANAR = 1,
+       WPT_DISTORTION_RADIAL_ONLY = 2, WPT_DISTORTION_OPENCV = 3 };
+
+/* Camera + Optics (camera.hpp:42-107, optics.hpp:37-351). A camera animation that
+ * is an AnimationKeyframes is passed as key frames; n_keyframes = 0 uses `pose`. */
+typedef struct wpt_camera_desc {
+    int32_t surround_mode;
+    float stereoscopic_distance;
+    float l, r, b, t;           /* Projection: frustum at near = 1 (optics.hpp:40) */
+    int32_t distortion_type;
+    float k1, k2, k3, p1, p2;
+    float b1, b2, b3, b4;
+    float lens_radius, focus_dist;
+    float pose_translation[3];
+    float pose_rotation[4];
+    float pose_scaling[3];
+    uint32_t n_keyframes;
+    const wpt_keyframe* keyframes;
+} wpt_camera_desc;
+
+/* -------------------------------------------------------------------- sensor */
+
+enum { WPT_SENSOR_RGB = 0, WPT_SENSOR_TOF_AMCW = 1 };
+
+/* SensorRGB (sensor_rgb.hpp:41-87) / SensorTofAmcw (sensor_tof_amcw.hpp:227-259). */
+typedef struct wpt_sensor_desc {
+    int32_t type;
+    uint32_t width, height;
+    /* RGB gating */
+    float min_dist_to_light, max_dist_to_light;
+    float min_path_len, max_path_len;
+    /* ToF AMCW */
+    float pixel_area;           /* um^2 */
+    float exposure_time;        /* us */
+    float contrast;
+    uint32_t phase_index;       /* setPhaseIndex(), enters tau(), sensor_tof_amcw.hpp:97-105 */
+    uint32_t phase_count;       /* phaseImageCount */
+    uint32_t _pad;
+    double modulation_frequency;/* Hz; f/c is formed in double then cast (sensor_tof_amcw.hpp:107-110) */
+} wpt_sensor_desc;
+
+/* Parameters (wurblpt.hpp:79-96). */
+typedef struct wpt_params {
+    uint32_t max_path_components;
+    float rr_threshold;
+    int32_t randomize_ray_over_pixel;
+    float min_hit_distance;
+} wpt_params;
+
+/* ------------------------------------------------------------ render control */
+
+enum {
+    WPT_TRAVERSAL_WIDE      = 0,    /* 4-wide BVH, near-to-far ordered (default) */
+    WPT_TRAVERSAL_REFERENCE = 1     /* binary BVH walked in the reference's storage order (bvh.hpp:277-311) */
+};
+
+typedef struct wpt_render_opts {
+    int32_t traversal;          /* WPT_TRAVERSAL_* */
+    int32_t substreams;         /* PRNG sub-streams per pixel: 1 = the reference's one stream per pixel
+                                   (wurblpt.hpp:342), 2..32 (power of two) split a pixel's samples over
+                                   lanes, 0 = choose from image size */
+    uint32_t tile_first;        /* this call renders pixel tiles tile_first, tile_first+tile_stride, ... */
+    uint32_t tile_stride;       /* 0 or 1 = all tiles; N = one of N GPUs (the MPICoordinator block split, mpi.hpp:241-254) */
+    int32_t frame_on_device;    /* `frame` is a device pointer; untouched tiles are left as they are */
+    int32_t _pad;
+    void* stream;               /* cudaStream_t to launch on (NULL = default stream) */
+} wpt_render_opts;
+
+typedef struct wpt_stats {
+    uint64_t samples;           /* camera paths started */
+    uint64_t rays;              /* closest-hit queries issued from the path loop (wurblpt.hpp:131,204,236) */
+    uint64_t nested_queries;    /* medium-boundary queries (hitable_medium.hpp:75-79) */
+    uint64_t tiles;             /* pixel tiles rendered by this call */
+    float kernel_ms;            /* device time of the render kernel (CUDA events) */
+    float total_ms;             /* host wall time of the call including copies */
+    uint32_t launches;          /* kernels launched by this call */
+    uint32_t _pad;
+} wpt_stats;
+
+typedef struct wpt_scene_info {
+    uint64_t hitables;          /* in the top-level BVH */
+    uint64_t triangles, spheres, media;
+    uint64_t binary_nodes;      /* reference-layout nodes (2n-1) */
+    uint64_t wide_nodes;
+    uint32_t binary_depth, wide_depth;
+    uint32_t hot_spots;
+    uint32_t _pad;
+    uint64_t device_bytes;
+    double build_seconds;       /* host SAH build + collapse */
+    double upload_seconds;
+} wpt_scene_info;
+
+typedef struct wpt_scene wpt_scene;
+
+/* ------------------------------------------------------------- entry points */
+
+/* Library / ABI version string. */
+const char* wpt_version(void);
+
+/* Message for the last failure on the calling thread. */
+const char* wpt_last_error(void);
+
+/* Number of usable CUDA devices (0 without a GPU). */
+int wpt_device_count(void);
+
+/* Ingest a scene description: copies what it needs (the caller may free `desc`
+ * afterwards) and uploads time-independent data to `device`. Replaces the sum of
+ * Scene::take() calls (scene.hpp:86-141). */
+int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** scene);
+
+/* Scene::updateBVH(t0, t1) (scene.hpp:151-169): bound every hitable over [t0,t1]
+ * (hitable_triangle.hpp:336-395, hitable_sphere.hpp:97-110, hitable_medium.hpp:59-67),
+ * build the SAH tree (bvh.hpp:93-193), derive the device layouts and upload them. */
+int wpt_scene_update_bvh(wpt_scene* scene, float t0, float t1);
+
+int wpt_scene_get_info(const wpt_scene* scene, wpt_scene_info* info);
+
+void wpt_scene_destroy(wpt_scene* scene);
+
+/* mcpt() (wurblpt.hpp:279-436): render samples_sqrt^2 paths per pixel into `frame`
+ * (w*h*3 floats; host memory unless opts->frame_on_device). `opts` and `stats` may be NULL. */
+int wpt_render(wpt_scene* scene, const wpt_camera_desc* camera, const wpt_sensor_desc* sensor,
+        const wpt_params* params, uint32_t samples_sqrt, float t0, float t1,
+        const wpt_render_opts* opts, float* frame, wpt_stats* stats);
+
+/* The primary-ray closest-hit query of getGroundTruth() (wurblpt.hpp:659-668): one ray
+ * through each pixel centre at time t, randomness off. ids[pixel] = global hitable id or -1,
+ * a[pixel] = hit distance (undefined where id = -1). Host pointers. */
+int wpt_primary_hits(wpt_scene* scene, const wpt_camera_desc* camera,
+        uint32_t width, uint32_t height, float t, float min_hit_distance,
+        const wpt_render_opts* opts, int32_t* ids, float* a);
+
+/* Closest-hit queries for caller-supplied rays (origin xyz, unit direction xyz per ray;
+ * host pointers). Used to check BVH::hit() parity on secondary-ray distributions. */
+int wpt_trace_rays(wpt_scene* scene, const float* origins, const float* directions, uint64_t n_rays,
+        float time, float min_hit_distance, const wpt_render_opts* opts, int32_t* ids, float* a);
+
+/* Prng known-answer hook (prng.hpp:79-95): out[i*n_draws + k] = k-th in01() of Prng(seeds[i]),
+ * evaluated on the device. Host pointers. */
+int wpt_prng_kat(const uint32_t* seeds, uint32_t n_seeds, uint32_t n_draws, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
