@@ -363,10 +363,18 @@ const char* wpt_last_error(void);
 /* Number of usable CUDA devices (0 without a GPU). */
 int wpt_device_count(void);
 
+/* sizeof() of the ABI structs as compiled into the library, in declaration order
+ * (0 = wpt_keyframe ... 16 = wpt_scene_info); lets a foreign-language binding verify its layout. */
+size_t wpt_abi_sizeof(int which);
+
+#define WPT_DEVICE_NONE (-1)
+
 /* Ingest a scene description: copies what it needs (the caller may free `desc`
  * afterwards) and uploads time-independent data to `device`. Replaces the sum of
  * Scene::take() calls (scene.hpp:86-141). */
 int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** scene);
+/* device = WPT_DEVICE_NONE creates a host-only scene: wpt_scene_update_bvh() and the inspection
+ * calls work (they are pure host code), every rendering call fails with WPT_E_NO_DEVICE. */
 
 /* Scene::updateBVH(t0, t1) (scene.hpp:151-169): bound every hitable over [t0,t1]
  * (hitable_triangle.hpp:336-395, hitable_sphere.hpp:97-110, hitable_medium.hpp:59-67),
@@ -377,6 +385,11 @@ int wpt_scene_get_info(const wpt_scene* scene, wpt_scene_info* info);
 
 void wpt_scene_destroy(wpt_scene* scene);
 
+/* Inspection: the top-level tree in the reference's linear layout (BVHNodeLinear, bvh.hpp:217-246),
+ * binary_nodes entries: boxes[i*6..] = lo xyz, hi xyz; inner nodes have leaf[i] = -1 and link[i] =
+ * index of child 2 (child 1 is i+1); leaves have leaf[i] = global hitable id. */
+int wpt_scene_get_binary_nodes(const wpt_scene* scene, uint64_t capacity, float* boxes, uint32_t* link, int32_t* leaf);
+
 /* mcpt() (wurblpt.hpp:279-436): render samples_sqrt^2 paths per pixel into `frame`
  * (w*h*3 floats; host memory unless opts->frame_on_device). `opts` and `stats` may be NULL. */
 int wpt_render(wpt_scene* scene, const wpt_camera_desc* camera, const wpt_sensor_desc* sensor,
@@ -385,15 +398,18 @@ int wpt_render(wpt_scene* scene, const wpt_camera_desc* camera, const wpt_sensor
 
 /* The primary-ray closest-hit query of getGroundTruth() (wurblpt.hpp:659-668): one ray
  * through each pixel centre at time t, randomness off. ids[pixel] = global hitable id or -1,
- * a[pixel] = hit distance (undefined where id = -1). Host pointers. */
+ * a[pixel] = hit distance (0 where id = -1). Host pointers. `counters`, if not NULL, receives
+ * { tree nodes visited, leaf (hitable) tests, nested medium-boundary queries } summed over all
+ * rays: with WPT_TRAVERSAL_REFERENCE these are the reference's own visit counts, the n and l of
+ * the algorithmic-bytes formula. */
 int wpt_primary_hits(wpt_scene* scene, const wpt_camera_desc* camera,
         uint32_t width, uint32_t height, float t, float min_hit_distance,
-        const wpt_render_opts* opts, int32_t* ids, float* a);
+        const wpt_render_opts* opts, int32_t* ids, float* a, uint64_t* counters);
 
 /* Closest-hit queries for caller-supplied rays (origin xyz, unit direction xyz per ray;
  * host pointers). Used to check BVH::hit() parity on secondary-ray distributions. */
 int wpt_trace_rays(wpt_scene* scene, const float* origins, const float* directions, uint64_t n_rays,
-        float time, float min_hit_distance, const wpt_render_opts* opts, int32_t* ids, float* a);
+        float time, float min_hit_distance, const wpt_render_opts* opts, int32_t* ids, float* a, uint64_t* counters);
 
 /* Prng known-answer hook (prng.hpp:79-95): out[i*n_draws + k] = k-th in01() of Prng(seeds[i]),
  * evaluated on the device. Host pointers. */

@@ -718,6 +718,35 @@ int ref_default_view(const char* name, wpt_camera_desc* cam, wpt_sensor_desc* se
     return 0;
 }
 
+/* The reference's linearised top-level tree (BVH::_nodes, bvh.hpp:217-246) in the layout of
+ * wpt_scene_get_binary_nodes(). Returns the node count, or -1. */
+long long ref_bvh_nodes(int h, uint64_t capacity, float* boxes, uint32_t* link, int32_t* leaf)
+{
+    RefScene* rs = getScene(h);
+    if (!rs || !rs->scene._bvh)
+        return -1;
+    const std::vector<BVHNodeLinear>& nodes = rs->scene._bvh->_nodes;
+    if (!boxes)
+        return (long long)nodes.size();
+    if (capacity < nodes.size())
+        return -1;
+    for (size_t i = 0; i < nodes.size(); i++) {
+        for (int k = 0; k < 3; k++) {
+            boxes[i * 6 + k] = nodes[i].aabb.lo[k];
+            boxes[i * 6 + 3 + k] = nodes[i].aabb.hi[k];
+        }
+        if (nodes[i].child2IndexMulTwoPlusOne % 2 == 1) {
+            link[i] = nodes[i].child2IndexMulTwoPlusOne / 2;
+            leaf[i] = -1;
+        } else {
+            link[i] = 0;
+            auto it = rs->flat.hitableId.find(nodes[i].hitable);
+            leaf[i] = (it == rs->flat.hitableId.end() ? -2 : it->second);
+        }
+    }
+    return (long long)nodes.size();
+}
+
 /* mcpt() of the reference (wurblpt.hpp:279-436). Returns wall seconds spent inside mcpt(),
  * or a negative value on error. The BVH must have been updated for [t0,t1]. */
 double ref_render(int h, const wpt_camera_desc* cam, const wpt_sensor_desc* sensor, const wpt_params* params,

@@ -138,3 +138,18 @@ def prng_kat(seeds, n_draws, flavour="strict"):
     out = np.zeros((len(seeds), n_draws), dtype=np.float32)
     load(flavour).ref_prng_kat(seeds.ctypes.data, len(seeds), n_draws, out.ctypes.data)
     return out
+
+
+def bvh_nodes(scene):
+    """The reference's linearised BVH of a RefScene: (boxes[n,6], link[n], leaf[n])."""
+    lib = scene.lib
+    lib.ref_bvh_nodes.restype = C.c_longlong
+    lib.ref_bvh_nodes.argtypes = [C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = lib.ref_bvh_nodes(scene.h, 0, None, None, None)
+    if n < 0:
+        raise RuntimeError("reference BVH not built")
+    boxes = np.zeros((n, 6), dtype=np.float32)
+    link = np.zeros(n, dtype=np.uint32)
+    leaf = np.zeros(n, dtype=np.int32)
+    lib.ref_bvh_nodes(scene.h, n, boxes.ctypes.data, link.ctypes.data, leaf.ctypes.data)
+    return boxes, link, leaf

@@ -245,14 +245,17 @@ inline void buildSynth(Scene& scene, float scale = 1.0f, int envWidth = 2048, in
             float z = -9.0f + 2.0f * i;
             Transformation base(vec3(x, 0.15f, z), quat::null(), vec3(0.42f, 0.15f, 0.42f));
             scene.take(new MeshInstance(scene.take(generateCube(base, tess(14))), ggx()));
+            // column shafts are stretched spheres: evenly shaped triangles. (Very thin slivers such
+            // as a 1000-slice cylinder with one stack drive the reference's SAH sweep into trees
+            // deeper than its 128-level limit, bvh.hpp:230,260-263.)
             Transformation shaft(vec3(x, 1.8f, z), quat::null(), vec3(0.28f, 1.5f, 0.28f));
-            scene.take(new MeshInstance(scene.take(generateClosedCylinder(shaft, tess(1000))), ggx()));
+            scene.take(new MeshInstance(scene.take(generateSphere(shaft, tess(100), tess(60))), ggx()));
             Transformation cap(vec3(x, 3.4f, z), quat::null(), vec3(0.4f, 0.1f, 0.4f));
             scene.take(new MeshInstance(scene.take(generateCube(cap, tess(10))), ggx()));
             if (i < 9) {
                 Transformation arch(vec3(x, 3.5f, z + 1.0f),
                         toQuat(radians(90.0f), vec3(0.0f, 1.0f, 0.0f)), vec3(1.0f, 1.0f, 0.35f));
-                scene.take(new MeshInstance(scene.take(generateTorus(arch, 0.72f, tess(96), tess(96))), ggx()));
+                scene.take(new MeshInstance(scene.take(generateTorus(arch, 0.72f, tess(92), tess(92))), ggx()));
             }
         }
     }
@@ -263,14 +266,14 @@ inline void buildSynth(Scene& scene, float scale = 1.0f, int envWidth = 2048, in
         Transformation ped(vec3(x, 0.3f, z), toQuat(radians(20.0f * i), vec3(0.0f, 1.0f, 0.0f)), vec3(0.3f));
         scene.take(new MeshInstance(scene.take(generateCube(ped, tess(12))), ggx()));
         Transformation ball(vec3(x, 0.95f, z), quat::null(), vec3(0.35f));
-        scene.take(new MeshInstance(scene.take(generateSphere(ball, tess(200), tess(100))), ggx()));
+        scene.take(new MeshInstance(scene.take(generateSphere(ball, tess(170), tess(85))), ggx()));
     }
     // centre piece: a big lying torus and a cone
     {
         Transformation T(vec3(0.0f, 0.45f, 0.5f), upright, vec3(1.6f, 1.6f, 1.2f));
-        scene.take(new MeshInstance(scene.take(generateTorus(T, 0.55f, tess(310), tess(310))), ggx()));
-        Transformation C(vec3(0.0f, 1.6f, 0.5f), quat::null(), vec3(0.5f, 1.0f, 0.5f));
-        scene.take(new MeshInstance(scene.take(generateClosedCone(C, tess(160), tess(80))), ggx()));
+        scene.take(new MeshInstance(scene.take(generateTorus(T, 0.55f, tess(240), tess(240))), ggx()));
+        Transformation C(vec3(0.0f, 1.6f, 0.5f), toQuat(radians(35.0f), vec3(0.0f, 0.0f, 1.0f)), vec3(0.45f, 0.45f, 0.3f));
+        scene.take(new MeshInstance(scene.take(generateTorus(C, 0.3f, tess(150), tess(150))), ggx()));
     }
     // back wall
     {

@@ -1,0 +1,729 @@
+/*
+ * capi.cu -- the C ABI (include/wurblpt_b200.h): scene upload, launch set-up, result copies.
+ * Host code only; the kernels live in kernels.cu. There is no CPU rendering path in this
+ * library: every compute entry point needs a CUDA device and fails loudly without one.
+ */
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "wurblpt_b200.h"
+#include "scene_host.hpp"
+#include "device_scene.cuh"
+#include "kernels.hpp"
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const std::string& message)
+{
+    g_lastError = message;
+    return code;
+}
+
+int failCuda(cudaError_t e, const char* what)
+{
+    return fail(WPT_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define WPT_CUDA(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return failCuda(e_, what); } while (0)
+
+/* Device allocation that grows on demand and is freed with its owner. */
+struct DeviceBuf {
+    void* p = nullptr;
+    size_t capacity = 0;
+
+    ~DeviceBuf() { release(); }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        capacity = 0;
+    }
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= capacity)
+            return cudaSuccess;
+        release();
+        size_t want = bytes < 256 ? 256 : bytes;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess)
+            capacity = want;
+        return e;
+    }
+    cudaError_t upload(const void* src, size_t bytes, cudaStream_t stream = 0)
+    {
+        cudaError_t e = reserve(bytes);
+        if (e != cudaSuccess || bytes == 0)
+            return e;
+        return cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, stream);
+    }
+    template<typename T> const T* as() const { return static_cast<const T*>(p); }
+};
+
+/* color.hpp:270-278,287-295 */
+float srgbToLinear(float x)
+{
+    return (x <= 0.04045f ? (x * (1.0f / 12.92f)) : std::pow((x + 0.055f) * (1.0f / 1.055f), 2.4f));
+}
+
+/* TextureImage::value(x, y) (texture_image.hpp:85-180): decode one texel to RGBA float */
+void decodeTexel(const wpt_texture& t, const uint8_t* base, size_t index, float* out)
+{
+    float c[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+    for (int k = 0; k < t.components; k++) {
+        if (t.texel_type == WPT_TEXEL_U8)
+            c[k] = base[index * t.components + k] / 255.0f;
+        else if (t.texel_type == WPT_TEXEL_U16)
+            c[k] = reinterpret_cast<const uint16_t*>(base)[index * t.components + k] / 65535.0f;
+        else
+            c[k] = reinterpret_cast<const float*>(base)[index * t.components + k];
+    }
+    const bool srgb = t.linearize_srgb != 0;
+    if (t.components == 3) {
+        out[0] = srgb ? srgbToLinear(c[0]) : c[0];
+        out[1] = srgb ? srgbToLinear(c[1]) : c[1];
+        out[2] = srgb ? srgbToLinear(c[2]) : c[2];
+        out[3] = 1.0f;
+    } else if (t.components == 4) {
+        out[0] = srgb ? srgbToLinear(c[0]) : c[0];
+        out[1] = srgb ? srgbToLinear(c[1]) : c[1];
+        out[2] = srgb ? srgbToLinear(c[2]) : c[2];
+        out[3] = c[3];
+    } else if (t.components == 1) {
+        float v = srgb ? srgbToLinear(c[0]) : c[0];
+        out[0] = out[1] = out[2] = v;
+        out[3] = 1.0f;
+    } else {
+        float v = srgb ? srgbToLinear(c[0]) : c[0];
+        out[0] = out[1] = out[2] = v;
+        out[3] = c[1];
+    }
+}
+
+}
+
+struct wpt_scene {
+    wpt::HostScene host;
+    int device = 0;
+    int numSMs = 0;
+    bool sceneHasMedia = false, sceneHasAnimation = false;
+    /* time-independent arrays */
+    DeviceBuf materials, instances, meshes, vertices, indices, textures, texels;
+    DeviceBuf animations, keyframes, envM, envMs, envMcs;
+    /* per updateBVH */
+    DeviceBuf node4, bnode, tri, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs;
+    /* per call scratch */
+    DeviceBuf counters, camKeys, frame, qOrigins, qDirections, qIds, qDist, qStats;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    wptd::DScene d;
+    double uploadSeconds = 0.0;
+
+    ~wpt_scene()
+    {
+        if (evStart) cudaEventDestroy(evStart);
+        if (evStop) cudaEventDestroy(evStop);
+    }
+
+    uint64_t deviceBytes() const
+    {
+        const DeviceBuf* all[] = { &materials, &instances, &meshes, &vertices, &indices, &textures, &texels,
+            &animations, &keyframes, &envM, &envMs, &envMcs, &node4, &bnode, &tri, &sph, &med,
+            &triGlobal, &sphGlobal, &medGlobal, &hotRefs };
+        uint64_t n = 0;
+        for (const DeviceBuf* b : all)
+            n += b->capacity;
+        return n;
+    }
+};
+
+namespace {
+
+int selectDevice(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(WPT_E_NO_DEVICE, std::string("no CUDA device available (")
+                + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0")
+                + "); this library has no CPU fallback");
+    if (device < 0 || device >= n)
+        return fail(WPT_E_INVALID, "device index out of range");
+    WPT_CUDA(cudaSetDevice(device), "cudaSetDevice");
+    return WPT_OK;
+}
+
+int uploadStatic(wpt_scene* s)
+{
+    const wpt::HostScene& h = s->host;
+    WPT_CUDA(s->materials.upload(h.materials.data(), h.materials.size() * sizeof(wpt_material)), "upload materials");
+    WPT_CUDA(s->instances.upload(h.instances.data(), h.instances.size() * sizeof(wpt_instance)), "upload instances");
+    WPT_CUDA(s->meshes.upload(h.meshes.data(), h.meshes.size() * sizeof(wpt_mesh)), "upload meshes");
+    WPT_CUDA(s->vertices.upload(h.vertices.data(), h.vertices.size() * sizeof(float)), "upload vertices");
+    WPT_CUDA(s->indices.upload(h.indices.data(), h.indices.size() * sizeof(uint32_t)), "upload indices");
+    WPT_CUDA(s->animations.upload(h.animations.data(), h.animations.size() * sizeof(wpt_animation)), "upload animations");
+    WPT_CUDA(s->keyframes.upload(h.keyframes.data(), h.keyframes.size() * sizeof(wpt_keyframe)), "upload keyframes");
+    WPT_CUDA(s->envM.upload(h.envM.data(), h.envM.size() * sizeof(float)), "upload envmap M");
+    WPT_CUDA(s->envMs.upload(h.envMs.data(), h.envMs.size() * sizeof(int32_t)), "upload envmap Ms");
+    WPT_CUDA(s->envMcs.upload(h.envMcs.data(), h.envMcs.size() * sizeof(float)), "upload envmap Mcs");
+
+    /* textures: descriptors + image texels decoded once to RGBA float (16-byte texel fetches) */
+    std::vector<wptd::DTexture> dt(h.textures.size());
+    size_t texelCount = 0;
+    for (const wpt_texture& t : h.textures)
+        if (t.type == WPT_TEX_IMAGE)
+            texelCount += size_t(t.width) * t.height;
+    if (texelCount >= 0xFFFFFFFFull)
+        return fail(WPT_E_UNSUPPORTED, "too many texels");
+    std::vector<float> decoded(texelCount * 4);
+    size_t cursor = 0;
+    for (size_t i = 0; i < h.textures.size(); i++) {
+        const wpt_texture& t = h.textures[i];
+        wptd::DTexture& o = dt[i];
+        std::memset(&o, 0, sizeof(o));
+        o.type = t.type;
+        o.src = t.src_texture;
+        o.width = t.width;
+        o.height = t.height;
+        o.horiz = t.horiz;
+        o.vert = t.vert;
+        o.color0 = make_float4(t.color0[0], t.color0[1], t.color0[2], t.color0[3]);
+        o.color1 = make_float4(t.color1[0], t.color1[1], t.color1[2], t.color1[3]);
+        o.coordFactor = make_float2(t.coord_factor[0], t.coord_factor[1]);
+        o.coordOffset = make_float2(t.coord_offset[0], t.coord_offset[1]);
+        o.valFactor = make_float4(t.val_factor[0], t.val_factor[1], t.val_factor[2], t.val_factor[3]);
+        o.valOffset = make_float4(t.val_offset[0], t.val_offset[1], t.val_offset[2], t.val_offset[3]);
+        if (t.type == WPT_TEX_IMAGE) {
+            o.texelBase = uint32_t(cursor);
+            const uint8_t* base = h.texels.data() + t.texel_offset;
+            const size_t n = size_t(t.width) * t.height;
+            float* dst = decoded.data() + cursor * 4;
+            #pragma omp parallel for schedule(static)
+            for (size_t k = 0; k < n; k++)
+                decodeTexel(t, base, k, dst + k * 4);
+            cursor += n;
+        }
+    }
+    WPT_CUDA(s->textures.upload(dt.data(), dt.size() * sizeof(wptd::DTexture)), "upload textures");
+    WPT_CUDA(s->texels.upload(decoded.data(), decoded.size() * sizeof(float)), "upload texels");
+    WPT_CUDA(cudaDeviceSynchronize(), "upload scene");
+    return WPT_OK;
+}
+
+void refreshDeviceScene(wpt_scene* s)
+{
+    wptd::DScene& d = s->d;
+    const wpt::HostScene& h = s->host;
+    d.node4 = s->node4.as<float4>();
+    d.bnode = s->bnode.as<float4>();
+    d.tri = s->tri.as<float4>();
+    d.sph = s->sph.as<float4>();
+    d.med = s->med.as<float4>();
+    d.triGlobal = s->triGlobal.as<uint32_t>();
+    d.sphGlobal = s->sphGlobal.as<uint32_t>();
+    d.medGlobal = s->medGlobal.as<uint32_t>();
+    d.hotRefs = s->hotRefs.as<uint32_t>();
+    d.materials = s->materials.as<wpt_material>();
+    d.instances = s->instances.as<wpt_instance>();
+    d.meshes = s->meshes.as<wpt_mesh>();
+    d.vertices = s->vertices.as<float>();
+    d.indices = s->indices.as<uint32_t>();
+    d.textures = s->textures.as<wptd::DTexture>();
+    d.texels = s->texels.as<float4>();
+    d.animations = s->animations.as<wpt_animation>();
+    d.keyframes = s->keyframes.as<wpt_keyframe>();
+    d.envM = s->envM.as<float>();
+    d.envMs = s->envMs.as<int32_t>();
+    d.envMcs = s->envMcs.as<float>();
+    d.root4 = h.root4;
+    d.nHot = uint32_t(h.hotSpotRefs.size());
+    d.nAnimations = uint32_t(h.animations.size());
+    d.envType = h.env.type;
+    d.envCompat = h.env.compat;
+    d.envN = h.env.is_n;
+    for (int i = 0; i < 6; i++)
+        d.envTex[i] = h.env.tex[i];
+}
+
+wpt::Trs cameraPose(const wpt_camera_desc* c, float t)
+{
+    if (c->n_keyframes > 0 && c->keyframes)
+        return wpt::keyframesAt(c->keyframes, c->n_keyframes, t);
+    return wpt::Trs{ wpt::v3(c->pose_translation[0], c->pose_translation[1], c->pose_translation[2]),
+        wpt::Quat{ c->pose_rotation[0], c->pose_rotation[1], c->pose_rotation[2], c->pose_rotation[3] },
+        wpt::v3(c->pose_scaling[0], c->pose_scaling[1], c->pose_scaling[2]) };
+}
+
+/* camera part of the launch parameters: Camera::getRayHelper (camera.hpp:114-120) */
+int fillCamera(wpt_scene* s, const wpt_camera_desc* c, float t0, uint32_t width, uint32_t height,
+        wptd::RenderParams& P, cudaStream_t stream)
+{
+    if (c->surround_mode < WPT_SURROUND_OFF || c->surround_mode > WPT_SURROUND_360
+            || c->distortion_type < WPT_DISTORTION_NONE || c->distortion_type > WPT_DISTORTION_OPENCV)
+        return fail(WPT_E_INVALID, "camera description is malformed");
+    P.surround = c->surround_mode;
+    P.stereo = c->stereoscopic_distance;
+    P.l = c->l; P.r = c->r; P.b = c->b; P.t = c->t;
+    P.distortionType = c->distortion_type;
+    P.k1 = c->k1; P.k2 = c->k2; P.k3 = c->k3; P.p1 = c->p1; P.p2 = c->p2;
+    P.b1 = c->b1; P.b2 = c->b2; P.b3 = c->b3; P.b4 = c->b4;
+    P.lensRadius = c->lens_radius;
+    P.focusDist = c->focus_dist;
+    const wpt::Trs T = cameraPose(c, t0);
+    P.camT = make_float3(T.t.x, T.t.y, T.t.z);
+    P.camR = make_float4(T.r.x, T.r.y, T.r.z, T.r.w);
+    P.camS = make_float3(T.s.x, T.s.y, T.s.z);
+    P.nCamKeys = (c->keyframes ? c->n_keyframes : 0);
+    P.camKeys = nullptr;
+    if (P.nCamKeys > 0) {
+        WPT_CUDA(s->camKeys.upload(c->keyframes, size_t(P.nCamKeys) * sizeof(wpt_keyframe), stream), "upload camera key frames");
+        P.camKeys = s->camKeys.as<wpt_keyframe>();
+    }
+    /* LensDistortion::getHelper (optics.hpp:215-224) with Projection::center/focalLength (optics.hpp:83-97) */
+    P.distCenter = make_float2(c->l / (c->l - c->r), c->b / (c->b - c->t));
+    P.distFocal = make_float2(1.0f / (c->r - c->l), 1.0f / (c->t - c->b));
+    P.distInvFocal = make_float2(c->r - c->l, c->t - c->b);
+    P.width = width;
+    P.height = height;
+    return WPT_OK;
+}
+
+int sceneFeatures(const wpt_scene* s, bool needOpl)
+{
+    return (s->sceneHasMedia || s->sceneHasAnimation || needOpl) ? 7 : 0;
+}
+
+int checkReady(wpt_scene* s)
+{
+    if (!s)
+        return fail(WPT_E_INVALID, "null scene");
+    if (s->device == WPT_DEVICE_NONE)
+        return fail(WPT_E_NO_DEVICE, "this scene was created without a device (WPT_DEVICE_NONE); "
+                "rendering needs a CUDA device, there is no CPU fallback");
+    if (!s->host.haveBvh)
+        return fail(WPT_E_STATE, "wpt_scene_update_bvh() must be called before rendering "
+                "(the reference asserts !scene.bvhNeedsUpdate(), wurblpt.hpp:289)");
+    WPT_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
+    return WPT_OK;
+}
+
+}
+
+extern "C" {
+
+const char* wpt_version(void)
+{
+    return "wurblpt_b200 0.1 (abi 1, sm_100a)";
+}
+
+const char* wpt_last_error(void)
+{
+    return g_lastError.c_str();
+}
+
+int wpt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+size_t wpt_abi_sizeof(int which)
+{
+    switch (which) {
+    case 0: return sizeof(wpt_keyframe);
+    case 1: return sizeof(wpt_animation);
+    case 2: return sizeof(wpt_texture);
+    case 3: return sizeof(wpt_material);
+    case 4: return sizeof(wpt_mesh);
+    case 5: return sizeof(wpt_instance);
+    case 6: return sizeof(wpt_sphere);
+    case 7: return sizeof(wpt_medium);
+    case 8: return sizeof(wpt_component);
+    case 9: return sizeof(wpt_envmap);
+    case 10: return sizeof(wpt_scene_desc);
+    case 11: return sizeof(wpt_camera_desc);
+    case 12: return sizeof(wpt_sensor_desc);
+    case 13: return sizeof(wpt_params);
+    case 14: return sizeof(wpt_render_opts);
+    case 15: return sizeof(wpt_stats);
+    case 16: return sizeof(wpt_scene_info);
+    }
+    return 0;
+}
+
+int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** out)
+{
+    if (!out)
+        return fail(WPT_E_INVALID, "null output pointer");
+    *out = nullptr;
+    std::unique_ptr<wpt_scene> s(new wpt_scene);
+    int rc = s->host.ingest(desc);
+    if (rc != WPT_OK)
+        return fail(rc, s->host.error);
+    if (device == WPT_DEVICE_NONE) {
+        /* host-only scene: bounds and tree can be built and inspected, nothing can be rendered */
+        s->device = WPT_DEVICE_NONE;
+        *out = s.release();
+        return WPT_OK;
+    }
+    rc = selectDevice(device);
+    if (rc != WPT_OK)
+        return rc;
+    s->device = device;
+    cudaDeviceProp prop;
+    WPT_CUDA(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major < 10)
+        return fail(WPT_E_NO_DEVICE, std::string("device '") + prop.name + "' is not a Blackwell (sm_100) GPU; "
+                "this library ships sm_100a code only");
+    s->numSMs = prop.multiProcessorCount;
+    s->sceneHasMedia = !s->host.media.empty();
+    for (const wpt_instance& in : s->host.instances)
+        s->sceneHasAnimation = s->sceneHasAnimation || in.animation >= 0;
+    for (const wpt_sphere& sp : s->host.spheres)
+        s->sceneHasAnimation = s->sceneHasAnimation || sp.animation >= 0;
+    if (s->sceneHasAnimation && s->host.animations.size() > size_t(wptd::MAX_CACHED_ANIMATIONS))
+        return fail(WPT_E_UNSUPPORTED, "more than " + std::to_string(wptd::MAX_CACHED_ANIMATIONS)
+                + " scene animations are not supported yet");
+    auto start = std::chrono::steady_clock::now();
+    rc = uploadStatic(s.get());
+    if (rc != WPT_OK)
+        return rc;
+    s->uploadSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    WPT_CUDA(cudaEventCreate(&s->evStart), "cudaEventCreate");
+    WPT_CUDA(cudaEventCreate(&s->evStop), "cudaEventCreate");
+    WPT_CUDA(s->counters.reserve(4 * sizeof(unsigned long long)), "allocate counters");
+    *out = s.release();
+    return WPT_OK;
+}
+
+int wpt_scene_update_bvh(wpt_scene* s, float t0, float t1)
+{
+    if (!s)
+        return fail(WPT_E_INVALID, "null scene");
+    if (s->device != WPT_DEVICE_NONE)
+        WPT_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
+    int rc = s->host.updateBvh(t0, t1);
+    if (rc != WPT_OK)
+        return fail(rc, s->host.error);
+    if (s->device == WPT_DEVICE_NONE)
+        return WPT_OK;
+    auto start = std::chrono::steady_clock::now();
+    const wpt::HostScene& h = s->host;
+    WPT_CUDA(s->node4.upload(h.nodes4.data(), h.nodes4.size() * sizeof(wpt::Node4)), "upload wide nodes");
+    WPT_CUDA(s->bnode.upload(h.bnodes.data(), h.bnodes.size() * sizeof(wpt::BNode)), "upload binary nodes");
+    WPT_CUDA(s->tri.upload(h.triData.data(), h.triData.size() * sizeof(float)), "upload triangles");
+    WPT_CUDA(s->sph.upload(h.sphData.data(), h.sphData.size() * sizeof(float)), "upload spheres");
+    WPT_CUDA(s->med.upload(h.medData.data(), h.medData.size() * sizeof(float)), "upload media");
+    WPT_CUDA(s->triGlobal.upload(h.triGlobal.data(), h.triGlobal.size() * sizeof(uint32_t)), "upload triangle ids");
+    WPT_CUDA(s->sphGlobal.upload(h.sphGlobal.data(), h.sphGlobal.size() * sizeof(uint32_t)), "upload sphere ids");
+    WPT_CUDA(s->medGlobal.upload(h.medGlobal.data(), h.medGlobal.size() * sizeof(uint32_t)), "upload medium ids");
+    WPT_CUDA(s->hotRefs.upload(h.hotSpotRefs.data(), h.hotSpotRefs.size() * sizeof(uint32_t)), "upload hot spots");
+    WPT_CUDA(cudaDeviceSynchronize(), "upload acceleration structure");
+    refreshDeviceScene(s);
+    s->uploadSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    return WPT_OK;
+}
+
+int wpt_scene_get_info(const wpt_scene* s, wpt_scene_info* info)
+{
+    if (!s || !info)
+        return fail(WPT_E_INVALID, "null argument");
+    std::memset(info, 0, sizeof(*info));
+    const wpt::HostScene& h = s->host;
+    info->hitables = h.topLevel.size();
+    info->triangles = h.triGlobal.size();
+    info->spheres = h.sphGlobal.size();
+    info->media = h.medGlobal.size();
+    info->binary_nodes = h.topLevelNodes;
+    info->wide_nodes = h.nodes4.size();
+    info->binary_depth = h.binaryDepth;
+    info->wide_depth = h.wideDepth;
+    info->hot_spots = uint32_t(h.hotSpotIds.size());
+    info->device_bytes = s->deviceBytes();
+    info->build_seconds = h.buildSeconds;
+    info->upload_seconds = s->uploadSeconds;
+    return WPT_OK;
+}
+
+void wpt_scene_destroy(wpt_scene* s)
+{
+    if (s) {
+        if (s->device != WPT_DEVICE_NONE)
+            cudaSetDevice(s->device);
+        delete s;
+    }
+}
+
+int wpt_scene_get_binary_nodes(const wpt_scene* s, uint64_t capacity, float* boxes, uint32_t* link, int32_t* leaf)
+{
+    if (!s || !boxes || !link || !leaf)
+        return fail(WPT_E_INVALID, "null argument");
+    const wpt::HostScene& h = s->host;
+    if (!h.haveBvh)
+        return fail(WPT_E_STATE, "wpt_scene_update_bvh() has not been called");
+    if (capacity < h.topLevelNodes)
+        return fail(WPT_E_INVALID, "capacity too small");
+    for (uint64_t i = 0; i < h.topLevelNodes; i++) {
+        const wpt::BNode& n = h.bnodes[i];
+        for (int k = 0; k < 3; k++) {
+            boxes[i * 6 + k] = n.lo[k];
+            boxes[i * 6 + 3 + k] = n.hi[k];
+        }
+        if (n.leaf == wpt::INNER) {
+            link[i] = n.link;
+            leaf[i] = -1;
+        } else {
+            const uint32_t type = n.leaf >> wpt::REF_TYPE_SHIFT, slot = n.leaf & wpt::REF_SLOT_MASK;
+            link[i] = 0;
+            leaf[i] = int32_t(type == wpt::PRIM_TRIANGLE ? h.triGlobal[slot]
+                    : type == wpt::PRIM_SPHERE ? h.sphGlobal[slot] : h.medGlobal[slot]);
+        }
+    }
+    return WPT_OK;
+}
+
+int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_desc* sensor,
+        const wpt_params* params, uint32_t samplesSqrt, float t0, float t1,
+        const wpt_render_opts* opts, float* frame, wpt_stats* stats)
+{
+    auto wallStart = std::chrono::steady_clock::now();
+    int rc = checkReady(s);
+    if (rc != WPT_OK)
+        return rc;
+    if (!camera || !sensor || !params || !frame)
+        return fail(WPT_E_INVALID, "null argument");
+    if (sensor->width == 0 || sensor->height == 0 || samplesSqrt == 0
+            || uint64_t(sensor->width) * sensor->height >= (1ull << 31))
+        return fail(WPT_E_INVALID, "invalid image size or sample count");
+    if (sensor->type != WPT_SENSOR_RGB && sensor->type != WPT_SENSOR_TOF_AMCW)
+        return fail(WPT_E_UNSUPPORTED, "unknown sensor type");
+    if (s->host.animations.size() > 0 && (s->host.bvhT0 > t0 || s->host.bvhT1 < t1))
+        return fail(WPT_E_STATE, "the acceleration structure does not cover [t0,t1]; call wpt_scene_update_bvh(t0,t1) "
+                "(Scene::bvhNeedsUpdate, scene.hpp:145-149)");
+    wpt_render_opts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts)
+        o = *opts;
+    cudaStream_t stream = static_cast<cudaStream_t>(o.stream);
+
+    wptd::RenderParams P;
+    std::memset(&P, 0, sizeof(P));
+    rc = fillCamera(s, camera, t0, sensor->width, sensor->height, P, stream);
+    if (rc != WPT_OK)
+        return rc;
+    P.sensorType = sensor->type;
+    P.minDistToLight = sensor->min_dist_to_light;
+    P.maxDistToLight = sensor->max_dist_to_light;
+    P.minPathLen = sensor->min_path_len;
+    P.maxPathLen = sensor->max_path_len;
+    bool needOpl = false;
+    if (sensor->type == WPT_SENSOR_TOF_AMCW) {
+        needOpl = true;
+        if (sensor->phase_count == 0)
+            return fail(WPT_E_INVALID, "ToF sensor needs phase_count > 0");
+        P.tofPixelArea = sensor->pixel_area;
+        P.tofExposureTime = sensor->exposure_time;
+        P.tofContrast = sensor->contrast;
+        /* tau(): phaseImageIndex * (2.0f * pi) / phaseImageCount (sensor_tof_amcw.hpp:102-105) */
+        P.tofTau = float(sensor->phase_index) * (2.0f * 3.14159274f) / float(sensor->phase_count);
+        /* fracModfreqC(): double division, then cast (sensor_tof_amcw.hpp:107-110) */
+        P.tofFracModfreqC = float(sensor->modulation_frequency / 299792458.0);
+    } else {
+        const float fmax = std::numeric_limits<float>::max();
+        needOpl = !(sensor->min_dist_to_light <= 0.0f && sensor->max_dist_to_light >= fmax
+                && sensor->min_path_len <= 0.0f && sensor->max_path_len >= fmax);
+    }
+    P.maxPathComponents = params->max_path_components;
+    P.rrThreshold = params->rr_threshold;
+    P.randomize = params->randomize_ray_over_pixel;
+    P.minHit = params->min_hit_distance;
+    P.samplesSqrt = samplesSqrt;
+    P.samples = samplesSqrt * samplesSqrt;
+    P.invSamples = 1.0f / float(P.samples);
+    P.invSamplesSqrt = 1.0f / float(samplesSqrt);
+    P.invWidth = 1.0f / float(sensor->width);
+    P.invHeight = 1.0f / float(sensor->height);
+    P.t0 = t0;
+    P.t1 = t1;
+    P.traversal = o.traversal;
+    if (o.traversal == WPT_TRAVERSAL_WIDE && !(P.minHit > 0.0f))
+        P.traversal = WPT_TRAVERSAL_REFERENCE;  /* the ordered walk needs a positive lower bound */
+    if (o.traversal == WPT_TRAVERSAL_WIDE && 3 * s->host.wideDepth + 1 > uint32_t(12 + 84))
+        P.traversal = WPT_TRAVERSAL_REFERENCE;  /* deeper than the wide walk's stack */
+
+    /* sub-streams per pixel: enough lanes to fill the GPU a few times over */
+    uint32_t sub = 1;
+    if (o.substreams > 0) {
+        if (o.substreams > 32 || (o.substreams & (o.substreams - 1)) != 0)
+            return fail(WPT_E_INVALID, "substreams must be a power of two <= 32");
+        sub = uint32_t(o.substreams);
+    } else {
+        const uint64_t pixels = uint64_t(sensor->width) * sensor->height;
+        const uint64_t wantLanes = uint64_t(s->numSMs) * 2048ull * 4ull;
+        while (sub < 32 && pixels * sub < wantLanes && sub * 2 <= P.samples)
+            sub *= 2;
+    }
+    while (sub > P.samples && sub > 1)
+        sub /= 2;
+    P.substreams = sub;
+    P.subShift = 0;
+    while ((1u << P.subShift) < sub)
+        P.subShift++;
+    const uint32_t pixelsPerTile = 32u / sub;
+    static const uint32_t tileWs[6] = { 8, 4, 4, 2, 2, 1 };     /* 32, 16, 8, 4, 2, 1 pixels per tile */
+    P.tileW = tileWs[P.subShift];
+    P.tileH = pixelsPerTile / P.tileW;
+    P.tilesX = (sensor->width + P.tileW - 1) / P.tileW;
+    const uint32_t tilesY = (sensor->height + P.tileH - 1) / P.tileH;
+    P.tilesTotal = P.tilesX * tilesY;
+    P.tileStride = (o.tile_stride == 0 ? 1 : o.tile_stride);
+    P.tileFirst = o.tile_first;
+    if (P.tileFirst >= P.tileStride)
+        return fail(WPT_E_INVALID, "tile_first must be smaller than tile_stride");
+    P.nLocalTiles = (P.tileFirst < P.tilesTotal ? (P.tilesTotal - P.tileFirst + P.tileStride - 1) / P.tileStride : 0);
+
+    const size_t frameBytes = size_t(sensor->width) * sensor->height * 3 * sizeof(float);
+    if (o.frame_on_device) {
+        P.frame = frame;
+    } else {
+        WPT_CUDA(s->frame.reserve(frameBytes), "allocate frame");
+        WPT_CUDA(cudaMemsetAsync(s->frame.p, 0, frameBytes, stream), "clear frame");
+        P.frame = static_cast<float*>(s->frame.p);
+    }
+    P.counters = static_cast<unsigned long long*>(s->counters.p);
+    WPT_CUDA(cudaMemsetAsync(s->counters.p, 0, 4 * sizeof(unsigned long long), stream), "clear counters");
+
+    const bool timed = (stats != nullptr) || !o.frame_on_device;
+    int grid = 0;
+    if (timed)
+        WPT_CUDA(cudaEventRecord(s->evStart, stream), "cudaEventRecord");
+    if (P.nLocalTiles > 0)
+        WPT_CUDA(wptd::launchRender(sceneFeatures(s, needOpl), s->d, P, s->numSMs, stream, &grid), "render kernel launch");
+    if (timed)
+        WPT_CUDA(cudaEventRecord(s->evStop, stream), "cudaEventRecord");
+    if (!o.frame_on_device)
+        WPT_CUDA(cudaMemcpyAsync(frame, s->frame.p, frameBytes, cudaMemcpyDeviceToHost, stream), "copy frame to host");
+    if (timed) {
+        unsigned long long c[4] = { 0, 0, 0, 0 };
+        WPT_CUDA(cudaMemcpyAsync(c, s->counters.p, sizeof(c), cudaMemcpyDeviceToHost, stream), "copy counters");
+        WPT_CUDA(cudaStreamSynchronize(stream), "render kernel");
+        if (stats) {
+            std::memset(stats, 0, sizeof(*stats));
+            stats->samples = c[1];
+            stats->rays = c[2];
+            stats->nested_queries = c[3];
+            stats->tiles = P.nLocalTiles;
+            cudaEventElapsedTime(&stats->kernel_ms, s->evStart, s->evStop);
+            stats->launches = (P.nLocalTiles > 0 ? 1 : 0);
+            stats->total_ms = float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wallStart).count());
+        }
+    }
+    return WPT_OK;
+}
+
+static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width, uint32_t height,
+        const float* origins, const float* directions, uint64_t nRays, float time, float minHit,
+        const wpt_render_opts* opts, int32_t* ids, float* a, uint64_t* counters)
+{
+    int rc = checkReady(s);
+    if (rc != WPT_OK)
+        return rc;
+    if (!ids || !a)
+        return fail(WPT_E_INVALID, "null output pointer");
+    wpt_render_opts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts)
+        o = *opts;
+    cudaStream_t stream = static_cast<cudaStream_t>(o.stream);
+    wptd::RenderParams P;
+    std::memset(&P, 0, sizeof(P));
+    if (camera) {
+        rc = fillCamera(s, camera, time, width, height, P, stream);
+        if (rc != WPT_OK)
+            return rc;
+        nRays = uint64_t(width) * height;
+    }
+    P.t0 = P.t1 = time;
+    P.minHit = minHit;
+    P.traversal = o.traversal;
+    if (o.traversal == WPT_TRAVERSAL_WIDE && (!(minHit > 0.0f) || 3 * s->host.wideDepth + 1 > uint32_t(12 + 84)))
+        P.traversal = WPT_TRAVERSAL_REFERENCE;
+    if (nRays == 0)
+        return WPT_OK;
+    const float* dO = nullptr;
+    const float* dD = nullptr;
+    if (!camera) {
+        if (!origins || !directions)
+            return fail(WPT_E_INVALID, "null ray arrays");
+        WPT_CUDA(s->qOrigins.upload(origins, nRays * 3 * sizeof(float), stream), "upload ray origins");
+        WPT_CUDA(s->qDirections.upload(directions, nRays * 3 * sizeof(float), stream), "upload ray directions");
+        dO = s->qOrigins.as<float>();
+        dD = s->qDirections.as<float>();
+    }
+    WPT_CUDA(s->qIds.reserve(nRays * sizeof(int32_t)), "allocate ids");
+    WPT_CUDA(s->qDist.reserve(nRays * sizeof(float)), "allocate distances");
+    wptd::TraceStats* dStats = nullptr;
+    if (counters) {
+        WPT_CUDA(s->qStats.reserve(sizeof(wptd::TraceStats)), "allocate stats");
+        WPT_CUDA(cudaMemsetAsync(s->qStats.p, 0, sizeof(wptd::TraceStats), stream), "clear stats");
+        dStats = static_cast<wptd::TraceStats*>(s->qStats.p);
+    }
+    WPT_CUDA(wptd::launchQuery(sceneFeatures(s, false), counters != nullptr, s->d, P, dO, dD, nRays, time,
+                static_cast<int32_t*>(s->qIds.p), static_cast<float*>(s->qDist.p), dStats, stream), "query kernel launch");
+    WPT_CUDA(cudaMemcpyAsync(ids, s->qIds.p, nRays * sizeof(int32_t), cudaMemcpyDeviceToHost, stream), "copy ids");
+    WPT_CUDA(cudaMemcpyAsync(a, s->qDist.p, nRays * sizeof(float), cudaMemcpyDeviceToHost, stream), "copy distances");
+    wptd::TraceStats hs = { 0, 0, 0 };
+    if (counters)
+        WPT_CUDA(cudaMemcpyAsync(&hs, s->qStats.p, sizeof(hs), cudaMemcpyDeviceToHost, stream), "copy stats");
+    WPT_CUDA(cudaStreamSynchronize(stream), "query kernel");
+    if (counters) {
+        counters[0] = hs.nodes;
+        counters[1] = hs.leaves;
+        counters[2] = hs.nested;
+    }
+    return WPT_OK;
+}
+
+int wpt_primary_hits(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width, uint32_t height,
+        float t, float minHitDistance, const wpt_render_opts* opts, int32_t* ids, float* a, uint64_t* counters)
+{
+    if (!camera || width == 0 || height == 0)
+        return fail(WPT_E_INVALID, "invalid camera or image size");
+    return runQuery(s, camera, width, height, nullptr, nullptr, 0, t, minHitDistance, opts, ids, a, counters);
+}
+
+int wpt_trace_rays(wpt_scene* s, const float* origins, const float* directions, uint64_t nRays,
+        float time, float minHitDistance, const wpt_render_opts* opts, int32_t* ids, float* a, uint64_t* counters)
+{
+    return runQuery(s, nullptr, 0, 0, origins, directions, nRays, time, minHitDistance, opts, ids, a, counters);
+}
+
+int wpt_prng_kat(const uint32_t* seeds, uint32_t nSeeds, uint32_t nDraws, float* out)
+{
+    int rc = selectDevice(0);
+    if (rc != WPT_OK)
+        return rc;
+    if (!seeds || !out)
+        return fail(WPT_E_INVALID, "null argument");
+    DeviceBuf dSeeds, dOut;
+    WPT_CUDA(dSeeds.upload(seeds, size_t(nSeeds) * sizeof(uint32_t)), "upload seeds");
+    WPT_CUDA(dOut.reserve(size_t(nSeeds) * nDraws * sizeof(float)), "allocate output");
+    WPT_CUDA(wptd::launchPrng(dSeeds.as<uint32_t>(), nSeeds, nDraws, static_cast<float*>(dOut.p), 0), "prng kernel launch");
+    WPT_CUDA(cudaMemcpy(out, dOut.p, size_t(nSeeds) * nDraws * sizeof(float), cudaMemcpyDeviceToHost), "copy prng output");
+    return WPT_OK;
+}
+
+}

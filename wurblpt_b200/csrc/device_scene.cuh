@@ -1,0 +1,118 @@
+/*
+ * device_scene.cuh -- layout of the scene in HBM and of the per-launch parameter blocks.
+ *
+ * Everything a kernel needs is reachable from two small structs passed by value as
+ * __grid_constant__ kernel parameters (constant bank, no global load to find a pointer):
+ *   DScene        pointers to the device-resident scene arrays
+ *   RenderParams  camera, sensor, Parameters, tiling and output of one mcpt() call
+ *
+ * Arrays (all cudaMalloc'd, 256-byte aligned; 16-byte elements are read with 128-bit loads):
+ *   node4     Node4[ ]         128 B per node: six float4 of child slabs, int4 children, pad
+ *   bnode     float4[2*n]      the reference-layout binary tree (32 B per node), top level at 0,
+ *                              nested medium-boundary trees behind it
+ *   tri       float4[3*slots]  world-space corners; .w of the three = instance, triangle number,
+ *                              animation index + 1 (0 = static)
+ *   sph       float4[3*slots]  (centre, radius) (rotation quaternion) (material, animation+1, -, -)
+ *   med       float4[slots]    (density, material, nested root, -)
+ *   *Global   uint32[slots]    slot -> global hitable id (for reporting)
+ *   materials wpt_material[ ]  128 B each, the C-ABI struct as is
+ *   instances wpt_instance[ ]  128 B each
+ *   meshes    wpt_mesh[ ]
+ *   vertices  float[ ], indices uint32[ ]   interleaved vertex data for shading normals / uv / tangents
+ *   textures  DTexture[ ], texels float4[ ] image textures decoded to RGBA float once at upload
+ *   envM / envMs / envMcs      importance tables of the environment map
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "wurblpt_b200.h"
+
+namespace wptd {
+
+struct DTexture {
+    int32_t type;
+    int32_t src;
+    int32_t width, height;
+    int32_t horiz, vert;
+    uint32_t texelBase;         /* index into DScene::texels */
+    int32_t pad;
+    float4 color0, color1;
+    float2 coordFactor, coordOffset;
+    float4 valFactor, valOffset;
+};
+
+struct DScene {
+    const float4* node4;
+    const float4* bnode;
+    const float4* tri;
+    const float4* sph;
+    const float4* med;
+    const uint32_t* triGlobal;
+    const uint32_t* sphGlobal;
+    const uint32_t* medGlobal;
+    const uint32_t* hotRefs;
+    const wpt_material* materials;
+    const wpt_instance* instances;
+    const wpt_mesh* meshes;
+    const float* vertices;
+    const uint32_t* indices;
+    const DTexture* textures;
+    const float4* texels;
+    const wpt_animation* animations;
+    const wpt_keyframe* keyframes;
+    const float* envM;
+    const int32_t* envMs;
+    const float* envMcs;
+    int32_t root4;              /* encoded child of the 4-wide tree */
+    uint32_t nHot;
+    uint32_t nAnimations;
+    int32_t envType, envCompat, envN;
+    int32_t envTex[6];
+};
+
+constexpr int MAX_CACHED_ANIMATIONS = 4;    /* per-thread animation cache entries (AnimationCache) */
+
+struct RenderParams {
+    /* camera (camera.hpp:42-107, optics.hpp) */
+    int32_t surround;
+    float stereo;
+    float l, r, b, t;
+    int32_t distortionType;
+    float k1, k2, k3, p1, p2, b1, b2, b3, b4;
+    float lensRadius, focusDist;
+    float3 camT; float4 camR; float3 camS;      /* camera pose at t0 (RayHelper::cameraAtT0) */
+    const wpt_keyframe* camKeys;
+    uint32_t nCamKeys;
+    float2 distCenter, distFocal, distInvFocal; /* LensDistortion::Helper */
+    /* sensor */
+    int32_t sensorType;
+    uint32_t width, height;
+    float minDistToLight, maxDistToLight, minPathLen, maxPathLen;
+    float tofPixelArea, tofExposureTime, tofContrast, tofTau, tofFracModfreqC;
+    /* Parameters */
+    uint32_t maxPathComponents;
+    float rrThreshold;
+    int32_t randomize;
+    float minHit;
+    /* sampling */
+    uint32_t samplesSqrt, samples;
+    float invSamples, invSamplesSqrt, invWidth, invHeight;
+    float t0, t1;
+    /* tiling */
+    uint32_t substreams, subShift;
+    uint32_t tileW, tileH, tilesX, tilesTotal;
+    uint32_t tileFirst, tileStride, nLocalTiles;
+    /* output */
+    float* frame;
+    unsigned long long* counters;   /* [0] tile ticket, [1] samples, [2] rays, [3] nested queries */
+    int32_t traversal;
+};
+
+/* counters for the ray-query kernels */
+struct TraceStats {
+    unsigned long long nodes, leaves, nested;
+};
+
+}

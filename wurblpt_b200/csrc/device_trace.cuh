@@ -1,0 +1,531 @@
+/*
+ * device_trace.cuh -- closest-hit queries on the device: ray/box, ray/triangle, ray/sphere,
+ * medium free-flight sampling, and the two tree walks.
+ *
+ *   traverseReference  the reference's walk (bvh.hpp:277-311): binary tree in storage order,
+ *                      child 1 before child 2, no near/far ordering, last-accepted-wins.
+ *                      Same tests in the same order => same answer as the reference, ties
+ *                      included. Used for parity runs and for the nested medium boundaries.
+ *   traverseWide       the production walk: 4-wide nodes (one 128-byte line, eight 128-bit
+ *                      loads), children visited near to far, stack in shared memory with a
+ *                      local-memory spill. Exact distance ties between triangles are settled
+ *                      by slot number, which the host assigned in the reference's visiting
+ *                      order, so the reference's winner is reproduced.
+ *
+ * Roofline bound of both: node/primitive fetch bandwidth (L1/L2 for small scenes, HBM when
+ * the tree exceeds the 126 MB L2). Algorithmic bytes per query as defined by SURVEY.md 8(d):
+ * 32 B per reference node visit + 68 B per reference leaf test.
+ */
+#pragma once
+
+#include "device_math.cuh"
+#include "device_scene.cuh"
+
+namespace wptd {
+
+constexpr uint32_t NO_HIT = 0xFFFFFFFFu;
+constexpr uint32_t REF_TYPE_SHIFT = 29;
+constexpr uint32_t REF_SLOT_MASK = (1u << REF_TYPE_SHIFT) - 1u;
+constexpr uint32_t PRIM_TRIANGLE = 0, PRIM_SPHERE = 1, PRIM_MEDIUM = 2;
+constexpr int32_t EMPTY_CHILD = 0x7FFFFFFF;
+constexpr uint32_t NO_NODE = 0xFFFFFFFFu;
+
+constexpr int F_MEDIA = 1;      /* scene contains media (nested walks, PRNG draws inside the walk) */
+constexpr int F_ANIM = 2;       /* scene contains animated hitables */
+constexpr int F_OPL = 4;        /* track optical path length / refractive index (ToF sensor, gated RGB) */
+constexpr int F_COUNT = 8;      /* count node visits and leaf tests (query kernels only) */
+
+constexpr int SM_STACK = 12;    /* shared-memory stack entries per thread */
+constexpr int LOCAL_STACK = 84; /* spill entries per thread (local memory, touched only when deep) */
+constexpr int BINARY_STACK = 128;   /* BVH::maxTreeDepth, bvh.hpp:230 */
+
+struct Ray {
+    float3 o, d;
+    float time;
+};
+
+/* RayIntersectionHelper (hitable.hpp:66-113) */
+struct RayHelper {
+    float3 inv;
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+};
+
+WPT_DEV RayHelper makeRayHelper(const Ray& ray)
+{
+    RayHelper h;
+    h.inv = 1.0f / ray.d;
+    float ax = fabsf(ray.d.x), ay = fabsf(ray.d.y), az = fabsf(ray.d.z);
+    if (az >= ay && az >= ax)
+        h.kz = 2;
+    else if (ay >= ax)
+        h.kz = 1;
+    else
+        h.kz = 0;
+    h.kx = h.kz + 1;
+    if (h.kx == 3)
+        h.kx = 0;
+    h.ky = h.kx + 1;
+    if (h.ky == 3)
+        h.ky = 0;
+    if (sel(ray.d, h.kz) < 0.0f) {
+        int tmp = h.kx;
+        h.kx = h.ky;
+        h.ky = tmp;
+    }
+    h.Sx = sel(ray.d, h.kx) * sel(h.inv, h.kz);
+    h.Sy = sel(ray.d, h.ky) * sel(h.inv, h.kz);
+    h.Sz = sel(h.inv, h.kz);
+    return h;
+}
+
+struct Hit {
+    float a;
+    uint32_t ref;
+};
+
+/* Per-thread state that a walk may touch: the pixel's Prng (media draw inside the walk,
+ * hitable_medium.hpp:89) and the animation cache (animation.hpp:52-125). */
+template<int F>
+struct Ctx {
+    Prng prng;
+    unsigned int nested;
+    unsigned int nodes, leaves;
+    Trs animT[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
+    Mat34 animM[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
+    Mat33 animN[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
+};
+
+/* AnimationKeyframes::at (animation_keyframes.hpp:191-215) */
+WPT_DEV Trs keyframeTrs(const wpt_keyframe& k)
+{
+    Trs T;
+    T.t = f3(k.translation[0], k.translation[1], k.translation[2]);
+    T.r = f4(k.rotation[0], k.rotation[1], k.rotation[2], k.rotation[3]);
+    T.s = f3(k.scaling[0], k.scaling[1], k.scaling[2]);
+    return T;
+}
+
+__device__ __noinline__ Trs keyframesAt(const wpt_keyframe* kf, uint32_t count, float t)
+{
+    if (count == 0) {
+        Trs T;
+        T.t = f3(0.0f);
+        T.r = f4(0.0f, 0.0f, 0.0f, 1.0f);
+        T.s = f3(1.0f);
+        return T;
+    }
+    if (t <= kf[0].t)
+        return keyframeTrs(kf[0]);
+    if (t >= kf[count - 1].t)
+        return keyframeTrs(kf[count - 1]);
+    int a = 0, b = int(count) - 1;
+    int lower = -1, higher = -1;
+    while (b >= a) {
+        int c = (a + b) / 2;
+        float tc = kf[c].t;
+        if (tc < t) {
+            a = c + 1;
+        } else if (tc > t) {
+            b = c - 1;
+        } else {
+            lower = higher = c;
+            break;
+        }
+    }
+    if (lower < 0) {
+        lower = b;
+        higher = a;
+    }
+    if (lower == higher)
+        return keyframeTrs(kf[lower]);
+    float alpha = 1.0f - (kf[higher].t - t) / (kf[higher].t - kf[lower].t);
+    return trsMix(keyframeTrs(kf[lower]), keyframeTrs(kf[higher]), alpha);
+}
+
+/* AnimationCache::init(t) followed by the lazy per-index evaluation (animation.hpp:62-70,96-101);
+ * evaluated eagerly here for the (few) animations of the scene. */
+template<int F>
+WPT_DEV void animationCacheInit(const DScene& S, Ctx<F>& ctx, float t)
+{
+    if (F & F_ANIM) {
+        for (uint32_t i = 0; i < S.nAnimations && i < uint32_t(MAX_CACHED_ANIMATIONS); i++) {
+            const wpt_animation an = S.animations[i];
+            Trs T = keyframesAt(S.keyframes + an.first_keyframe, an.keyframe_count, t);
+            Mat33 N = toMat33(T.r);
+            ctx.animT[i] = T;
+            ctx.animN[i] = N;
+            ctx.animM[i] = toMat34(T, N);
+        }
+    }
+}
+
+/* ------------------------------------------------------------ ray / triangle */
+
+/* Corners of the triangle in slot `slot`, animated to the current cache time. */
+template<int F>
+WPT_DEV void triangleCorners(const DScene& S, uint32_t slot, const Ctx<F>& ctx,
+        float3& v0, float3& v1, float3& v2, uint32_t& instance, uint32_t& triIndex, uint32_t& anim)
+{
+    const float4* p = S.tri + size_t(slot) * 3;
+    const float4 a = __ldg(p + 0), b = __ldg(p + 1), c = __ldg(p + 2);
+    v0 = xyz(a); v1 = xyz(b); v2 = xyz(c);
+    instance = __float_as_uint(a.w);
+    triIndex = __float_as_uint(b.w);
+    anim = __float_as_uint(c.w);
+    if (F & F_ANIM) {
+        if (anim != 0) {
+            const float* M = ctx.animM[anim - 1].m;
+            v0 = transformPoint(M, 3, v0);
+            v1 = transformPoint(M, 3, v1);
+            v2 = transformPoint(M, 3, v2);
+        }
+    }
+}
+
+/* Woop/Benthin/Wald watertight test as the reference runs it (hitable_triangle.hpp:189-271).
+ * Returns false on a miss; on a hit `a` is the distance, (U,V,W)/det the barycentrics. */
+WPT_DEV bool triangleTest(float3 v0, float3 v1, float3 v2, const Ray& ray, const RayHelper& h,
+        float amin, float amax, bool bounded, float& a, float& U, float& V, float& W, float& det)
+{
+    const float3 A = v0 - ray.o;
+    const float3 B = v1 - ray.o;
+    const float3 C = v2 - ray.o;
+    const float Akz = sel(A, h.kz), Bkz = sel(B, h.kz), Ckz = sel(C, h.kz);
+    const float Ax = sel(A, h.kx) - h.Sx * Akz;
+    const float Ay = sel(A, h.ky) - h.Sy * Akz;
+    const float Bx = sel(B, h.kx) - h.Sx * Bkz;
+    const float By = sel(B, h.ky) - h.Sy * Bkz;
+    const float Cx = sel(C, h.kx) - h.Sx * Ckz;
+    const float Cy = sel(C, h.ky) - h.Sy * Ckz;
+    U = Cx * By - Cy * Bx;
+    V = Ax * Cy - Ay * Cx;
+    W = Bx * Ay - By * Ax;
+    if (fabsf(U) < LDBL_EPS_F || fabsf(V) < LDBL_EPS_F || fabsf(W) < LDBL_EPS_F) {
+        /* FP64 edge fallback (hitable_triangle.hpp:240-250); __dmul_rn/__dsub_rn keep the
+         * products and the difference un-contracted like the strict host build */
+        U = float(__dsub_rn(__dmul_rn(double(Cx), double(By)), __dmul_rn(double(Cy), double(Bx))));
+        V = float(__dsub_rn(__dmul_rn(double(Ax), double(Cy)), __dmul_rn(double(Ay), double(Cx))));
+        W = float(__dsub_rn(__dmul_rn(double(Bx), double(Ay)), __dmul_rn(double(By), double(Ax))));
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f))
+        return false;
+    det = U + V + W;
+    if (det == 0.0f)
+        return false;
+    const float Az = h.Sz * Akz;
+    const float Bz = h.Sz * Bkz;
+    const float Cz = h.Sz * Ckz;
+    const float T = U * Az + V * Bz + W * Cz;
+    if (bounded) {
+        const uint32_t detSign = __float_as_uint(det) & 0x80000000u;
+        const float Ts = __uint_as_float(__float_as_uint(T) ^ detSign);
+        const float ds = __uint_as_float(__float_as_uint(det) ^ detSign);
+        if (Ts < amin * ds || Ts > amax * ds)
+            return false;
+    }
+    const float invDet = 1.0f / det;
+    a = invDet * T;
+    return true;
+}
+
+/* ------------------------------------------------------------- ray / sphere */
+
+struct SphereGeom {
+    float3 center;
+    float radius;
+    float4 rotation;
+    uint32_t material;
+};
+
+/* HitableSphere::hit prologue (hitable_sphere.hpp:114-126) */
+template<int F>
+WPT_DEV SphereGeom sphereGeom(const DScene& S, uint32_t slot, const Ctx<F>& ctx)
+{
+    const float4* p = S.sph + size_t(slot) * 3;
+    const float4 a = __ldg(p + 0), b = __ldg(p + 1), c = __ldg(p + 2);
+    SphereGeom g;
+    g.center = xyz(a);
+    g.radius = a.w;
+    g.rotation = b;
+    g.material = __float_as_uint(c.x);
+    if (F & F_ANIM) {
+        uint32_t anim = __float_as_uint(c.y);
+        if (anim != 0) {
+            const Trs& T = ctx.animT[anim - 1];
+            g.center = g.center + T.t;
+            g.radius = g.radius * rmax(rmax(T.s.x, T.s.y), T.s.z);
+            g.rotation = qmul(g.rotation, T.r);
+        }
+    }
+    return g;
+}
+
+/* HitableSphere::hit (hitable_sphere.hpp:128-152): distance only */
+WPT_DEV bool sphereTest(float3 center, float radius, const Ray& ray, float amin, float amax, float& a)
+{
+    const float3 oc = ray.o - center;
+    const float ocd = dot(oc, ray.d);
+    const float aq = -ocd;
+    const float3 tmp = oc - ocd * ray.d;
+    const float discriminant = radius * radius - dot(tmp, tmp);
+    if (discriminant > 0.0f) {
+        float a1, a2;
+        if (aq < 0.0f) {
+            a2 = aq - sqrtf(discriminant);
+            a1 = 2.0f * aq - a2;
+        } else {
+            a1 = aq + sqrtf(discriminant);
+            a2 = 2.0f * aq - a1;
+        }
+        if (a2 > amin && a2 < amax) {
+            a = a2;
+            return true;
+        } else if (a1 > amin && a1 < amax) {
+            a = a1;
+            return true;
+        }
+    }
+    return false;
+}
+
+/* ------------------------------------------------------------ ray / box */
+
+/* AABB::mayHit (aabb.hpp:70-86) with gvm's select-based min/max and reductions */
+WPT_DEV bool boxTestReference(float3 lo, float3 hi, const Ray& ray, float3 inv, float amin, float amax)
+{
+    const float3 t0 = (lo - ray.o) * inv;
+    const float3 t1 = (hi - ray.o) * inv;
+    const float3 mn = vmin(t0, t1);
+    const float3 mx = vmax(t0, t1);
+    float tmin = amin;
+    if (mn.x > tmin) tmin = mn.x;
+    if (mn.y > tmin) tmin = mn.y;
+    if (mn.z > tmin) tmin = mn.z;
+    float tmax = amax;
+    if (mx.x < tmax) tmax = mx.x;
+    if (mx.y < tmax) tmax = mx.y;
+    if (mx.z < tmax) tmax = mx.z;
+    return tmin <= tmax;
+}
+
+/* ------------------------------------------------- reference-order tree walk */
+
+template<int F, bool TOP>
+__device__ Hit traverseReference(const DScene& S, uint32_t root, const Ray& ray, const RayHelper& h,
+        float amin, float amax, float minHit, Ctx<F>& ctx);
+
+/* HitableMedium::hit (hitable_medium.hpp:69-98) */
+template<int F>
+WPT_DEV bool mediumTest(const DScene& S, uint32_t slot, const Ray& ray, const RayHelper& h,
+        float amin, float amax, float minHit, Ctx<F>& ctx, float& a)
+{
+    const float4 m = __ldg(S.med + slot);
+    const uint32_t root = __float_as_uint(m.z);
+    if (root == NO_NODE)
+        return false;
+    ctx.nested++;
+    Hit hr1 = traverseReference<F, false>(S, root, ray, h, -MAXVAL, MAXVAL, minHit, ctx);
+    if (hr1.ref == NO_HIT)
+        return false;
+    ctx.nested++;
+    Hit hr2 = traverseReference<F, false>(S, root, ray, h, hr1.a + minHit, MAXVAL, minHit, ctx);
+    if (hr2.ref == NO_HIT)
+        return false;
+    float a1 = hr1.a, a2 = hr2.a;
+    if (a1 < amin)
+        a1 = amin;
+    if (a2 > amax)
+        a2 = amax;
+    if (a1 < a2) {
+        if (a1 < 0.0f)
+            a1 = 0.0f;
+        const float inside = a2 - a1;
+        const float freeFlight = -(1.0f / m.x) * logf(in01(ctx.prng));
+        if (freeFlight < inside) {
+            a = a1 + freeFlight;
+            return true;
+        }
+    }
+    return false;
+}
+
+/* One leaf of either walk. Returns true if the hitable reports a hit under (amin, amax). */
+template<int F, bool TOP>
+WPT_DEV bool leafTest(const DScene& S, uint32_t ref, const Ray& ray, const RayHelper& h,
+        float amin, float amax, float minHit, Ctx<F>& ctx, float& a)
+{
+    const uint32_t type = ref >> REF_TYPE_SHIFT;
+    const uint32_t slot = ref & REF_SLOT_MASK;
+    if (F & F_COUNT)
+        ctx.leaves++;
+    if (type == PRIM_TRIANGLE) {
+        float3 v0, v1, v2;
+        uint32_t inst, tri, anim;
+        triangleCorners<F>(S, slot, ctx, v0, v1, v2, inst, tri, anim);
+        float U, V, W, det;
+        return triangleTest(v0, v1, v2, ray, h, amin, amax, true, a, U, V, W, det);
+    } else if (type == PRIM_SPHERE) {
+        SphereGeom g = sphereGeom<F>(S, slot, ctx);
+        return sphereTest(g.center, g.radius, ray, amin, amax, a);
+    } else if (TOP && (F & F_MEDIA)) {
+        return mediumTest<F>(S, slot, ray, h, amin, amax, minHit, ctx, a);
+    }
+    return false;
+}
+
+/* BVH::hit (bvh.hpp:277-311). The 32-byte node is two 128-bit loads:
+ *   (lo.x lo.y lo.z hi.x) (hi.y hi.z link leaf) */
+template<int F, bool TOP>
+__device__ Hit traverseReference(const DScene& S, uint32_t root, const Ray& ray, const RayHelper& h,
+        float amin, float amax, float minHit, Ctx<F>& ctx)
+{
+    Hit best;
+    best.a = amax;
+    best.ref = NO_HIT;
+    uint32_t stack[BINARY_STACK];
+    int sp = 0;
+    uint32_t node = root;
+    for (;;) {
+        const float4 n0 = __ldg(S.bnode + size_t(node) * 2);
+        const float4 n1 = __ldg(S.bnode + size_t(node) * 2 + 1);
+        if (F & F_COUNT)
+            ctx.nodes++;
+        if (boxTestReference(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), ray, h.inv, amin, best.a)) {
+            const uint32_t leaf = __float_as_uint(n1.w);
+            if (leaf != 0xFFFFFFFFu) {
+                float a;
+                if (leafTest<F, TOP>(S, leaf, ray, h, amin, best.a, minHit, ctx, a)) {
+                    best.a = a;
+                    best.ref = leaf;
+                }
+                if (sp == 0)
+                    break;
+                node = stack[--sp];
+            } else {
+                stack[sp++] = __float_as_uint(n1.z);
+                node++;
+            }
+        } else {
+            if (sp == 0)
+                break;
+            node = stack[--sp];
+        }
+    }
+    return best;
+}
+
+/* ------------------------------------------------------------ 4-wide walk */
+
+struct WideStack {
+    uint2* sm;              /* this thread's column of the shared-memory stack, stride = blockDim.x */
+    int stride;
+    uint2 spill[LOCAL_STACK];
+    int sp;
+
+    WPT_DEV void push(uint32_t code, float tmin)
+    {
+        uint2 e = make_uint2(code, __float_as_uint(tmin));
+        if (sp < SM_STACK)
+            sm[sp * stride] = e;
+        else
+            spill[sp - SM_STACK] = e;
+        sp++;
+    }
+    WPT_DEV uint2 pop()
+    {
+        --sp;
+        return sp < SM_STACK ? sm[sp * stride] : spill[sp - SM_STACK];
+    }
+};
+
+WPT_DEV void sort2(uint32_t& a, uint32_t& b)
+{
+    uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo;
+    b = hi;
+}
+
+/* Slab test of one child with hardware min/max. NaNs (ray parallel to and inside a slab plane)
+ * drop out of fminf/fmaxf, which only ever widens the interval: conservative. */
+WPT_DEV uint32_t childKey(float lox, float hix, float loy, float hiy, float loz, float hiz,
+        float3 o, float3 inv, float amin, float amax, uint32_t k)
+{
+    const float t0x = (lox - o.x) * inv.x, t1x = (hix - o.x) * inv.x;
+    const float t0y = (loy - o.y) * inv.y, t1y = (hiy - o.y) * inv.y;
+    const float t0z = (loz - o.z) * inv.z, t1z = (hiz - o.z) * inv.z;
+    const float tmin = fmaxf(fmaxf(fmaxf(amin, fminf(t0x, t1x)), fminf(t0y, t1y)), fminf(t0z, t1z));
+    const float tmax = fminf(fminf(fminf(amax, fmaxf(t0x, t1x)), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    return tmin <= tmax ? ((__float_as_uint(tmin) & ~3u) | k) : 0xFFFFFFFFu;
+}
+
+/* Closest hit under (amin, amax), amin > 0. */
+template<int F>
+__device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
+        float amin, float amax, float minHit, Ctx<F>& ctx, uint2* smStack, int smStride)
+{
+    Hit best;
+    best.a = amax;
+    best.ref = NO_HIT;
+    WideStack st;
+    st.sm = smStack;
+    st.stride = smStride;
+    st.sp = 0;
+    int32_t cur = S.root4;
+    if (cur == EMPTY_CHILD)
+        return best;
+    for (;;) {
+        if (cur >= 0) {
+            const float4* n = S.node4 + size_t(cur) * 8;
+            const float4 lox = __ldg(n + 0), hix = __ldg(n + 1);
+            const float4 loy = __ldg(n + 2), hiy = __ldg(n + 3);
+            const float4 loz = __ldg(n + 4), hiz = __ldg(n + 5);
+            const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
+            if (F & F_COUNT)
+                ctx.nodes++;
+            uint32_t k0 = childKey(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ray.o, h.inv, amin, best.a, 0);
+            uint32_t k1 = childKey(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ray.o, h.inv, amin, best.a, 1);
+            uint32_t k2 = childKey(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ray.o, h.inv, amin, best.a, 2);
+            uint32_t k3 = childKey(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ray.o, h.inv, amin, best.a, 3);
+            /* 5-comparator sorting network, ascending: nearest entry distance first */
+            sort2(k0, k1); sort2(k2, k3); sort2(k0, k2); sort2(k1, k3); sort2(k1, k2);
+            if (k0 != 0xFFFFFFFFu) {
+                /* far children go on the stack farthest first, the nearest is visited next */
+                if (k3 != 0xFFFFFFFFu)
+                    st.push(uint32_t(sel4i(ch, k3 & 3u)), __uint_as_float(k3 & ~3u));
+                if (k2 != 0xFFFFFFFFu)
+                    st.push(uint32_t(sel4i(ch, k2 & 3u)), __uint_as_float(k2 & ~3u));
+                if (k1 != 0xFFFFFFFFu)
+                    st.push(uint32_t(sel4i(ch, k1 & 3u)), __uint_as_float(k1 & ~3u));
+                cur = sel4i(ch, k0 & 3u);
+                continue;
+            }
+        } else {
+            const uint32_t ref = uint32_t(~cur);
+            float a;
+            if (leafTest<F, true>(S, ref, ray, h, amin, best.a, minHit, ctx, a)) {
+                /* Exact tie between two triangles: the reference keeps the one it visits last,
+                 * i.e. the higher slot (slots follow the reference's storage order). */
+                const bool tieLoses = (a == best.a) && (best.ref != NO_HIT)
+                    && ((best.ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE) && ((ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE)
+                    && (ref < best.ref);
+                if (!tieLoses) {
+                    best.a = a;
+                    best.ref = ref;
+                }
+            }
+        }
+        /* pop the next entry that can still contain a hit at or before the current best */
+        for (;;) {
+            if (st.sp == 0)
+                return best;
+            const uint2 e = st.pop();
+            if (__uint_as_float(e.y) <= best.a) {
+                cur = int32_t(e.x);
+                break;
+            }
+        }
+    }
+}
+
+}

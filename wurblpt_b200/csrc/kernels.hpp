@@ -1,0 +1,21 @@
+/* kernels.hpp -- host-callable launchers of kernels.cu */
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "device_scene.cuh"
+
+namespace wptd {
+
+/* features: 0 = static scene, RGB sensor with open gates; anything else selects the full variant
+ * (media, animations, optical path length tracking). */
+cudaError_t launchRender(int features, const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream, int* grid);
+
+/* origins == nullptr: pixel-centre camera rays of P (width*height rays). */
+cudaError_t launchQuery(int features, bool count, const DScene& S, const RenderParams& P,
+        const float* origins, const float* directions, unsigned long long nRays, float time,
+        int32_t* ids, float* dist, TraceStats* stats, cudaStream_t stream);
+
+cudaError_t launchPrng(const uint32_t* seeds, uint32_t nSeeds, uint32_t nDraws, float* out, cudaStream_t stream);
+
+}
