@@ -18,6 +18,6 @@ sed -e 's|^#pragma once|#pragma once\n#include "ref_counters.hpp"|' \
     -e 's|^\( *\)HitRecord currentHr = node.hitable->hit(|\1WPT_REF_COUNT(leaves);\n&|' \
     "$REF/libwurblpt/bvh.hpp" > "$OUT/bvh.hpp"
 sed -e 's|^#pragma once|#pragma once\n#include "ref_counters.hpp"|' \
-    -e 's|^\( *\)HitRecord \(hr\|directHR\|lightHR\) = scene.bvh().hit(|\1WPT_REF_COUNT(rays);\n&|' \
+    -e 's#^\( *\)HitRecord \(hr\|directHR\|lightHR\) = scene.bvh().hit(#\1WPT_REF_COUNT(rays);\n&#' \
     "$REF/libwurblpt/wurblpt.hpp" > "$OUT/wurblpt.hpp"
 grep -c WPT_REF_COUNT "$OUT/bvh.hpp" "$OUT/wurblpt.hpp"

@@ -255,7 +255,7 @@ inline void buildSynth(Scene& scene, float scale = 1.0f, int envWidth = 2048, in
             if (i < 9) {
                 Transformation arch(vec3(x, 3.5f, z + 1.0f),
                         toQuat(radians(90.0f), vec3(0.0f, 1.0f, 0.0f)), vec3(1.0f, 1.0f, 0.35f));
-                scene.take(new MeshInstance(scene.take(generateTorus(arch, 0.72f, tess(92), tess(92))), ggx()));
+                scene.take(new MeshInstance(scene.take(generateTorus(arch, 0.72f, tess(90), tess(90))), ggx()));
             }
         }
     }

@@ -1,0 +1,53 @@
+"""CPU tests of Scene::updateBVH's host side: the SAH tree must be the reference's tree, node for
+node and bit for bit (bvh.hpp:93-246), against committed fixtures and against the live reference."""
+import numpy as np
+import pytest
+
+from util import Golden, GOLDEN_SCENES
+
+
+@pytest.mark.parametrize("name", GOLDEN_SCENES)
+def test_tree_equals_golden_reference_tree(capi, name):
+    g = Golden(name)
+    s = capi.Scene(g.desc, device=-1).update_bvh(g.t0, g.t1)
+    boxes, link, leaf = s.binary_nodes()
+    assert np.array_equal(link, g.z["bvh_link"])
+    assert np.array_equal(leaf, g.z["bvh_leaf"])
+    assert np.array_equal(boxes.view(np.uint32), g.z["bvh_boxes"].view(np.uint32))
+    info = s.info()
+    assert info.binary_nodes == len(link)
+    assert info.wide_nodes <= max(1, info.binary_nodes // 2 + 1)
+    assert info.wide_depth <= info.binary_depth
+
+
+@pytest.mark.parametrize("name,scale,times", [
+    ("tof", 1.0, (1.0, 1.25)), ("tof", 1.0, (2.4, 2.6)), ("synth", 0.05, (0.0, 0.0)), ("rtiow", 1.0, (0.0, 0.0))])
+def test_tree_equals_live_reference_tree(capi, ref, name, scale, times):
+    r = ref.RefScene(name, scale, 0)
+    r.update_bvh(*times)
+    rb = ref.bvh_nodes(r)
+    s = capi.Scene(r.desc, device=-1).update_bvh(*times)
+    mb = s.binary_nodes()
+    assert np.array_equal(rb[1], mb[1]) and np.array_equal(rb[2], mb[2])
+    assert np.array_equal(rb[0].view(np.uint32), mb[0].view(np.uint32))
+
+
+def test_every_hitable_appears_exactly_once(capi):
+    g = Golden("mixed")
+    s = capi.Scene(g.desc, device=-1).update_bvh()
+    _, link, leaf = s.binary_nodes()
+    ids = np.sort(leaf[leaf >= 0])
+    assert np.array_equal(ids, np.arange(len(ids)))
+    inner = leaf < 0
+    assert inner.sum() == len(ids) - 1
+    assert (link[inner] > np.nonzero(inner)[0] + 1).all()
+
+
+def test_empty_scene_builds(capi):
+    g = Golden("furnace")
+    arrays = dict(g.host.arrays)
+    arrays["components"] = np.zeros(0, dtype=np.uint8)
+    arrays["spheres"] = np.zeros(0, dtype=np.uint8)
+    from wurblpt_b200 import scene_desc as sd
+    s = capi.Scene(sd.HostScene(arrays).desc, device=-1).update_bvh()
+    assert s.info().hitables == 0

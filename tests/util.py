@@ -1,0 +1,77 @@
+"""Shared helpers for the tests: golden fixtures, image metrics."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from wurblpt_b200 import abi
+from wurblpt_b200 import scene_desc as sd
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_SCENES = ["cornell", "rtiow", "mis", "mis_nohot", "media", "tof", "furnace", "mixed", "synth"]
+
+
+class Golden:
+    """One tests/golden/<name>.npz: scene description, view, and the reference's outputs."""
+
+    def __init__(self, name):
+        self.name = name
+        with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+            self.z = {k: z[k] for k in z.files}
+        self.host = sd.HostScene({k[len("scene_"):]: v for k, v in self.z.items() if k.startswith("scene_")})
+        self.camera = abi.wpt_camera_desc.from_buffer_copy(self.z["camera"].tobytes())
+        self._keys = None
+        if self.camera.n_keyframes:
+            self._keys = np.ascontiguousarray(self.z["camera_keyframes"])
+            self.camera.keyframes = C.cast(self._keys.ctypes.data, C.POINTER(abi.wpt_keyframe))
+        else:
+            self.camera.keyframes = None
+        self.sensor = abi.wpt_sensor_desc.from_buffer_copy(self.z["sensor"].tobytes())
+        self.params = abi.wpt_params.from_buffer_copy(self.z["params"].tobytes())
+        self.t0 = float(self.z["t0"])
+        self.t1 = float(self.z["t1"])
+        self.scale = float(self.z["scale"])
+
+    @property
+    def desc(self):
+        return self.host.desc
+
+
+def box_downsample(img, k):
+    h, w = img.shape[:2]
+    h2, w2 = (h // k) * k, (w // k) * k
+    return img[:h2, :w2].reshape(h2 // k, k, w2 // k, k, -1).mean(axis=(1, 3))
+
+
+def rel_rmse(a, b, floor=1e-2):
+    """Relative RMSE of a against b: sqrt(mean((a-b)^2 / (b^2 + floor)))."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(np.mean((a - b) ** 2 / (b ** 2 + floor))))
+
+
+def compare_hits(ids, dist, ref_ids, ref_dist):
+    """Classify per-ray differences between a device closest-hit result and the reference's.
+
+    Returns dict(total, same, ties, near, wrong):
+      same   identical id
+      ties   different id, bit-equal (or 1-ulp) distance: an exact tie settled differently
+      near   different id, distances within 4 ulp or 1e-6 relative: rounding at an edge
+      wrong  everything else (must be 0)
+    """
+    ids = ids.ravel(); ref_ids = ref_ids.ravel()
+    dist = dist.ravel(); ref_dist = ref_dist.ravel()
+    diff = ids != ref_ids
+    n_diff = int(diff.sum())
+    ties = near = wrong = 0
+    if n_diff:
+        d = dist[diff]; r = ref_dist[diff]
+        both = (ids[diff] >= 0) & (ref_ids[diff] >= 0)
+        ulp = np.abs(d.view(np.int32).astype(np.int64) - r.view(np.int32).astype(np.int64))
+        is_tie = both & (ulp <= 1)
+        is_near = both & ~is_tie & ((ulp <= 4) | (np.abs(d - r) <= 1e-6 * np.abs(r)))
+        ties = int(is_tie.sum()); near = int(is_near.sum())
+        wrong = n_diff - ties - near
+    same = ids.size - n_diff
+    bit_equal_dist = int((dist[~diff].view(np.int32) == ref_dist[~diff].view(np.int32)).sum())
+    return dict(total=int(ids.size), same=same, ties=ties, near=near, wrong=wrong, dist_bit_equal=bit_equal_dist)
