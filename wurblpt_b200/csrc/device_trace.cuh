@@ -186,7 +186,8 @@ WPT_DEV void triangleCorners(const DScene& S, uint32_t slot, const Ctx<F>& ctx,
 /* Woop/Benthin/Wald watertight test as the reference runs it (hitable_triangle.hpp:189-271).
  * Returns false on a miss; on a hit `a` is the distance, (U,V,W)/det the barycentrics. */
 WPT_DEV bool triangleTest(float3 v0, float3 v1, float3 v2, const Ray& ray, const RayHelper& h,
-        float amin, float amax, bool bounded, float& a, float& U, float& V, float& W, float& det)
+        float amin, float amax, bool bounded, float& a, float& U, float& V, float& W, float& det,
+        float& Tsigned, float& detAbs)
 {
     const float3 A = v0 - ray.o;
     const float3 B = v1 - ray.o;
@@ -217,16 +218,23 @@ WPT_DEV bool triangleTest(float3 v0, float3 v1, float3 v2, const Ray& ray, const
     const float Bz = h.Sz * Bkz;
     const float Cz = h.Sz * Ckz;
     const float T = U * Az + V * Bz + W * Cz;
+    const uint32_t detSign = __float_as_uint(det) & 0x80000000u;
+    Tsigned = __uint_as_float(__float_as_uint(T) ^ detSign);
+    detAbs = __uint_as_float(__float_as_uint(det) ^ detSign);
     if (bounded) {
-        const uint32_t detSign = __float_as_uint(det) & 0x80000000u;
-        const float Ts = __uint_as_float(__float_as_uint(T) ^ detSign);
-        const float ds = __uint_as_float(__float_as_uint(det) ^ detSign);
-        if (Ts < amin * ds || Ts > amax * ds)
+        if (Tsigned < amin * detAbs || Tsigned > amax * detAbs)
             return false;
     }
     const float invDet = 1.0f / det;
     a = invDet * T;
     return true;
+}
+
+WPT_DEV bool triangleTest(float3 v0, float3 v1, float3 v2, const Ray& ray, const RayHelper& h,
+        float amin, float amax, bool bounded, float& a, float& U, float& V, float& W, float& det)
+{
+    float Ts, da;
+    return triangleTest(v0, v1, v2, ray, h, amin, amax, bounded, a, U, V, W, det, Ts, da);
 }
 
 /* ------------------------------------------------------------- ray / sphere */
@@ -353,8 +361,10 @@ WPT_DEV bool mediumTest(const DScene& S, uint32_t slot, const Ray& ray, const Ra
 /* One leaf of either walk. Returns true if the hitable reports a hit under (amin, amax). */
 template<int F, bool TOP>
 WPT_DEV bool leafTest(const DScene& S, uint32_t ref, const Ray& ray, const RayHelper& h,
-        float amin, float amax, float minHit, Ctx<F>& ctx, float& a)
+        float amin, float amax, float minHit, Ctx<F>& ctx, float& a, float& Tsigned, float& detAbs)
 {
+    Tsigned = 0.0f;
+    detAbs = 0.0f;
     const uint32_t type = ref >> REF_TYPE_SHIFT;
     const uint32_t slot = ref & REF_SLOT_MASK;
     if (F & F_COUNT)
@@ -364,7 +374,7 @@ WPT_DEV bool leafTest(const DScene& S, uint32_t ref, const Ray& ray, const RayHe
         uint32_t inst, tri, anim;
         triangleCorners<F>(S, slot, ctx, v0, v1, v2, inst, tri, anim);
         float U, V, W, det;
-        return triangleTest(v0, v1, v2, ray, h, amin, amax, true, a, U, V, W, det);
+        return triangleTest(v0, v1, v2, ray, h, amin, amax, true, a, U, V, W, det, Tsigned, detAbs);
     } else if (type == PRIM_SPHERE) {
         SphereGeom g = sphereGeom<F>(S, slot, ctx);
         return sphereTest(g.center, g.radius, ray, amin, amax, a);
@@ -394,8 +404,8 @@ __device__ Hit traverseReference(const DScene& S, uint32_t root, const Ray& ray,
         if (boxTestReference(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), ray, h.inv, amin, best.a)) {
             const uint32_t leaf = __float_as_uint(n1.w);
             if (leaf != 0xFFFFFFFFu) {
-                float a;
-                if (leafTest<F, TOP>(S, leaf, ray, h, amin, best.a, minHit, ctx, a)) {
+                float a, Ts, da;
+                if (leafTest<F, TOP>(S, leaf, ray, h, amin, best.a, minHit, ctx, a, Ts, da)) {
                     best.a = a;
                     best.ref = leaf;
                 }
@@ -471,6 +481,7 @@ __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
     st.sm = smStack;
     st.stride = smStride;
     st.sp = 0;
+    float bestTs = 0.0f, bestDet = 0.0f;    /* T and |det| of the current best triangle */
     int32_t cur = S.root4;
     if (cur == EMPTY_CHILD)
         return best;
@@ -502,16 +513,21 @@ __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
             }
         } else {
             const uint32_t ref = uint32_t(~cur);
-            float a;
-            if (leafTest<F, true>(S, ref, ray, h, amin, best.a, minHit, ctx, a)) {
-                /* Exact tie between two triangles: the reference keeps the one it visits last,
-                 * i.e. the higher slot (slots follow the reference's storage order). */
-                const bool tieLoses = (a == best.a) && (best.ref != NO_HIT)
+            float a, Ts, da;
+            if (leafTest<F, true>(S, ref, ray, h, amin, best.a, minHit, ctx, a, Ts, da)) {
+                /* (Near-)ties between two triangles. The reference meets triangles in storage order,
+                 * i.e. in slot order, and a later triangle Y replaces an earlier X iff
+                 * T_Y <= a_X * det_Y (hitable_triangle.hpp:263-264, bvh.hpp:292-295). When this walk
+                 * meets them the other way round (best = Y, candidate = X with the lower slot), redo
+                 * that very comparison with Y's stored T and det to decide as the reference does. */
+                const bool keepBest = (best.ref != NO_HIT)
                     && ((best.ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE) && ((ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE)
-                    && (ref < best.ref);
-                if (!tieLoses) {
+                    && (ref < best.ref) && (bestTs <= a * bestDet);
+                if (!keepBest) {
                     best.a = a;
                     best.ref = ref;
+                    bestTs = Ts;
+                    bestDet = da;
                 }
             }
         }
