@@ -15,6 +15,7 @@
 #pragma once
 
 #include <cmath>
+#include <cstddef>
 #include <cstdint>
 #include <limits>
 #include <type_traits>
@@ -103,8 +104,11 @@ public:
     explicit vector(const T* p) { for (int i = 0; i < N; i++) values[i] = p[i]; }
     template<typename U> explicit vector(const vector<U, N>& v) { for (int i = 0; i < N; i++) values[i] = T(v[i]); }
 
-    const T& operator[](int i) const { return values[i]; }
-    T& operator[](int i) { return values[i]; }
+    /* like the reference, a vector converts to a pointer to its components; the index operators
+     * take ptrdiff_t so that v[i] stays unambiguous next to that conversion */
+    operator const T*() const { return values; }
+    const T& operator[](std::ptrdiff_t i) const { return values[i]; }
+    T& operator[](std::ptrdiff_t i) { return values[i]; }
 
     /* named components */
     const T& x() const { return values[0]; }

@@ -1,0 +1,155 @@
+/* texture.hpp -- Texture interface and the procedural textures (mirror of reference
+ * libwurblpt/texture.hpp:40-246). value() is evaluated on the host for environment-map importance
+ * tables and application use; the device evaluates the same four texture kinds from their flattened
+ * description (csrc/device_shade.cuh). A user-defined Texture subclass cannot run on the device:
+ * flattening it is reported as an error when the scene is prepared. */
+#pragma once
+
+#include <tgd/array.hpp>
+#include <tgd/io.hpp>
+
+#include "scene_component.hpp"
+#include "color.hpp"
+#include "animation.hpp"
+#include "flatten.hpp"
+
+namespace WurblPT {
+
+enum LinearizeSRGBType
+{
+    LinearizeSRGB_On,
+    LinearizeSRGB_Off,
+    LinearizeSRGB_Auto
+};
+
+class Texture : public SceneComponent
+{
+public:
+    virtual ~Texture() {}
+
+    virtual vec4 value(const vec2& texcoords, float t = 0.0f) const = 0;
+    virtual vec2 texelSize() const { return vec2(0.0f, 0.0f); }
+    virtual unsigned int componentCount() const { return 4; }
+    virtual TGD::Type componentType() const { return TGD::float32; }
+    virtual enum LinearizeSRGBType linearizeSRGBType() const { return LinearizeSRGB_Auto; }
+
+    /* Fill `out` (and append texels) for the C ABI; return false if this texture kind cannot be
+     * expressed there. */
+    virtual bool flatten(Flattener& /* F */, wpt_texture& /* out */) const { return false; }
+};
+
+class TextureConstant final : public Texture
+{
+private:
+    const vec4 _color;
+
+public:
+    TextureConstant(const vec4& color) : _color(color) {}
+
+    virtual vec4 value(const vec2& /* texcoords */, float /* t */) const override { return _color; }
+    virtual vec2 texelSize() const override { return vec2(1.0f, 1.0f); }
+
+    virtual bool flatten(Flattener&, wpt_texture& out) const override
+    {
+        out.type = WPT_TEX_CONSTANT;
+        detail::store(out.color0, _color, 4);
+        return true;
+    }
+};
+
+class TextureChecker final : public Texture
+{
+private:
+    vec4 _color0, _color1;
+    int _horiz, _vert;
+
+public:
+    TextureChecker(const vec4& color0, const vec4& color1, int horiz = 9, int vert = 9) :
+        _color0(color0), _color1(color1), _horiz(horiz), _vert(vert)
+    {
+    }
+
+    TextureChecker(const vec3& color0, const vec3& color1, int horiz = 9, int vert = 9) :
+        TextureChecker(vec4(color0, average(color0)), vec4(color1, average(color1)), horiz, vert)
+    {
+    }
+
+    virtual vec4 value(const vec2& texcoords, float /* t */) const override
+    {
+        int row = texcoords.y() * _vert;
+        int col = texcoords.x() * _horiz;
+        return (row % 2 == col % 2 ? _color0 : _color1);
+    }
+
+    virtual bool flatten(Flattener&, wpt_texture& out) const override
+    {
+        out.type = WPT_TEX_CHECKER;
+        detail::store(out.color0, _color0, 4);
+        detail::store(out.color1, _color1, 4);
+        out.horiz = _horiz;
+        out.vert = _vert;
+        return true;
+    }
+};
+
+class TextureTransformer final : public Texture
+{
+private:
+    const Texture* _texture;
+    const vec2 _coordFactor;
+    const vec2 _coordOffset;
+    const vec4 _valFactor;
+    const vec4 _valOffset;
+
+public:
+    TextureTransformer(const Texture* texture,
+            const vec2& coordFactor, const vec2& coordOffset = vec2(0.0f),
+            const vec4& valFactor = vec4(1.0f), const vec4& valOffset = vec4(0.0f)) :
+        _texture(texture), _coordFactor(coordFactor), _coordOffset(coordOffset),
+        _valFactor(valFactor), _valOffset(valOffset)
+    {
+    }
+
+    virtual vec4 value(const vec2& texcoords, float t) const override
+    {
+        vec4 val = _texture->value(_coordFactor * texcoords + _coordOffset, t);
+        return _valFactor * val + _valOffset;
+    }
+
+    virtual vec2 texelSize() const override { return _texture->texelSize() / _coordFactor; }
+    virtual unsigned int componentCount() const override { return _texture->componentCount(); }
+    virtual TGD::Type componentType() const override { return _texture->componentType(); }
+
+    virtual bool flatten(Flattener& F, wpt_texture& out) const override
+    {
+        out.type = WPT_TEX_TRANSFORMER;
+        out.src_texture = F.texture(_texture);
+        detail::store(out.coord_factor, _coordFactor, 2);
+        detail::store(out.coord_offset, _coordOffset, 2);
+        detail::store(out.val_factor, _valFactor, 4);
+        detail::store(out.val_offset, _valOffset, 4);
+        return out.src_texture >= 0;
+    }
+};
+
+inline int Flattener::texture(const Texture* tex)
+{
+    if (!tex)
+        return -1;
+    auto it = textureIndex.find(tex);
+    if (it != textureIndex.end())
+        return it->second;
+    wpt_texture t;
+    std::memset(&t, 0, sizeof(t));
+    t.src_texture = -1;
+    if (!tex->flatten(*this, t)) {
+        fail("a user-defined Texture subclass cannot be evaluated on the device");
+        return -1;
+    }
+    int index = textures.size();
+    textures.push_back(t);
+    textureIndex[tex] = index;
+    return index;
+}
+
+}
