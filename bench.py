@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the path-tracing hot path (mcpt -> tracePath -> BVH::hit) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores
+
+A "step" is one mcpt() of the workload: the 1M-triangle synthetic scene (BASELINE.json config C3:
+GGX materials, HDR environment map with importance sampling, 1920x1080, 256 spp). Rank r of N renders
+the pixel tiles r, r+N, ... of the same image and the frames are combined with one NCCL reduce, so the
+total work is fixed as N grows ("scaling": "strong").
+
+Keys of the JSON line (see the task contract):
+  value      Msamples/s, scene resident in HBM, frame left on the device, CUDA-event timed
+  e2e        the same through the C-ABI call a user of the library makes (wpt_render with a HOST frame
+             buffer): parameter upload + kernel + device->host copy of the frame inside the timed region
+  roofline   the render kernel against measured HBM bandwidth, using the reference's algorithmic bytes
+             per closest-hit query (32 B per node visit + 68 B per leaf test)
+  cpu_baseline  the unmodified reference (oracle/_ref, compiled with its release flags) timed on this
+             box's host cores on a bounded sample of the same workload
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene, scale, width, height, samples_sqrt)
+    "synth": ("synth", 1.0, 1920, 1080, 16),
+    "cornell": ("cornell", 1.0, 512, 512, 8),
+    "rtiow": ("rtiow", 1.0, 1920, 1080, 16),
+    # reduced copies for profiler runs (ncu replays every launch ~40 times)
+    "synth_profile": ("synth", 1.0, 960, 540, 4),
+    "cornell_profile": ("cornell", 1.0, 512, 512, 4),
+}
+
+
+def load_json(path, default):
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return default
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=6)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def reference_timing(workload, samples_sqrt, flavour="fast"):
+    """mcpt() of the unmodified reference on the host cores: (Msamples/s, threads, seconds, sample text)."""
+    from oracle import refapi
+    scene_name, scale, width, height, _ = WORKLOADS[workload]
+    if not refapi.available(flavour):
+        flavour = "strict"
+    view = refapi.View(scene_name, flavour=flavour)
+    view.sensor.width, view.sensor.height = width, height
+    scene = refapi.RefScene(scene_name, scale, 0, flavour=flavour)
+    scene.update_bvh(view.t0, view.t1)
+    _, seconds = scene.render(view.camera, view.sensor, view.params, samples_sqrt, view.t0, view.t1)
+    samples = width * height * samples_sqrt * samples_sqrt
+    threads = scene.lib.ref_threads()
+    flags = scene.lib.ref_build_flags().decode()
+    scene.close()
+    text = "%s %dx%d at %d spp (%d samples) of the %d-spp workload, reference built with %s" % (
+        scene_name, width, height, samples_sqrt ** 2, samples, WORKLOADS[workload][4] ** 2, flags)
+    return samples / seconds / 1e6, threads, seconds, text
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    workload = args.workload
+    spp = args.cpu_samples_sqrt
+    values = []
+    threads, text = 0, ""
+    for i in range(args.warmup + args.steps):
+        v, threads, seconds, text = reference_timing(workload, spp)
+        if i >= args.warmup:
+            values.append((v, seconds))
+    value = sum(v for v, _ in values) / len(values)
+    ms = 1e3 * sum(s for _, s in values) / len(values)
+    scene_name, scale, width, height, full_spp = WORKLOADS[workload]
+    line = {
+        "impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s %dx%d %dspp" % (workload, width, height, full_spp ** 2),
+                   "step": "one mcpt() of the reference on the host cores at %d spp (bounded sample)" % (spp * spp)},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "reference", "sample": text},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="synth", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-samples-sqrt", type=int, default=4, help="samples_sqrt of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traversal", type=int, default=0)
+    ap.add_argument("--substreams", type=int, default=0)
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from wurblpt_b200 import abi, capi, multi, scenes
+
+    if not torch.cuda.is_available() or capi.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: the library has no CPU fallback")
+    rank, world, local = multi.init_process_group()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+
+    scene_name, scale, width, height, samples_sqrt = WORKLOADS[args.workload]
+    t = time.time()
+    built = scenes.BuiltScene(scene_name, scale)
+    view = scenes.View(scene_name)
+    view.sensor.width, view.sensor.height = width, height
+    build_scene_s = time.time() - t
+    scene = capi.Scene(built.desc, device=local)
+    scene.update_bvh(view.t0, view.t1)
+    built.close()
+    info = scene.info()
+
+    stream = torch.cuda.current_stream(device)
+    frame = torch.zeros((height, width, 3), dtype=torch.float32, device=device)
+    host_frame = torch.zeros((height, width, 3), dtype=torch.float32).pin_memory()
+    opts = multi.rank_opts(rank, world, substreams=args.substreams, stream=stream.cuda_stream, traversal=args.traversal)
+    # > 126 MB so that node / triangle lines cached in L2 by the previous step are gone
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def step():
+        """one mcpt(): clear the rank's frame, render its tiles, combine the frames on rank 0"""
+        frame.zero_()
+        scene.render_device(view.camera, view.sensor, view.params, samples_sqrt, frame.data_ptr(), view.t0, view.t1, opts)
+        multi.reduce_frame(frame)
+
+    for _ in range(args.warmup):
+        l2_flush.fill_(1)
+        step()
+    barrier()
+
+    # ---- timed region 1: device-resident throughput (the metric `value`) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    step_ms = []
+    barrier()
+    for _ in range(args.steps):
+        l2_flush.fill_(1)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        step_ms.append((e0, e1))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in step_ms)
+    t_ms = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t_ms.item())
+    ms_per_step = total_ms / args.steps
+    samples_per_step = width * height * samples_sqrt * samples_sqrt
+    value = samples_per_step / (ms_per_step * 1e3)
+
+    # ---- kernel-only duration and ray count of this rank's render kernel (for the roofline) ----
+    l2_flush.fill_(1)
+    frame.zero_()
+    torch.cuda.synchronize(device)
+    st = scene.render_device(view.camera, view.sensor, view.params, samples_sqrt, frame.data_ptr(), view.t0, view.t1,
+                             opts, want_stats=True)
+    kernel_ms, rays_rank, samples_rank = st.kernel_ms, st.rays, st.samples
+    c = torch.tensor([float(rays_rank), float(samples_rank)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    rays_total = float(c[0].item())
+
+    # ---- timed region 2: end to end through the C-ABI call with a HOST frame buffer ----
+    e2e = None
+    if world == 1:
+        e2e_opts = capi.make_opts(traversal=args.traversal, substreams=args.substreams)
+        host_np = host_frame.numpy()
+        for _ in range(2):
+            scene.render(view.camera, view.sensor, view.params, samples_sqrt, view.t0, view.t1, e2e_opts, host_np)
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            scene.render(view.camera, view.sensor, view.params, samples_sqrt, view.t0, view.t1, e2e_opts, host_np)
+        e2e_s = (time.perf_counter() - t0) / args.steps
+        h2d = C.sizeof(abi.wpt_camera_desc) + C.sizeof(abi.wpt_sensor_desc) + C.sizeof(abi.wpt_params) + C.sizeof(abi.wpt_render_opts)
+        e2e = {"value": samples_per_step / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(host_np.nbytes), "checksum": float(host_np.mean())}
+    else:
+        # multi-GPU: the user-facing call is the same step plus the device->host read of the combined frame on rank 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+            if rank == 0:
+                host_frame.copy_(frame, non_blocking=False)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.steps
+        ts = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        h2d = C.sizeof(abi.wpt_camera_desc) + C.sizeof(abi.wpt_sensor_desc) + C.sizeof(abi.wpt_params) + C.sizeof(abi.wpt_render_opts)
+        e2e = {"value": samples_per_step / float(ts.item()) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(host_frame.numel() * 4), "checksum": float(host_frame.mean()) if rank == 0 else 0.0}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the render kernel ----
+    work = load_json(os.path.join(ROOT, "profiles", "r1_algorithmic_work.json"), {}).get(scene_name)
+    peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"), None)
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks else (6650.0, "fallback")
+    roofline = None
+    if work:
+        algo_bytes = rays_rank * work["bytes_per_query"]
+        achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = load_json(os.path.join(ROOT, "profiles", "r1_dram_traffic.json"), {}).get(scene_name)
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel": "renderKernel", "kernel_ms": kernel_ms,
+                    "queries_per_launch": rays_rank, "bytes_per_query": work["bytes_per_query"],
+                    "nodes_per_query": work["nodes_per_query"], "leaves_per_query": work["leaves_per_query"],
+                    "mrays_per_s": rays_rank / kernel_ms / 1e3}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            v, threads, seconds, text = reference_timing(args.workload, args.cpu_samples_sqrt)
+            cpu = {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "reference", "sample": text,
+                   "seconds": seconds}
+        except Exception as ex:     # the checker is optional for the product arm
+            cpu = {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
+
+    line = {
+        "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s %dx%d %dspp" % (args.workload, width, height, samples_sqrt ** 2),
+                   "triangles": int(info.triangles), "hitables": int(info.hitables),
+                   "wide_nodes": int(info.wide_nodes), "device_mb": info.device_bytes / 1e6,
+                   "parallelism": "tiles interleaved over %d GPU(s), one NCCL reduce per frame" % world,
+                   "cache": "256 MiB buffer written between timed steps (L2 flush); scene 250 MB > 126 MB L2",
+                   "traversal": "wide4" if args.traversal == 0 else "reference-order",
+                   "scene_build_s": build_scene_s, "bvh_build_s": info.build_seconds, "upload_s": info.upload_seconds},
+        "mrays_per_s": rays_total / (ms_per_step * 1e3), "rays_per_sample": rays_total / samples_per_step,
+        "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

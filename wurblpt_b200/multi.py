@@ -1,0 +1,65 @@
+"""One process per GPU: tile partition and frame combination (torch.distributed plumbing).
+
+The reference distributes 4096-pixel blocks over MPI ranks from a coordinator thread and gathers
+the finished blocks on rank 0 (reference libwurblpt/mpi.hpp:42-289). Here every rank holds a
+replica of the scene, renders the pixel tiles  rank, rank+N, rank+2N, ...  (inside a GPU, warps
+pull their rank's tiles from a device-side atomic ticket counter), and the per-rank frames are
+combined with ONE reduce over NCCL / NVLink. A pixel is written by exactly one rank and is zero
+everywhere else, so the sum is an exact gather: the N-GPU frame is bit-identical to the 1-GPU frame.
+"""
+import os
+
+import numpy as np
+
+from . import capi
+
+_TILE_W = {1: 8, 2: 4, 4: 4, 8: 2, 16: 2, 32: 1}      # capi.cu: tileWs by log2(substreams)
+
+
+def env_rank():
+    """(rank, world_size, local_rank) from the torchrun environment (defaults: single process)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def init_process_group(backend=None):
+    """Initialise torch.distributed when launched by torchrun with more than one rank."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = env_rank()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def rank_opts(rank, world, substreams=0, stream=None, traversal=0, frame_on_device=True):
+    """Render options that make `rank` of `world` render its interleaved share of the tiles."""
+    return capi.make_opts(traversal=traversal, substreams=substreams, tile_first=rank, tile_stride=world,
+                          frame_on_device=frame_on_device, stream=stream)
+
+
+def tile_shape(substreams):
+    """(tile width, tile height) in pixels: a warp covers 32 / substreams pixels."""
+    w = _TILE_W[substreams]
+    return w, (32 // substreams) // w
+
+
+def owner_map(width, height, substreams, world):
+    """owner[y, x] = rank that renders pixel (x, y): mirror of the tiling arithmetic in wpt_render()."""
+    tw, th = tile_shape(substreams)
+    tiles_x = (width + tw - 1) // tw
+    ys, xs = np.mgrid[0:height, 0:width]
+    tile = (ys // th) * tiles_x + (xs // tw)
+    return (tile % world).astype(np.int32)
+
+
+def reduce_frame(frame, dst=0):
+    """Combine per-rank frames (torch tensors on each rank's device) into rank `dst` with one reduce."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(frame, dst=dst, op=dist.ReduceOp.SUM)
+    return frame
