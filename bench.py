@@ -38,6 +38,7 @@ WORKLOADS = {
     "rtiow": ("rtiow", 1.0, 1920, 1080, 16),
     # reduced copies for profiler runs (ncu replays every launch ~40 times)
     "synth_profile": ("synth", 1.0, 960, 540, 4),
+    "synth_64spp": ("synth", 1.0, 1920, 1080, 8),
     "cornell_profile": ("cornell", 1.0, 512, 512, 4),
 }
 

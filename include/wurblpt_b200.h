@@ -314,6 +314,12 @@ enum {
     WPT_TRAVERSAL_REFERENCE = 1     /* binary BVH walked in the reference's storage order (bvh.hpp:277-311) */
 };
 
+enum {
+    WPT_PIPELINE_AUTO       = 0,    /* the faster one for the scene (currently: wavefront) */
+    WPT_PIPELINE_MEGAKERNEL = 1,    /* one persistent kernel, path state in registers */
+    WPT_PIPELINE_WAVEFRONT  = 2     /* shade / trace kernel pairs, path state in HBM */
+};
+
 typedef struct wpt_render_opts {
     int32_t traversal;          /* WPT_TRAVERSAL_* */
     int32_t substreams;         /* PRNG sub-streams per pixel: 1 = the reference's one stream per pixel
@@ -322,7 +328,7 @@ typedef struct wpt_render_opts {
     uint32_t tile_first;        /* this call renders pixel tiles tile_first, tile_first+tile_stride, ... */
     uint32_t tile_stride;       /* 0 or 1 = all tiles; N = one of N GPUs (the MPICoordinator block split, mpi.hpp:241-254) */
     int32_t frame_on_device;    /* `frame` is a device pointer; untouched tiles are left as they are */
-    int32_t _pad;
+    int32_t pipeline;           /* WPT_PIPELINE_* */
     void* stream;               /* cudaStream_t to launch on (NULL = default stream) */
 } wpt_render_opts;
 

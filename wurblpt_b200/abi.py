@@ -25,6 +25,7 @@ WPT_ENV_NONE, WPT_ENV_EQUIRECT, WPT_ENV_CUBE = range(3)
 WPT_SURROUND_OFF, WPT_SURROUND_180, WPT_SURROUND_360 = range(3)
 WPT_SENSOR_RGB, WPT_SENSOR_TOF_AMCW = range(2)
 WPT_TRAVERSAL_WIDE, WPT_TRAVERSAL_REFERENCE = range(2)
+WPT_PIPELINE_AUTO, WPT_PIPELINE_MEGAKERNEL, WPT_PIPELINE_WAVEFRONT = range(3)
 
 f32, i32, u32, u64 = C.c_float, C.c_int32, C.c_uint32, C.c_uint64
 
@@ -125,7 +126,7 @@ class wpt_params(C.Structure):
 
 class wpt_render_opts(C.Structure):
     _fields_ = [("traversal", i32), ("substreams", i32), ("tile_first", u32), ("tile_stride", u32),
-                ("frame_on_device", i32), ("_pad", i32), ("stream", C.c_void_p)]
+                ("frame_on_device", i32), ("pipeline", i32), ("stream", C.c_void_p)]
 
 
 class wpt_stats(C.Structure):

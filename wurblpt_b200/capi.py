@@ -12,7 +12,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwurblpt_b200.so")
+# WPT_LIB selects an experiment build (see csrc/Makefile VARIANT=...); the default is the product library
+LIB_PATH = os.environ.get("WPT_LIB") or os.path.join(_HERE, "lib", "libwurblpt_b200.so")
 
 EXPORTS = ["wpt_version", "wpt_last_error", "wpt_device_count", "wpt_abi_sizeof", "wpt_scene_create",
            "wpt_scene_update_bvh", "wpt_scene_get_info", "wpt_scene_destroy", "wpt_scene_get_binary_nodes",
@@ -68,8 +69,9 @@ def device_count():
 
 
 def make_opts(traversal=abi.WPT_TRAVERSAL_WIDE, substreams=0, tile_first=0, tile_stride=1,
-              frame_on_device=False, stream=None):
+              frame_on_device=False, stream=None, pipeline=abi.WPT_PIPELINE_AUTO):
     o = abi.wpt_render_opts()
+    o.pipeline = pipeline
     o.traversal = traversal
     o.substreams = substreams
     o.tile_first = tile_first

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -123,8 +124,9 @@ struct wpt_scene {
     /* per updateBVH */
     DeviceBuf node4, bnode, tri, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs;
     /* per call scratch */
-    DeviceBuf counters, camKeys, frame, qOrigins, qDirections, qIds, qDist, qStats;
-    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    DeviceBuf counters, camKeys, frame, partials, wave[14], qOrigins, qDirections, qIds, qDist, qStats;
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[2] = { nullptr, nullptr };
+    unsigned long long* hostDone = nullptr;     /* pinned, 2 counters */
     wptd::DScene d;
     double uploadSeconds = 0.0;
 
@@ -132,6 +134,9 @@ struct wpt_scene {
     {
         if (evStart) cudaEventDestroy(evStart);
         if (evStop) cudaEventDestroy(evStop);
+        if (evWave[0]) cudaEventDestroy(evWave[0]);
+        if (evWave[1]) cudaEventDestroy(evWave[1]);
+        if (hostDone) cudaFreeHost(hostDone);
     }
 
     uint64_t deviceBytes() const
@@ -297,6 +302,22 @@ int fillCamera(wpt_scene* s, const wpt_camera_desc* c, float t0, uint32_t width,
     return WPT_OK;
 }
 
+/* WPT_PIPELINE / WPT_WAVE_SLOTS: experiment knobs (environment), see DESIGN.md */
+int defaultPipeline()
+{
+    const char* e = std::getenv("WPT_PIPELINE");
+    if (e && std::string(e) == "megakernel")
+        return WPT_PIPELINE_MEGAKERNEL;
+    return WPT_PIPELINE_WAVEFRONT;
+}
+
+uint32_t waveSlotLimit()
+{
+    const char* e = std::getenv("WPT_WAVE_SLOTS");
+    long v = e ? std::atol(e) : 0;
+    return v > 0 ? uint32_t(v) : (1u << 20);
+}
+
 int sceneFeatures(const wpt_scene* s, bool needOpl)
 {
     return (s->sceneHasMedia || s->sceneHasAnimation || needOpl) ? 7 : 0;
@@ -404,7 +425,10 @@ int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** out)
     s->uploadSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     WPT_CUDA(cudaEventCreate(&s->evStart), "cudaEventCreate");
     WPT_CUDA(cudaEventCreate(&s->evStop), "cudaEventCreate");
-    WPT_CUDA(s->counters.reserve(4 * sizeof(unsigned long long)), "allocate counters");
+    WPT_CUDA(cudaEventCreateWithFlags(&s->evWave[0], cudaEventDisableTiming), "cudaEventCreate");
+    WPT_CUDA(cudaEventCreateWithFlags(&s->evWave[1], cudaEventDisableTiming), "cudaEventCreate");
+    WPT_CUDA(cudaMallocHost(&s->hostDone, 2 * sizeof(unsigned long long)), "allocate pinned counters");
+    WPT_CUDA(s->counters.reserve(8 * sizeof(unsigned long long)), "allocate counters");
     *out = s.release();
     return WPT_OK;
 }
@@ -571,9 +595,11 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
             return fail(WPT_E_INVALID, "substreams must be a power of two <= 32");
         sub = uint32_t(o.substreams);
     } else {
+        /* enough work items that every lane (megakernel) or slot (wavefront) gets several: short
+         * items keep the tail, where few lanes still have work, short */
         const uint64_t pixels = uint64_t(sensor->width) * sensor->height;
-        const uint64_t wantLanes = uint64_t(s->numSMs) * 2048ull * 4ull;
-        while (sub < 32 && pixels * sub < wantLanes && sub * 2 <= P.samples)
+        const uint64_t wantItems = 8ull * waveSlotLimit();
+        while (sub < 32 && pixels * sub < wantItems && sub * 2 <= P.samples && (P.samples / (sub * 2)) >= 8)
             sub *= 2;
     }
     while (sub > P.samples && sub > 1)
@@ -594,6 +620,9 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
     if (P.tileFirst >= P.tileStride)
         return fail(WPT_E_INVALID, "tile_first must be smaller than tile_stride");
     P.nLocalTiles = (P.tileFirst < P.tilesTotal ? (P.tilesTotal - P.tileFirst + P.tileStride - 1) / P.tileStride : 0);
+    if (uint64_t(P.nLocalTiles) * 32ull >= 0xFFFFFFFFull)
+        return fail(WPT_E_UNSUPPORTED, "image too large for 32-bit work item indices");
+    P.nItems = P.nLocalTiles * 32u;
 
     const size_t frameBytes = size_t(sensor->width) * sensor->height * 3 * sizeof(float);
     if (o.frame_on_device) {
@@ -603,15 +632,58 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
         WPT_CUDA(cudaMemsetAsync(s->frame.p, 0, frameBytes, stream), "clear frame");
         P.frame = static_cast<float*>(s->frame.p);
     }
+    P.partials = nullptr;
+    if (P.substreams > 1) {
+        WPT_CUDA(s->partials.reserve(size_t(sensor->width) * sensor->height * P.substreams * 3 * sizeof(float)), "allocate partial sums");
+        P.partials = static_cast<float*>(s->partials.p);
+    }
     P.counters = static_cast<unsigned long long*>(s->counters.p);
-    WPT_CUDA(cudaMemsetAsync(s->counters.p, 0, 4 * sizeof(unsigned long long), stream), "clear counters");
+    WPT_CUDA(cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), stream), "clear counters");
+
+    /* pipeline */
+    int pipeline = o.pipeline;
+    if (pipeline < WPT_PIPELINE_AUTO || pipeline > WPT_PIPELINE_WAVEFRONT)
+        return fail(WPT_E_INVALID, "unknown pipeline");
+    if (pipeline == WPT_PIPELINE_AUTO)
+        pipeline = defaultPipeline();
+    const int features = sceneFeatures(s, needOpl);
+    if (pipeline == WPT_PIPELINE_WAVEFRONT && P.nItems > 0) {
+        uint32_t slots = waveSlotLimit();
+        if (slots > P.nItems)
+            slots = P.nItems;
+        P.W.nSlots = slots;
+        const size_t n = slots;
+        const size_t sizes[14] = { sizeof(int4), sizeof(uint4), sizeof(float4), sizeof(float4), sizeof(uint2), sizeof(float4),
+            sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4) };
+        const int used = (features != 0 ? 14 : 10);
+        for (int k = 0; k < used; k++)
+            WPT_CUDA(s->wave[k].reserve(n * sizes[k]), "allocate wavefront state");
+        P.W.item = static_cast<int4*>(s->wave[0].p);
+        P.W.prng = static_cast<uint4*>(s->wave[1].p);
+        P.W.rayO = static_cast<float4*>(s->wave[2].p);
+        P.W.rayD = static_cast<float4*>(s->wave[3].p);
+        P.W.hit = static_cast<uint2*>(s->wave[4].p);
+        P.W.acc = static_cast<float4*>(s->wave[5].p);
+        P.W.att = static_cast<float4*>(s->wave[6].p);
+        P.W.nextAtt = static_cast<float4*>(s->wave[7].p);
+        P.W.nextDirHot = static_cast<float4*>(s->wave[8].p);
+        P.W.pendRad = static_cast<float4*>(s->wave[9].p);
+        P.W.opl = static_cast<float4*>(s->wave[10].p);
+        P.W.rayRi = static_cast<float4*>(s->wave[11].p);
+        P.W.nextRi = static_cast<float4*>(s->wave[12].p);
+        P.W.shadowRi = static_cast<float4*>(s->wave[13].p);
+    }
 
     const bool timed = (stats != nullptr) || !o.frame_on_device;
-    int grid = 0;
+    int launches = 0;
     if (timed)
         WPT_CUDA(cudaEventRecord(s->evStart, stream), "cudaEventRecord");
-    if (P.nLocalTiles > 0)
-        WPT_CUDA(wptd::launchRender(sceneFeatures(s, needOpl), s->d, P, s->numSMs, stream, &grid), "render kernel launch");
+    if (P.nLocalTiles > 0) {
+        if (pipeline == WPT_PIPELINE_WAVEFRONT)
+            WPT_CUDA(wptd::launchWavefront(features, s->d, P, s->numSMs, stream, s->hostDone, s->evWave, &launches), "wavefront launch");
+        else
+            WPT_CUDA(wptd::launchRender(features, s->d, P, s->numSMs, stream, &launches), "render kernel launch");
+    }
     if (timed)
         WPT_CUDA(cudaEventRecord(s->evStop, stream), "cudaEventRecord");
     if (!o.frame_on_device)
@@ -627,7 +699,7 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
             stats->nested_queries = c[3];
             stats->tiles = P.nLocalTiles;
             cudaEventElapsedTime(&stats->kernel_ms, s->evStart, s->evStop);
-            stats->launches = (P.nLocalTiles > 0 ? 1 : 0);
+            stats->launches = uint32_t(launches);
             stats->total_ms = float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wallStart).count());
         }
     }

@@ -280,21 +280,24 @@ WPT_DEV uint32_t prngNext(Prng& p)
     return result;
 }
 WPT_DEV float in01(Prng& p) { return float(prngNext(p) >> 8) * 5.9604644775390625e-08f; }
-/* xoshiro128+ jump(): advances by 2^64 draws (Blackman & Vigna's published jump polynomial).
- * Used only to derive sub-streams when a pixel's samples are split over several lanes. */
-WPT_DEV void prngJump(Prng& p)
+/* Sub-streams: when a pixel's samples are split over several work items, item `sub` of the pixel
+ * needs its own stream. sub == 0 is exactly the reference's Prng(pixel); sub > 0 seeds the same
+ * splitmix64 -> xoshiro128+ construction with (pixel + 42) + (sub << 32), which no other
+ * (pixel, sub) pair produces (pixel indices are below 2^31). (The generator's jump() function would
+ * also do, but costs ~1500 instructions per item start, executed by one lane at a time.) */
+WPT_DEV Prng prngInitSub(uint32_t pixelIndex, uint32_t sub)
 {
-    const uint32_t JUMP[4] = { 0x8764000bu, 0xf542d2d3u, 0x6fa035c3u, 0x77f2db5bu };
-    uint32_t a = 0, b = 0, c = 0, d = 0;
-    for (int i = 0; i < 4; i++) {
-        for (int bit = 0; bit < 32; bit++) {
-            if (JUMP[i] & (1u << bit)) {
-                a ^= p.s0; b ^= p.s1; c ^= p.s2; d ^= p.s3;
-            }
-            prngNext(p);
-        }
-    }
-    p.s0 = a; p.s1 = b; p.s2 = c; p.s3 = d;
+    uint64_t seed = pixelIndex;
+    seed += 42;
+    seed += uint64_t(sub) << 32;
+    uint64_t s01 = splitmix64(seed);
+    uint64_t s23 = splitmix64(s01);
+    Prng p;
+    p.s0 = uint32_t(s01 >> 32);
+    p.s1 = uint32_t(s01 & 0xffffffffull);
+    p.s2 = uint32_t(s23 >> 32);
+    p.s3 = uint32_t(s23 & 0xffffffffull);
+    return p;
 }
 /* in01x2() returns vec2(in01(), in01()) (prng.hpp:97-100). The oracle is built with g++, which
  * evaluates those two calls right to left: the FIRST draw lands in .y.

@@ -74,6 +74,23 @@ struct DScene {
 
 constexpr int MAX_CACHED_ANIMATIONS = 4;    /* per-thread animation cache entries (AnimationCache) */
 
+/* Wavefront slot arrays (structure of arrays, one element per slot; thread i <-> slot i, so every
+ * access is a coalesced 8- or 16-byte load/store). */
+struct WaveState {
+    int4* item;         /* pixel, sampleIndex, state | sub << 8 (all ones = idle), pathComponent */
+    uint4* prng;        /* xoshiro128+ state of the item's stream */
+    float4* rayO;       /* pending query: origin xyz, time */
+    float4* rayD;       /* pending query: direction xyz; .w = geometric path length so far */
+    uint2* hit;         /* answer of the trace kernel: distance bits, leaf reference */
+    float4* acc;        /* sample accumulator of the item */
+    float4* att;        /* path attenuation */
+    float4* nextAtt;    /* across a shadow query: attenuation of the next segment */
+    float4* nextDirHot; /* across a shadow query: next direction xyz, chosen hot spot reference */
+    float4* pendRad;    /* across a shadow query: light sample to add if visible */
+    float4* opl; float4* rayRi; float4* nextRi; float4* shadowRi;  /* F_OPL only */
+    uint32_t nSlots;
+};
+
 struct RenderParams {
     /* camera (camera.hpp:42-107, optics.hpp) */
     int32_t surround;
@@ -104,9 +121,12 @@ struct RenderParams {
     uint32_t substreams, subShift;
     uint32_t tileW, tileH, tilesX, tilesTotal;
     uint32_t tileFirst, tileStride, nLocalTiles;
+    uint32_t nItems;                /* nLocalTiles * 32 work items (pixel, sub-stream) */
     /* output */
     float* frame;
-    unsigned long long* counters;   /* [0] tile ticket, [1] samples, [2] rays, [3] nested queries */
+    float* partials;                /* [pixel][sub-stream][3] partial sums when substreams > 1 */
+    unsigned long long* counters;   /* [0] item ticket, [1] samples, [2] rays, [3] nested queries, [4] slots exhausted */
+    WaveState W;
     int32_t traversal;
 };
 

@@ -449,6 +449,17 @@ struct WideStack {
     }
 };
 
+/* next stack entry that can still contain a hit at or before `limit`; EMPTY_CHILD when the stack is empty */
+WPT_DEV int32_t popNext(WideStack& st, float limit)
+{
+    while (st.sp > 0) {
+        const uint2 e = st.pop();
+        if (__uint_as_float(e.y) <= limit)
+            return int32_t(e.x);
+    }
+    return EMPTY_CHILD;
+}
+
 WPT_DEV void sort2(uint32_t& a, uint32_t& b)
 {
     uint32_t lo = min(a, b), hi = max(a, b);
@@ -469,7 +480,12 @@ WPT_DEV uint32_t childKey(float lox, float hix, float loy, float hiy, float loz,
     return tmin <= tmax ? ((__float_as_uint(tmin) & ~3u) | k) : 0xFFFFFFFFu;
 }
 
-/* Closest hit under (amin, amax), amin > 0. */
+/* Closest hit under (amin, amax), amin > 0.
+ *
+ * "while-while" form (Aila & Laine 2009): an inner loop that only descends through inner nodes,
+ * then one leaf test. A lane that reaches a leaf early waits at the end of the inner loop until
+ * the other lanes of the warp have found theirs, so that the (long) node code and the (long) leaf
+ * code each run with as many lanes as possible instead of interleaving lane by lane. */
 template<int F>
 __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
         float amin, float amax, float minHit, Ctx<F>& ctx, uint2* smStack, int smStride)
@@ -482,11 +498,16 @@ __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
     st.stride = smStride;
     st.sp = 0;
     float bestTs = 0.0f, bestDet = 0.0f;    /* T and |det| of the current best triangle */
-    int32_t cur = S.root4;
-    if (cur == EMPTY_CHILD)
-        return best;
+    int32_t cur = S.root4;                  /* EMPTY_CHILD doubles as "walk finished" */
     for (;;) {
-        if (cur >= 0) {
+#ifndef WPT_WHILE_WHILE
+#define WPT_WHILE_WHILE 1
+#endif
+#if WPT_WHILE_WHILE
+        while (cur >= 0 && cur != EMPTY_CHILD) {
+#else
+        if (cur >= 0 && cur != EMPTY_CHILD) {
+#endif
             const float4* n = S.node4 + size_t(cur) * 8;
             const float4 lox = __ldg(n + 0), hix = __ldg(n + 1);
             const float4 loy = __ldg(n + 2), hiy = __ldg(n + 3);
@@ -509,9 +530,17 @@ __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
                 if (k1 != 0xFFFFFFFFu)
                     st.push(uint32_t(sel4i(ch, k1 & 3u)), __uint_as_float(k1 & ~3u));
                 cur = sel4i(ch, k0 & 3u);
-                continue;
+            } else {
+                cur = popNext(st, best.a);
             }
-        } else {
+        }
+        if (cur == EMPTY_CHILD)
+            return best;
+#if WPT_WHILE_WHILE
+        {
+#else
+        if (cur < 0) {
+#endif
             const uint32_t ref = uint32_t(~cur);
             float a, Ts, da;
             if (leafTest<F, true>(S, ref, ray, h, amin, best.a, minHit, ctx, a, Ts, da)) {
@@ -530,16 +559,7 @@ __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
                     bestDet = da;
                 }
             }
-        }
-        /* pop the next entry that can still contain a hit at or before the current best */
-        for (;;) {
-            if (st.sp == 0)
-                return best;
-            const uint2 e = st.pop();
-            if (__uint_as_float(e.y) <= best.a) {
-                cur = int32_t(e.x);
-                break;
-            }
+            cur = popNext(st, best.a);
         }
     }
 }

@@ -1,27 +1,46 @@
 /*
  * kernels.cu -- the sm_100a kernels of the path-tracing core and their launchers.
  *
- *   renderKernel<F>     mcpt() + tracePath() (reference wurblpt.hpp:108-436) as a persistent
- *                       megakernel: one CTA set per SM, warps pull pixel tiles from an atomic
- *                       ticket counter, every lane owns one (pixel, sub-stream) and runs a small
- *                       state machine with ONE tree-walk site, so lanes tracing camera rays,
- *                       bounce rays and shadow rays walk the tree together.
- *   queryKernel<F>      closest hit for explicit rays or pixel-centre camera rays (the loop of
- *                       getGroundTruth(), wurblpt.hpp:659-668); used for bit-exact parity checks.
- *   prngKernel          Prng known answers.
+ * Two pipelines run the same path logic (device_path.cuh):
+ *
+ *   megakernel   renderKernel<F>: persistent CTAs, every lane owns one work item (pixel, sub-stream)
+ *                and loops  startSample -> closest hit -> processHit  with ONE tree-walk site, so
+ *                lanes tracing camera rays, bounce rays and shadow rays walk the tree together. A lane
+ *                that finishes its item takes the next from an atomic ticket counter.
+ *   wavefront    waveShadeKernel<F> / waveTraceKernel<F>: the loop body split at the tree walk. Path
+ *                state lives in HBM (structure of arrays, one slot per in-flight item); the trace kernel
+ *                is lean (closest hit only) and runs at high occupancy, the shade kernel carries the fat
+ *                material / light / camera code. The host enqueues the two kernels in batches and reads a
+ *                "slots exhausted" counter one batch late, so the GPU never waits for the host.
+ *
+ *   queryKernel<F>   closest hit for explicit rays or pixel-centre camera rays (the loop of
+ *                    getGroundTruth(), wurblpt.hpp:659-668); used for bit-exact parity checks.
+ *   resolveKernel    fixed-order sum of sub-stream partial sums.
+ *   prngKernel       Prng known answers.
  *
  * Compiled with --fmad=false (no contraction) so FP32 results round like the strict oracle.
  */
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.hpp"
-#include "device_shade.cuh"
+#include "device_path.cuh"
 
 namespace wptd {
 
-constexpr int BLOCK = 128;
-
-enum { ST_NEW = 0, ST_MAIN = 1, ST_SHADOW_HOT = 2, ST_SHADOW_ENV = 3 };
+#ifndef WPT_BLOCK
+#define WPT_BLOCK 128
+#endif
+#ifndef WPT_MIN_BLOCKS
+#define WPT_MIN_BLOCKS 8
+#endif
+#ifndef WPT_TRACE_MIN_BLOCKS
+#define WPT_TRACE_MIN_BLOCKS 8
+#endif
+#ifndef WPT_SHADE_MIN_BLOCKS
+#define WPT_SHADE_MIN_BLOCKS 4
+#endif
+constexpr int BLOCK = WPT_BLOCK;
 
 template<int F>
 WPT_DEV Hit closestHit(const DScene& S, const RenderParams& P, const Ray& ray, const RayHelper& h,
@@ -32,244 +51,408 @@ WPT_DEV Hit closestHit(const DScene& S, const RenderParams& P, const Ray& ray, c
     return traverseWide<F>(S, ray, h, P.minHit, MAXVAL, P.minHit, ctx, smStack, BLOCK);
 }
 
-WPT_DEV bool isTofLight(const wpt_material* m)
-{
-    return m != nullptr && m->type == WPT_MAT_LIGHT_TOF;
-}
+/* ------------------------------------------------------------------ megakernel */
 
 template<int F>
-__global__ void __launch_bounds__(BLOCK) renderKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+__global__ void __launch_bounds__(BLOCK, WPT_MIN_BLOCKS) renderKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
     extern __shared__ uint2 smStackAll[];
     uint2* smStack = smStackAll + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
-    const float4 one4 = f4(1.0f);
+    const unsigned laneBelow = (1u << lane) - 1u;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
 
-    unsigned long long nSamples = 0, nRays = 0, nNested = 0;
+    unsigned long long nSamples = 0, nRays = 0;
+    Ctx<F> ctx;
+    ctx.prng = prngInit(0);
+    ctx.nested = 0;
+    ctx.nodes = ctx.leaves = 0;
+    PathState ps;
+    ps.state = ST_IDLE;
+    ps.pixel = ps.sub = ps.sampleIndex = 0;
+    ps.acc[0] = ps.acc[1] = ps.acc[2] = 0.0f;
+    ps.walkRay.o = f3(0.0f); ps.walkRay.d = f3(0.0f, 0.0f, 1.0f); ps.walkRay.time = 0.0f;
+    ps.att = ps.opl = ps.rayRi = ps.nextAtt = ps.pendRad = ps.nextRi = ps.shadowRi = f4(0.0f);
+    ps.nextDir = f3(0.0f);
+    ps.pathLength = 0.0f;
+    ps.pathComponent = 0;
+    ps.pendHot = NO_HIT;
+    bool exhausted = false;
 
     for (;;) {
-        /* ---- fetch a tile ticket (MPICoordinator::getBlock, mpi.hpp:241-254, as a device atomic) ---- */
-        unsigned int ticket = 0;
-        if (lane == 0)
-            ticket = (unsigned int)atomicAdd(P.counters + 0, 1ull);
-        ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
-        if (ticket >= P.nLocalTiles)
-            break;
-        const unsigned int tile = P.tileFirst + ticket * P.tileStride;
-        const unsigned int tileX = tile % P.tilesX, tileY = tile / P.tilesX;
-        const unsigned int sub = lane & (P.substreams - 1u);
-        const unsigned int pit = lane >> P.subShift;
-        const unsigned int x = tileX * P.tileW + pit % P.tileW;
-        const unsigned int y = tileY * P.tileH + pit / P.tileW;
-        const bool valid = (x < P.width && y < P.height);
-        const unsigned int pixel = y * P.width + x;
-
-        Ctx<F> ctx;
-        ctx.prng = prngInit(pixel);                     /* Prng prng(pixel) (wurblpt.hpp:342) */
-        for (unsigned int k = 0; k < sub; k++)
-            prngJump(ctx.prng);
-        ctx.nested = 0;
-        ctx.nodes = ctx.leaves = 0;
-
-        float acc[3] = { 0.0f, 0.0f, 0.0f };
-        unsigned int sampleIndex = sub;
-        int state = valid ? ST_NEW : -1;
-
-        /* path state */
-        Ray ray;
-        float4 att = one4, opl = f4(0.0f), rayRi = one4;
-        float pathLength = 0.0f;
-        unsigned int pathComponent = 0;
-        /* pending state across a shadow-ray walk */
-        float4 nextAtt = one4, nextRi = one4, pendRad = f4(0.0f), shadowRi = one4;
-        float3 nextDir = f3(0.0f);
-        uint32_t pendHot = NO_HIT;
-        ray.o = f3(0.0f); ray.d = f3(0.0f, 0.0f, 1.0f); ray.time = 0.0f;
-        Ray walkRay = ray;
-
-        while (state >= 0) {
-            if (state == ST_NEW) {
-                if (sampleIndex >= P.samples)
-                    break;
-                /* stratified jitter (wurblpt.hpp:349-359); first draw goes to the row offset, see in01x2 */
-                float u = float(x), v = float(y);
-                if (P.randomize) {
-                    const unsigned int j = sampleIndex / P.samplesSqrt;
-                    const unsigned int i = sampleIndex % P.samplesSqrt;
-                    const float rj = in01(ctx.prng);
-                    const float ri = in01(ctx.prng);
-                    u += (float(i) + ri) * P.invSamplesSqrt;
-                    v += (float(j) + rj) * P.invSamplesSqrt;
+        /* ---- hand new items to idle lanes (MPICoordinator::getBlock, mpi.hpp:241-254, as a device
+         * atomic; the whole warp passes here once per walk) ---- */
+        const unsigned wantMask = __ballot_sync(FULL, ps.state == ST_IDLE && !exhausted);
+        if (wantMask != 0u) {
+            const int leader = __ffs(wantMask) - 1;
+            unsigned int base = 0;
+            if (int(lane) == leader)
+                base = (unsigned int)atomicAdd(P.counters + 0, (unsigned long long)__popc(wantMask));
+            base = __shfl_sync(FULL, base, leader);
+            if (ps.state == ST_IDLE && !exhausted) {
+                const unsigned int item = base + __popc(wantMask & laneBelow);
+                if (item >= P.nItems) {
+                    exhausted = true;
                 } else {
-                    u += 0.5f;
-                    v += 0.5f;
+                    const WorkItem w = decodeItem(P, item);
+                    if (w.valid)
+                        beginItem<F>(ps, ctx, w);
                 }
-                u *= P.invWidth;
-                v *= P.invHeight;
-                ray = cameraRay(P, u, v, ctx.prng, true);
-                animationCacheInit<F>(S, ctx, ray.time);
-                att = one4;
-                pathLength = 0.0f;
-                opl = f4(0.0f);
-                rayRi = one4;       /* refractiveIndexOfVacuum (camera.hpp:184) */
-                pathComponent = 0;
-                sampleIndex += P.substreams;
-                nSamples++;
-                walkRay = ray;
-                state = ST_MAIN;
-            }
-
-            /* ---- the one tree-walk site ---- */
-            const RayHelper h = makeRayHelper(walkRay);
-            const Hit hit = closestHit<F>(S, P, walkRay, h, ctx, smStack);
-            nRays++;
-
-            bool advance = false;
-            if (state == ST_MAIN) {
-                if (hit.ref == NO_HIT) {
-                    /* no hit: environment map, end of path (wurblpt.hpp:136-146) */
-                    if (S.envType != WPT_ENV_NONE)
-                        accumulate<F>(P, acc, f4(MAXVAL), MAXVAL, att * envRadiance(S, ray.d), false);
-                    state = ST_NEW;
-                    continue;
-                }
-                pathLength += hit.a;
-                if (F & F_OPL)
-                    opl = opl + hit.a * rayRi;
-                if (!(pathComponent + 1 < P.maxPathComponents)) {
-                    state = ST_NEW;
-                    continue;
-                }
-                HitRec hr = buildHitRecord<F>(S, hit, ray, h, ctx);
-                const wpt_material* mat = resolveMaterial(S, hr.material, hr);
-                const ScatterRec sr = materialScatter(S, mat, ray, rayRi, hr, ctx.prng);
-                accumulate<F>(P, acc, opl, (pathComponent == 0 ? 0.0f : hit.a),
-                        att * materialEmitted(S, mat, ray, hr), isTofLight(mat));
-                if (sr.type == SCATTER_NONE) {
-                    state = ST_NEW;
-                    continue;
-                }
-                nextAtt = att * sr.att;
-                if (sr.type == SCATTER_RANDOM) {
-                    if (sr.pdf > 0.0f)
-                        nextAtt = nextAtt / sr.pdf;
-                    else
-                        nextAtt = f4(0.0f);
-                }
-                nextDir = sr.dir;
-                if (F & F_OPL)
-                    nextRi = sr.ri;
-                advance = true;
-                if (sr.type == SCATTER_RANDOM && S.nHot > 0) {
-                    /* next event estimation towards a hot spot with MIS (wurblpt.hpp:179-220) */
-                    const float hotPdf = hotSpotsPdf<F>(S, hr.p, sr.dir, ray.time, ctx);
-                    nextAtt = nextAtt * powerHeuristic(sr.pdf, hotPdf);
-                    unsigned int hotIndex = (unsigned int)(in01(ctx.prng) * float(S.nHot));
-                    hotIndex = min(hotIndex, S.nHot - 1u);
-                    const uint32_t hotRef = __ldg(S.hotRefs + hotIndex);
-                    const float3 directDir = hotSpotDirection<F>(S, hotRef, hr.p, ctx);
-                    const float directPdf = hotSpotsPdf<F>(S, hr.p, directDir, ray.time, ctx);
-                    if (directPdf > 0.0f) {
-                        const ScatterRec dsr = materialScatterToDirection(S, mat, ray, rayRi, hr, directDir);
-                        if (dsr.pdf > 0.0f) {
-                            const float weight = powerHeuristic(directPdf, dsr.pdf);
-                            pendRad = ((att * dsr.att) / directPdf) * weight;
-                            pendHot = hotRef;
-                            if (F & F_OPL)
-                                shadowRi = dsr.ri;
-                            walkRay.o = hr.p;
-                            walkRay.d = directDir;
-                            walkRay.time = ray.time;
-                            state = ST_SHADOW_HOT;
-                            advance = false;
-                        }
-                    }
-                } else if (sr.type == SCATTER_RANDOM && S.envType != WPT_ENV_NONE && S.envN > 0) {
-                    /* next event estimation towards the environment map (wurblpt.hpp:221-252) */
-                    const float lightsP = envPdf(S, sr.dir);
-                    nextAtt = nextAtt * powerHeuristic(sr.pdf, lightsP);
-                    const float3 lightDir = envSample(S, ctx.prng);
-                    const float lightDirP = envPdf(S, lightDir);
-                    const ScatterRec lsr = materialScatterToDirection(S, mat, ray, rayRi, hr, lightDir);
-                    if (lsr.pdf > 0.0f) {
-                        const float weight = powerHeuristic(lightDirP, lsr.pdf);
-                        pendRad = (((att * lsr.att) / lightDirP) * weight) * envRadiance(S, lightDir);
-                        walkRay.o = hr.p;
-                        walkRay.d = lightDir;
-                        walkRay.time = ray.time;
-                        state = ST_SHADOW_ENV;
-                        advance = false;
-                    }
-                }
-                /* the next path segment starts at the hit point (wurblpt.hpp:256) */
-                ray.o = hr.p;
-            } else if (state == ST_SHADOW_HOT) {
-                /* the chosen hot spot must be the closest hit (wurblpt.hpp:208) */
-                if (hit.ref == pendHot) {
-                    HitRec dhr = buildHitRecord<F>(S, hit, walkRay, h, ctx);
-                    const wpt_material* lightMat = resolveMaterial(S, dhr.material, dhr);
-                    const float4 rad = pendRad * materialEmitted(S, lightMat, walkRay, dhr);
-                    float4 oplAcc = opl;
-                    if (F & F_OPL)
-                        oplAcc = opl + hit.a * shadowRi;
-                    accumulate<F>(P, acc, oplAcc, hit.a, rad, isTofLight(lightMat));
-                }
-                advance = true;
-            } else {
-                /* the environment must be visible (wurblpt.hpp:240) */
-                if (hit.ref == NO_HIT)
-                    accumulate<F>(P, acc, f4(MAXVAL), MAXVAL, pendRad, false);
-                advance = true;
-            }
-
-            if (advance) {
-                /* update attenuation and ray, then Russian roulette (wurblpt.hpp:255-273) */
-                att = nextAtt;
-                ray.d = nextDir;
-                if (F & F_OPL)
-                    rayRi = nextRi;
-                walkRay = ray;
-                state = ST_MAIN;
-                const float maxAtt = vmaxcomp(att);
-                if (maxAtt < P.rrThreshold && pathComponent >= 5) {
-                    const float q = rclamp(1.0f - maxAtt, 0.0f, 0.95f);
-                    if (in01(ctx.prng) < q) {
-                        state = ST_NEW;
-                    } else {
-                        const float rrWeight = 1.0f / (1.0f - q);
-                        att = att * rrWeight;
-                    }
-                }
-                pathComponent++;
             }
         }
-        nNested += ctx.nested;
-
-        /* ---- combine the sub-streams of a pixel (fixed order => deterministic) and store ---- */
-        for (unsigned int off = P.substreams >> 1; off > 0; off >>= 1) {
-            acc[0] += __shfl_xor_sync(0xFFFFFFFFu, acc[0], off);
-            acc[1] += __shfl_xor_sync(0xFFFFFFFFu, acc[1], off);
-            acc[2] += __shfl_xor_sync(0xFFFFFFFFu, acc[2], off);
+        if (__all_sync(FULL, exhausted))
+            break;
+        if (ps.state == ST_IDLE)
+            continue;
+        if (ps.state == ST_NEW) {
+            if (!startSample<F>(S, P, ps, ctx)) {
+                finishItem(P, ps);
+                ps.state = ST_IDLE;
+                continue;
+            }
+            animationCacheInit<F>(S, ctx, ps.walkRay.time);
+            nSamples++;
         }
-        if (valid && sub == 0) {
-            /* Sensor::finishPixel (sensor_rgb.hpp:82-87) */
-            float* out = P.frame + size_t(pixel) * 3;
-            out[0] = P.invSamples * acc[0];
-            out[1] = P.invSamples * acc[1];
-            out[2] = P.invSamples * acc[2];
-        }
+        /* ---- the one tree-walk site ---- */
+        const RayHelper h = makeRayHelper(ps.walkRay);
+        const Hit hit = closestHit<F>(S, P, ps.walkRay, h, ctx, smStack);
+        nRays++;
+        processHit<F>(S, P, ps, ctx, hit, h);
     }
 
     /* statistics: one atomic per warp and counter */
+    unsigned long long nNested = ctx.nested;
     for (int off = 16; off > 0; off >>= 1) {
-        nSamples += __shfl_xor_sync(0xFFFFFFFFu, nSamples, off);
-        nRays += __shfl_xor_sync(0xFFFFFFFFu, nRays, off);
-        nNested += __shfl_xor_sync(0xFFFFFFFFu, nNested, off);
+        nSamples += __shfl_xor_sync(FULL, nSamples, off);
+        nRays += __shfl_xor_sync(FULL, nRays, off);
+        nNested += __shfl_xor_sync(FULL, nNested, off);
     }
     if (lane == 0) {
         atomicAdd(P.counters + 1, nSamples);
         atomicAdd(P.counters + 2, nRays);
         atomicAdd(P.counters + 3, nNested);
+    }
+}
+
+/* Adds the sub-stream partial sums of every pixel of this rank's tiles in a fixed order
+ * (deterministic result) and applies Sensor::finishPixel's 1/samples. */
+__global__ void resolveKernel(const __grid_constant__ RenderParams P)
+{
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;       /* (local tile, pixel in tile) */
+    const unsigned int pixelsPerTile = 32u >> P.subShift;
+    if (i >= P.nLocalTiles * pixelsPerTile)
+        return;
+    const unsigned int localTile = i / pixelsPerTile, pit = i % pixelsPerTile;
+    const WorkItem w = decodeItem(P, (localTile << 5) | (pit << P.subShift));
+    if (!w.valid)
+        return;
+    const float* part = P.partials + size_t(w.pixel) * P.substreams * 3;
+    float r = 0.0f, g = 0.0f, b = 0.0f;
+    for (unsigned int s = 0; s < P.substreams; s++) {
+        r += part[s * 3 + 0];
+        g += part[s * 3 + 1];
+        b += part[s * 3 + 2];
+    }
+    float* out = P.frame + size_t(w.pixel) * 3;
+    out[0] = P.invSamples * r;
+    out[1] = P.invSamples * g;
+    out[2] = P.invSamples * b;
+}
+
+/* ------------------------------------------------------------------- wavefront */
+
+/* slot state word: item.z = state | (sub << 8); -1 (all ones) = idle */
+WPT_DEV int slotState(int word) { return word < 0 ? ST_IDLE : (word & 0xFF); }
+
+/* Shade: consume the closest hit of the slot's pending query (if any), then make sure the slot has
+ * its next query ready (next bounce, shadow ray, or the camera ray of its next sample / item). */
+template<int F>
+__global__ void __launch_bounds__(BLOCK, WPT_SHADE_MIN_BLOCKS) waveShadeKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+{
+    const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
+    if (slot == 0)
+        P.counters[5] = 0ull;       /* ticket counter of the next (persistent) trace launch */
+    if (slot >= P.W.nSlots)
+        return;
+    const int4 item = P.W.item[slot];
+    int state = slotState(item.z);
+    if (state == ST_EXHAUSTED)
+        return;
+
+    Ctx<F> ctx;
+    ctx.nested = 0;
+    ctx.nodes = ctx.leaves = 0;
+    PathState ps;
+    ps.state = state;
+    ps.pixel = (unsigned int)item.x;
+    ps.sampleIndex = (unsigned int)item.y;
+    ps.sub = (item.z < 0 ? 0u : (unsigned int)(item.z >> 8));
+    ps.pathComponent = (unsigned int)item.w;
+    unsigned int newSamples = 0;
+
+    if (state != ST_IDLE) {
+        const uint4 r = P.W.prng[slot];
+        ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
+        const float4 acc = P.W.acc[slot];
+        ps.acc[0] = acc.x; ps.acc[1] = acc.y; ps.acc[2] = acc.z;
+    }
+    if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV) {
+        const float4 o = P.W.rayO[slot], d = P.W.rayD[slot];
+        ps.walkRay.o = xyz(o); ps.walkRay.time = o.w;
+        ps.walkRay.d = xyz(d); ps.pathLength = d.w;
+        ps.att = P.W.att[slot];
+        if (F & F_OPL) {
+            ps.opl = P.W.opl[slot];
+            ps.rayRi = P.W.rayRi[slot];
+        }
+        if (state != ST_MAIN) {
+            ps.nextAtt = P.W.nextAtt[slot];
+            const float4 nd = P.W.nextDirHot[slot];
+            ps.nextDir = xyz(nd);
+            ps.pendHot = __float_as_uint(nd.w);
+            ps.pendRad = P.W.pendRad[slot];
+            if (F & F_OPL) {
+                ps.nextRi = P.W.nextRi[slot];
+                ps.shadowRi = P.W.shadowRi[slot];
+            }
+        }
+        const uint2 hw = P.W.hit[slot];
+        Hit hit;
+        hit.a = __uint_as_float(hw.x);
+        hit.ref = hw.y;
+        animationCacheInit<F>(S, ctx, ps.walkRay.time);
+        const RayHelper h = makeRayHelper(ps.walkRay);
+        processHit<F>(S, P, ps, ctx, hit, h);
+    }
+    /* no query pending: start the next sample, the next item, or retire the slot */
+    while (ps.state == ST_NEW || ps.state == ST_IDLE) {
+        if (ps.state == ST_IDLE) {
+            const unsigned int it = (unsigned int)atomicAdd(P.counters + 0, 1ull);
+            if (it >= P.nItems) {
+                ps.state = ST_EXHAUSTED;
+                atomicAdd(P.counters + 4, 1ull);
+                break;
+            }
+            const WorkItem w = decodeItem(P, it);
+            if (w.valid)
+                beginItem<F>(ps, ctx, w);
+        } else if (startSample<F>(S, P, ps, ctx)) {
+            newSamples++;
+        } else {
+            finishItem(P, ps);
+            ps.state = ST_IDLE;
+        }
+    }
+
+    /* write the slot back */
+    P.W.item[slot] = make_int4(int(ps.pixel), int(ps.sampleIndex), ps.state | int(ps.sub << 8), int(ps.pathComponent));
+    if (ps.state != ST_EXHAUSTED) {
+        P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
+        P.W.acc[slot] = f4(ps.acc[0], ps.acc[1], ps.acc[2], 0.0f);
+        P.W.rayO[slot] = f4(ps.walkRay.o, ps.walkRay.time);
+        P.W.rayD[slot] = f4(ps.walkRay.d, ps.pathLength);
+        P.W.att[slot] = ps.att;
+        if (F & F_OPL) {
+            P.W.opl[slot] = ps.opl;
+            P.W.rayRi[slot] = ps.rayRi;
+        }
+        if (ps.state != ST_MAIN) {
+            P.W.nextAtt[slot] = ps.nextAtt;
+            P.W.nextDirHot[slot] = f4(ps.nextDir, __uint_as_float(ps.pendHot));
+            P.W.pendRad[slot] = ps.pendRad;
+            if (F & F_OPL) {
+                P.W.nextRi[slot] = ps.nextRi;
+                P.W.shadowRi[slot] = ps.shadowRi;
+            }
+        }
+    }
+    if (newSamples)
+        atomicAdd(P.counters + 1, (unsigned long long)newSamples);
+}
+
+/* Trace: the closest-hit query of every slot that has one pending. */
+template<int F>
+__global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+{
+    extern __shared__ uint2 smStackAll[];
+    uint2* smStack = smStackAll + threadIdx.x;
+    const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
+    unsigned int traced = 0;
+    Ctx<F> ctx;
+    ctx.nested = 0;
+    ctx.nodes = ctx.leaves = 0;
+    if (slot < P.W.nSlots) {
+        const int state = slotState(P.W.item[slot].z);
+        if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV) {
+            const float4 o = P.W.rayO[slot], d = P.W.rayD[slot];
+            Ray ray;
+            ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
+            if (F & F_MEDIA) {
+                const uint4 r = P.W.prng[slot];
+                ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
+            }
+            animationCacheInit<F>(S, ctx, ray.time);
+            const RayHelper h = makeRayHelper(ray);
+            const Hit hit = closestHit<F>(S, P, ray, h, ctx, smStack);
+            P.W.hit[slot] = make_uint2(__float_as_uint(hit.a), hit.ref);
+            if (F & F_MEDIA)
+                P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
+            traced = 1;
+        }
+    }
+    /* statistics: one atomic per warp */
+    const unsigned int n = __reduce_add_sync(0xFFFFFFFFu, traced);
+    const unsigned int q = __reduce_add_sync(0xFFFFFFFFu, ctx.nested);
+    if ((threadIdx.x & 31) == 0) {
+        if (n)
+            atomicAdd(P.counters + 2, (unsigned long long)n);
+        if (q)
+            atomicAdd(P.counters + 3, (unsigned long long)q);
+    }
+}
+
+/* Trace, persistent form (4-wide walk only): every lane walks the tree for one slot's query and, the
+ * moment its walk ends, stores the answer and takes the next slot from a ticket counter -- inside the
+ * walk loop, so a lane never waits for the longest ray of its warp. One loop iteration handles one
+ * inner node or one leaf. */
+template<int F>
+__global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersistentKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+{
+    extern __shared__ uint2 smStackAll[];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned laneBelow = (1u << lane) - 1u;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    Ctx<F> ctx;
+    ctx.nested = 0;
+    ctx.nodes = ctx.leaves = 0;
+    unsigned int traced = 0;
+
+    unsigned int slot = 0;
+    bool active = false, exhausted = false;
+    Ray ray;
+    ray.o = f3(0.0f); ray.d = f3(0.0f, 0.0f, 1.0f); ray.time = 0.0f;
+    RayHelper h = makeRayHelper(ray);
+    Hit best;
+    best.a = MAXVAL;
+    best.ref = NO_HIT;
+    float bestTs = 0.0f, bestDet = 0.0f;
+    int32_t cur = EMPTY_CHILD;
+    WideStack st;
+    st.sm = smStackAll + threadIdx.x;
+    st.stride = BLOCK;
+    st.sp = 0;
+    const float amin = P.minHit;
+
+    /* Tickets are drawn from the global counter a chunk at a time and handed out inside the warp
+     * without further atomics; idle lanes are only refilled once enough of them have gathered (or
+     * none is busy), because a refill stalls the whole warp on the loads of the new rays. */
+    constexpr unsigned int CHUNK = 256;
+    constexpr int REFILL_MIN = 8;
+    unsigned int warpNext = 0, warpEnd = 0;
+    bool drained = false;           /* the global ticket counter has run past the last slot */
+    for (;;) {
+        const unsigned wantMask = __ballot_sync(FULL, !active && !exhausted);
+        const unsigned busyMask = __ballot_sync(FULL, active);
+        if (wantMask != 0u && (__popc(wantMask) >= REFILL_MIN || busyMask == 0u)) {
+            if (warpNext >= warpEnd && !drained) {
+                unsigned int base = 0;
+                if (lane == 0)
+                    base = (unsigned int)atomicAdd(P.counters + 5, (unsigned long long)CHUNK);
+                base = __shfl_sync(FULL, base, 0);
+                warpNext = base;
+                warpEnd = min(base + CHUNK, P.W.nSlots);
+                if (base >= P.W.nSlots) {
+                    drained = true;
+                    warpNext = warpEnd = 0;
+                }
+            }
+            const unsigned int avail = warpEnd - warpNext;
+            const unsigned int rank = __popc(wantMask & laneBelow);
+            if (!active && !exhausted) {
+                if (rank < avail) {
+                    const unsigned int s = warpNext + rank;
+                    const int state = slotState(P.W.item[s].z);
+                    if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV) {
+                        const float4 o = P.W.rayO[s], d = P.W.rayD[s];
+                        ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
+                        if (F & F_MEDIA) {
+                            const uint4 r = P.W.prng[s];
+                            ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
+                        }
+                        animationCacheInit<F>(S, ctx, ray.time);
+                        h = makeRayHelper(ray);
+                        slot = s;
+                        active = true;
+                        best.a = MAXVAL;
+                        best.ref = NO_HIT;
+                        st.sp = 0;
+                        cur = S.root4;
+                    }
+                } else if (drained) {
+                    exhausted = true;
+                }
+            }
+            warpNext += min((unsigned int)__popc(wantMask), avail);
+        }
+        if (__all_sync(FULL, exhausted))
+            break;
+        if (!active)
+            continue;
+
+        if (cur >= 0 && cur != EMPTY_CHILD) {
+            const float4* n = S.node4 + size_t(cur) * 8;
+            const float4 lox = __ldg(n + 0), hix = __ldg(n + 1);
+            const float4 loy = __ldg(n + 2), hiy = __ldg(n + 3);
+            const float4 loz = __ldg(n + 4), hiz = __ldg(n + 5);
+            const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
+            uint32_t k0 = childKey(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ray.o, h.inv, amin, best.a, 0);
+            uint32_t k1 = childKey(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ray.o, h.inv, amin, best.a, 1);
+            uint32_t k2 = childKey(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ray.o, h.inv, amin, best.a, 2);
+            uint32_t k3 = childKey(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ray.o, h.inv, amin, best.a, 3);
+            sort2(k0, k1); sort2(k2, k3); sort2(k0, k2); sort2(k1, k3); sort2(k1, k2);
+            if (k0 != 0xFFFFFFFFu) {
+                if (k3 != 0xFFFFFFFFu)
+                    st.push(uint32_t(sel4i(ch, k3 & 3u)), __uint_as_float(k3 & ~3u));
+                if (k2 != 0xFFFFFFFFu)
+                    st.push(uint32_t(sel4i(ch, k2 & 3u)), __uint_as_float(k2 & ~3u));
+                if (k1 != 0xFFFFFFFFu)
+                    st.push(uint32_t(sel4i(ch, k1 & 3u)), __uint_as_float(k1 & ~3u));
+                cur = sel4i(ch, k0 & 3u);
+            } else {
+                cur = popNext(st, best.a);
+            }
+        } else if (cur != EMPTY_CHILD) {
+            const uint32_t ref = uint32_t(~cur);
+            float a, Ts, da;
+            if (leafTest<F, true>(S, ref, ray, h, amin, best.a, P.minHit, ctx, a, Ts, da)) {
+                /* same near-tie rule as traverseWide() */
+                const bool keepBest = (best.ref != NO_HIT)
+                    && ((best.ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE) && ((ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE)
+                    && (ref < best.ref) && (bestTs <= a * bestDet);
+                if (!keepBest) {
+                    best.a = a;
+                    best.ref = ref;
+                    bestTs = Ts;
+                    bestDet = da;
+                }
+            }
+            cur = popNext(st, best.a);
+        }
+        if (cur == EMPTY_CHILD) {
+            P.W.hit[slot] = make_uint2(__float_as_uint(best.a), best.ref);
+            if (F & F_MEDIA)
+                P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
+            active = false;
+            traced++;
+        }
+    }
+    const unsigned int n = __reduce_add_sync(FULL, traced);
+    const unsigned int q = __reduce_add_sync(FULL, ctx.nested);
+    if (lane == 0) {
+        if (n)
+            atomicAdd(P.counters + 2, (unsigned long long)n);
+        if (q)
+            atomicAdd(P.counters + 3, (unsigned long long)q);
     }
 }
 
@@ -341,8 +524,17 @@ static size_t stackBytes()
     return size_t(SM_STACK) * BLOCK * sizeof(uint2);
 }
 
+static cudaError_t launchResolve(const RenderParams& P, cudaStream_t stream)
+{
+    if (P.substreams == 1)
+        return cudaSuccess;
+    const unsigned int pixels = P.nLocalTiles * (32u >> P.subShift);
+    resolveKernel<<<(pixels + 255) / 256, 256, 0, stream>>>(P);
+    return cudaGetLastError();
+}
+
 template<int F>
-static cudaError_t launchRenderT(const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream, int* gridOut)
+static cudaError_t launchRenderT(const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream, int* launches)
 {
     int perSM = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, renderKernel<F>, BLOCK, stackBytes());
@@ -350,21 +542,94 @@ static cudaError_t launchRenderT(const DScene& S, const RenderParams& P, int num
         return e;
     if (perSM < 1)
         perSM = 1;
-    /* persistent: exactly as many CTAs as fit, but not more warps than there are tiles */
+    /* persistent: as many CTAs as are resident at once (a multiple of the SM count), fewer only
+     * when there are not enough work items to give every lane one */
     long long grid = (long long)numSMs * perSM;
-    long long needed = ((long long)P.nLocalTiles + (BLOCK / 32) - 1) / (BLOCK / 32);
+    long long needed = ((long long)P.nItems + BLOCK - 1) / BLOCK;
     if (needed < grid)
         grid = needed < 1 ? 1 : needed;
-    *gridOut = int(grid);
     renderKernel<F><<<int(grid), BLOCK, stackBytes(), stream>>>(S, P);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    *launches = (P.substreams == 1 ? 1 : 2);
+    if (e != cudaSuccess)
+        return e;
+    return launchResolve(P, stream);
 }
 
-cudaError_t launchRender(int features, const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream, int* grid)
+cudaError_t launchRender(int features, const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream, int* launches)
 {
     if (features == 0)
-        return launchRenderT<0>(S, P, numSMs, stream, grid);
-    return launchRenderT<F_MEDIA | F_ANIM | F_OPL>(S, P, numSMs, stream, grid);
+        return launchRenderT<0>(S, P, numSMs, stream, launches);
+    return launchRenderT<F_MEDIA | F_ANIM | F_OPL>(S, P, numSMs, stream, launches);
+}
+
+/* Wavefront driver. `hostDone` is pinned host memory for two counters, `events` two CUDA events.
+ * Batches of (trace, shade) pairs are enqueued; the "slots exhausted" counter is copied after every
+ * batch and inspected one batch late, so that a batch is always queued behind the running one. */
+static bool wavePlainTrace()
+{
+    const char* e = std::getenv("WPT_WAVE_PLAIN_TRACE");   /* experiment knob: one ray per thread, no refill */
+    return e && e[0] == '1';
+}
+
+template<int F>
+static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream,
+        unsigned long long* hostDone, cudaEvent_t* events, int* launches)
+{
+    const unsigned int grid = (P.W.nSlots + BLOCK - 1) / BLOCK;
+    const int batch = 16;
+    /* persistent trace kernel: as many CTAs as are resident at once */
+    int perSM = 0;
+    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, waveTracePersistentKernel<F>, BLOCK, stackBytes());
+    if (eo != cudaSuccess)
+        return eo;
+    unsigned int pgrid = (unsigned int)(numSMs * (perSM < 1 ? 1 : perSM));
+    if (pgrid > grid)
+        pgrid = grid;
+    const bool persistent = (P.traversal == WPT_TRAVERSAL_WIDE) && !wavePlainTrace();
+    int n = 0;
+    cudaError_t e = cudaMemsetAsync(P.W.item, 0xFF, size_t(P.W.nSlots) * sizeof(int4), stream);    /* all slots idle */
+    if (e != cudaSuccess)
+        return e;
+    waveShadeKernel<F><<<grid, BLOCK, 0, stream>>>(S, P);
+    n++;
+    hostDone[0] = hostDone[1] = 0;
+    for (int k = 0;; k++) {
+        for (int i = 0; i < batch; i++) {
+            if (persistent)
+                waveTracePersistentKernel<F><<<pgrid, BLOCK, stackBytes(), stream>>>(S, P);
+            else
+                waveTraceKernel<F><<<grid, BLOCK, stackBytes(), stream>>>(S, P);
+            waveShadeKernel<F><<<grid, BLOCK, 0, stream>>>(S, P);
+        }
+        n += 2 * batch;
+        e = cudaMemcpyAsync(hostDone + (k & 1), P.counters + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess)
+            return e;
+        e = cudaEventRecord(events[k & 1], stream);
+        if (e != cudaSuccess)
+            return e;
+        if (k >= 1) {
+            e = cudaEventSynchronize(events[(k - 1) & 1]);
+            if (e != cudaSuccess)
+                return e;
+            if (hostDone[(k - 1) & 1] >= P.W.nSlots)
+                break;
+        }
+    }
+    *launches = n + (P.substreams == 1 ? 0 : 1);
+    e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return e;
+    return launchResolve(P, stream);
+}
+
+cudaError_t launchWavefront(int features, const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream,
+        unsigned long long* hostDone, cudaEvent_t* events, int* launches)
+{
+    if (features == 0)
+        return launchWavefrontT<0>(S, P, numSMs, stream, hostDone, events, launches);
+    return launchWavefrontT<F_MEDIA | F_ANIM | F_OPL>(S, P, numSMs, stream, hostDone, events, launches);
 }
 
 cudaError_t launchQuery(int features, bool count, const DScene& S, const RenderParams& P,

@@ -9,7 +9,11 @@ namespace wptd {
 
 /* features: 0 = static scene, RGB sensor with open gates; anything else selects the full variant
  * (media, animations, optical path length tracking). */
-cudaError_t launchRender(int features, const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream, int* grid);
+cudaError_t launchRender(int features, const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream, int* launches);
+
+/* Wavefront pipeline; P.W must point at allocated slot arrays. hostDone: 2 pinned counters; events: 2 events. */
+cudaError_t launchWavefront(int features, const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream,
+        unsigned long long* hostDone, cudaEvent_t* events, int* launches);
 
 /* origins == nullptr: pixel-centre camera rays of P (width*height rays). */
 cudaError_t launchQuery(int features, bool count, const DScene& S, const RenderParams& P,

@@ -36,10 +36,10 @@ def init_process_group(backend=None):
     return rank, world, local
 
 
-def rank_opts(rank, world, substreams=0, stream=None, traversal=0, frame_on_device=True):
+def rank_opts(rank, world, substreams=0, stream=None, traversal=0, frame_on_device=True, pipeline=0):
     """Render options that make `rank` of `world` render its interleaved share of the tiles."""
     return capi.make_opts(traversal=traversal, substreams=substreams, tile_first=rank, tile_stride=world,
-                          frame_on_device=frame_on_device, stream=stream)
+                          frame_on_device=frame_on_device, stream=stream, pipeline=pipeline)
 
 
 def tile_shape(substreams):
