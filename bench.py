@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--substreams", type=int, default=0)
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "megakernel", "wavefront"])
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -184,7 +185,10 @@ def main():
     stream = torch.cuda.current_stream(device)
     frame = torch.zeros((height, width, 3), dtype=torch.float32, device=device)
     host_frame = torch.zeros((height, width, 3), dtype=torch.float32).pin_memory()
-    opts = multi.rank_opts(rank, world, substreams=args.substreams, stream=stream.cuda_stream, traversal=args.traversal)
+    pipeline = {"auto": abi.WPT_PIPELINE_AUTO, "megakernel": abi.WPT_PIPELINE_MEGAKERNEL,
+                "wavefront": abi.WPT_PIPELINE_WAVEFRONT}[args.pipeline]
+    opts = multi.rank_opts(rank, world, substreams=args.substreams, stream=stream.cuda_stream, traversal=args.traversal,
+                           pipeline=pipeline)
     # > 126 MB so that node / triangle lines cached in L2 by the previous step are gone
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
 
@@ -236,6 +240,7 @@ def main():
     st = scene.render_device(view.camera, view.sensor, view.params, samples_sqrt, frame.data_ptr(), view.t0, view.t1,
                              opts, want_stats=True)
     kernel_ms, rays_rank, samples_rank = st.kernel_ms, st.rays, st.samples
+    launches_per_step = int(st.launches)
     c = torch.tensor([float(rays_rank), float(samples_rank)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
@@ -244,7 +249,7 @@ def main():
     # ---- timed region 2: end to end through the C-ABI call with a HOST frame buffer ----
     e2e = None
     if world == 1:
-        e2e_opts = capi.make_opts(traversal=args.traversal, substreams=args.substreams)
+        e2e_opts = capi.make_opts(traversal=args.traversal, substreams=args.substreams, pipeline=pipeline)
         host_np = host_frame.numpy()
         for _ in range(2):
             scene.render(view.camera, view.sensor, view.params, samples_sqrt, view.t0, view.t1, e2e_opts, host_np)
@@ -287,7 +292,10 @@ def main():
         achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = load_json(os.path.join(ROOT, "profiles", "r1_dram_traffic.json"), {}).get(scene_name)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel": "renderKernel", "kernel_ms": kernel_ms,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "kernel": "renderKernel (megakernel)" if launches_per_step <= 2 else
+                    "waveTracePersistentKernel + waveLogicKernel + waveMaterialKernel (one mcpt = %d launches)" % launches_per_step,
+                    "kernel_ms": kernel_ms,
                     "queries_per_launch": rays_rank, "bytes_per_query": work["bytes_per_query"],
                     "nodes_per_query": work["nodes_per_query"], "leaves_per_query": work["leaves_per_query"],
                     "mrays_per_s": rays_rank / kernel_ms / 1e3}
@@ -311,9 +319,10 @@ def main():
                    "parallelism": "tiles interleaved over %d GPU(s), one NCCL reduce per frame" % world,
                    "cache": "256 MiB buffer written between timed steps (L2 flush); scene 250 MB > 126 MB L2",
                    "traversal": "wide4" if args.traversal == 0 else "reference-order",
+                   "pipeline": "megakernel" if launches_per_step <= 2 else "wavefront",
                    "scene_build_s": build_scene_s, "bvh_build_s": info.build_seconds, "upload_s": info.upload_seconds},
         "mrays_per_s": rays_total / (ms_per_step * 1e3), "rays_per_sample": rays_total / samples_per_step,
-        "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:

@@ -1,0 +1,134 @@
+"""CPU tests of the drop-in boundary: the C++ API mirror (include/wurblpt) must describe scenes
+exactly like the reference does, the reference's example applications must compile against it
+unchanged, and the libtgd stand-in must round-trip what it writes."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def scenes():
+    from wurblpt_b200 import scenes as s
+    try:
+        s.lib()
+    except Exception as e:
+        pytest.skip("libwpt_scenes.so not built: %s" % e)
+    return s
+
+
+@pytest.mark.parametrize("name,scale", [("cornell", 1.0), ("rtiow", 1.0), ("tof", 1.0), ("media", 1.0), ("mis", 1.0),
+                                        ("mis_nohot", 1.0), ("furnace", 1.0), ("mixed", 1.0), ("synth", 0.004)])
+def test_mirror_description_equals_golden(scenes, name, scale):
+    """The mirror's flattening of scenes/configs.hpp is byte-identical to the description the oracle
+    harness derived from the reference's own Scene object (stored in tests/golden)."""
+    from wurblpt_b200 import scene_desc as sd
+    from util import Golden
+    g = Golden(name)
+    built = scenes.BuiltScene(name, scale)
+    mine = sd.desc_to_arrays(built.desc)
+    assert sd.diff_descs(mine, g.host.arrays) == []
+    v = scenes.View(name)
+    assert bytes(v.params) == bytes(g.params)
+    assert bytes(v.camera)[:120] == bytes(g.camera)[:120]      # everything but the key-frame pointer
+    built.close()
+
+
+def test_mirror_description_equals_live_reference_1m_triangles(scenes, ref):
+    from wurblpt_b200 import scene_desc as sd
+    a = sd.desc_to_arrays(scenes.BuiltScene("synth", 1.0).desc)
+    b = sd.desc_to_arrays(ref.RefScene("synth", 1.0, 0).desc)
+    assert sd.diff_descs(a, b) == []
+
+
+def test_mirror_views_equal_reference_views(scenes, ref):
+    for name in ["cornell", "rtiow", "synth", "synth360", "tof", "media", "furnace", "mis", "mixed"]:
+        a, b = scenes.View(name), ref.View(name)
+        assert bytes(a.sensor) == bytes(b.sensor), name
+        assert bytes(a.params) == bytes(b.params), name
+        assert bytes(a.camera)[:120] == bytes(b.camera)[:120], name
+        assert (a.samples_sqrt, a.t0, a.t1) == (b.samples_sqrt, b.t0, b.t1), name
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE + "/wurblpt-cornellbox/wurblpt-cornellbox.cpp"),
+                    reason="reference sources not present")
+@pytest.mark.parametrize("app", ["wurblpt-cornellbox", "wurblpt-rtiow", "wurblpt-furnace-test", "wurblpt-mis-test",
+                                 "wurblpt-participating-media"])
+def test_reference_app_compiles_unchanged_against_the_mirror(app, tmp_path):
+    """'existing example apps link unchanged': compile the reference's own app source against
+    include/wurblpt + include/tgd and link it against libwurblpt_b200.so."""
+    src = "%s/%s/%s.cpp" % (REFERENCE, app, app)
+    out = str(tmp_path / app)
+    lib = os.path.join(ROOT, "wurblpt_b200", "lib")
+    cmd = ["/usr/bin/g++", "-std=c++20", "-O1", "-I" + os.path.join(ROOT, "include"), src, "-o", out,
+           "-L" + lib, "-lwurblpt_b200", "-Wl,-rpath," + lib]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_mirror_refuses_to_render_without_a_device(tmp_path):
+    """mcpt() through the mirror has no CPU fallback: without a GPU the app must stop with an error."""
+    from wurblpt_b200 import capi
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    src = tmp_path / "t.cpp"
+    src.write_text('''
+#include <wurblpt/wurblpt.hpp>
+using namespace WurblPT;
+int main() {
+    Scene scene;
+    scene.take(new Sphere(vec3(0.0f), 1.0f, scene.take(new MaterialLambertian(vec3(0.5f)))));
+    SensorRGB sensor(8, 8);
+    Camera camera(Optics(Projection(radians(40.0f), 1.0f)), Transformation(vec3(0.0f, 0.0f, 5.0f)));
+    scene.updateBVH();
+    mcpt(sensor, camera, scene, 1);
+    return 0;
+}
+''')
+    lib = os.path.join(ROOT, "wurblpt_b200", "lib")
+    exe = str(tmp_path / "t")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe,
+                        "-L" + lib, "-lwurblpt_b200", "-Wl,-rpath," + lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "no CUDA device" in r.stderr or "CPU fallback" in r.stderr
+
+
+def test_tgd_stand_in_round_trips(tmp_path):
+    src = tmp_path / "io.cpp"
+    src.write_text('''
+#include <tgd/array.hpp>
+#include <tgd/io.hpp>
+#include <cstdio>
+int main(int argc, char** argv) {
+    TGD::Array<float> a({ size_t(5), size_t(3) }, 3);
+    for (size_t i = 0; i < a.elementCount() * 3; i++) a.begin()[i] = 0.25f * i;
+    a.globalTagList().set("K", "V");
+    const char* names[] = { "a.pfm", "a.tgd" };
+    for (const char* n : names) {
+        std::string path = std::string(argv[1]) + "/" + n;
+        if (TGD::save(a, path) != TGD::ErrorNone) return 1;
+        TGD::Error e;
+        TGD::ArrayContainer b = TGD::load(path, TGD::TagList(), &e);
+        if (e != TGD::ErrorNone || b.dimension(0) != 5 || b.dimension(1) != 3 || b.componentCount() != 3) return 2;
+        for (size_t i = 0; i < 45; i++) if (static_cast<const float*>(b.data())[i] != 0.25f * i) return 3;
+    }
+    TGD::Error e;
+    if (TGD::load(std::string(argv[1]) + "/missing.png", TGD::TagList(), &e).elementCount() != 0 || e == TGD::ErrorNone) return 4;
+    TGD::Array<float> c = a;    // shares storage, like libtgd containers
+    c[{ 1, 1 }][2] = 42.0f;
+    if (a[{ 1, 1 }][2] != 42.0f) return 5;
+    return 0;
+}
+''')
+    exe = str(tmp_path / "io")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++20", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert subprocess.run([exe, str(tmp_path)]).returncode == 0

@@ -124,7 +124,7 @@ struct wpt_scene {
     /* per updateBVH */
     DeviceBuf node4, bnode, tri, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs;
     /* per call scratch */
-    DeviceBuf counters, camKeys, frame, partials, wave[14], qOrigins, qDirections, qIds, qDist, qStats;
+    DeviceBuf counters, camKeys, frame, partials, wave[15], qOrigins, qDirections, qIds, qDist, qStats;
     cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[2] = { nullptr, nullptr };
     unsigned long long* hostDone = nullptr;     /* pinned, 2 counters */
     wptd::DScene d;
@@ -394,6 +394,11 @@ int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** out)
     int rc = s->host.ingest(desc);
     if (rc != WPT_OK)
         return fail(rc, s->host.error);
+    if (const char* e = std::getenv("WPT_LEAF_TRIS")) {     /* experiment knob: triangles per wide-tree leaf, 1..4 */
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 4)
+            s->host.wideLeafTriangles = uint32_t(v);
+    }
     if (device == WPT_DEVICE_NONE) {
         /* host-only scene: bounds and tree can be built and inspected, nothing can be rendered */
         s->device = WPT_DEVICE_NONE;
@@ -672,6 +677,8 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
         P.W.rayRi = static_cast<float4*>(s->wave[11].p);
         P.W.nextRi = static_cast<float4*>(s->wave[12].p);
         P.W.shadowRi = static_cast<float4*>(s->wave[13].p);
+        WPT_CUDA(s->wave[14].reserve(n * sizeof(uint32_t)), "allocate material queue");
+        P.W.queue = static_cast<uint32_t*>(s->wave[14].p);
     }
 
     const bool timed = (stats != nullptr) || !o.frame_on_device;

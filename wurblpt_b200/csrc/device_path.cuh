@@ -77,11 +77,33 @@ WPT_DEV bool startSample(const DScene& S, const RenderParams& P, PathState& ps, 
     return true;
 }
 
-/* Everything tracePath() does after a closest-hit query returned `hit` for ps.walkRay. */
-template<int F>
-WPT_DEV void processHit(const DScene& S, const RenderParams& P, PathState& ps, Ctx<F>& ctx, const Hit& hit, const RayHelper& h)
+/* Update attenuation and ray for the next path segment, then Russian roulette (wurblpt.hpp:255-273). */
+WPT_DEV void advancePath(const RenderParams& P, PathState& ps, Prng& prng, bool trackRi)
 {
-    bool advance = false;
+    ps.att = ps.nextAtt;
+    ps.walkRay.d = ps.nextDir;
+    if (trackRi)
+        ps.rayRi = ps.nextRi;
+    ps.state = ST_MAIN;
+    const float maxAtt = vmaxcomp(ps.att);
+    if (maxAtt < P.rrThreshold && ps.pathComponent >= 5) {
+        const float q = rclamp(1.0f - maxAtt, 0.0f, 0.95f);
+        if (in01(prng) < q) {
+            ps.state = ST_NEW;
+        } else {
+            const float rrWeight = 1.0f / (1.0f - q);
+            ps.att = ps.att * rrWeight;
+        }
+    }
+    ps.pathComponent++;
+}
+
+/* The cheap part of tracePath() after a closest-hit query: a camera/bounce ray that left the scene
+ * or reached the last allowed path component, and the results of shadow rays. Returns true when the
+ * query was a camera/bounce ray that hit a surface which still has to be shaded (surfaceShade()). */
+template<int F>
+WPT_DEV bool processLogic(const DScene& S, const RenderParams& P, PathState& ps, Ctx<F>& ctx, const Hit& hit, const RayHelper& h)
+{
     const Ray ray = ps.walkRay;
     if (ps.state == ST_MAIN) {
         if (hit.ref == NO_HIT) {
@@ -89,75 +111,18 @@ WPT_DEV void processHit(const DScene& S, const RenderParams& P, PathState& ps, C
             if (S.envType != WPT_ENV_NONE)
                 accumulate<F>(P, ps.acc, f4(MAXVAL), MAXVAL, ps.att * envRadiance(S, ray.d), false);
             ps.state = ST_NEW;
-            return;
+            return false;
         }
         ps.pathLength += hit.a;
         if (F & F_OPL)
             ps.opl = ps.opl + hit.a * ps.rayRi;
         if (!(ps.pathComponent + 1 < P.maxPathComponents)) {
             ps.state = ST_NEW;
-            return;
+            return false;
         }
-        HitRec hr = buildHitRecord<F>(S, hit, ray, h, ctx);
-        const wpt_material* mat = resolveMaterial(S, hr.material, hr);
-        const ScatterRec sr = materialScatter(S, mat, ray, ps.rayRi, hr, ctx.prng);
-        accumulate<F>(P, ps.acc, ps.opl, (ps.pathComponent == 0 ? 0.0f : hit.a),
-                ps.att * materialEmitted(S, mat, ray, hr), isTofLight(mat));
-        if (sr.type == SCATTER_NONE) {
-            ps.state = ST_NEW;
-            return;
-        }
-        ps.nextAtt = ps.att * sr.att;
-        if (sr.type == SCATTER_RANDOM) {
-            if (sr.pdf > 0.0f)
-                ps.nextAtt = ps.nextAtt / sr.pdf;
-            else
-                ps.nextAtt = f4(0.0f);
-        }
-        ps.nextDir = sr.dir;
-        if (F & F_OPL)
-            ps.nextRi = sr.ri;
-        advance = true;
-        if (sr.type == SCATTER_RANDOM && S.nHot > 0) {
-            /* next event estimation towards a hot spot with MIS (wurblpt.hpp:179-220) */
-            const float hotPdf = hotSpotsPdf<F>(S, hr.p, sr.dir, ray.time, ctx);
-            ps.nextAtt = ps.nextAtt * powerHeuristic(sr.pdf, hotPdf);
-            unsigned int hotIndex = (unsigned int)(in01(ctx.prng) * float(S.nHot));
-            hotIndex = min(hotIndex, S.nHot - 1u);
-            const uint32_t hotRef = __ldg(S.hotRefs + hotIndex);
-            const float3 directDir = hotSpotDirection<F>(S, hotRef, hr.p, ctx);
-            const float directPdf = hotSpotsPdf<F>(S, hr.p, directDir, ray.time, ctx);
-            if (directPdf > 0.0f) {
-                const ScatterRec dsr = materialScatterToDirection(S, mat, ray, ps.rayRi, hr, directDir);
-                if (dsr.pdf > 0.0f) {
-                    const float weight = powerHeuristic(directPdf, dsr.pdf);
-                    ps.pendRad = ((ps.att * dsr.att) / directPdf) * weight;
-                    ps.pendHot = hotRef;
-                    if (F & F_OPL)
-                        ps.shadowRi = dsr.ri;
-                    ps.walkRay.d = directDir;
-                    ps.state = ST_SHADOW_HOT;
-                    advance = false;
-                }
-            }
-        } else if (sr.type == SCATTER_RANDOM && S.envType != WPT_ENV_NONE && S.envN > 0) {
-            /* next event estimation towards the environment map (wurblpt.hpp:221-252) */
-            const float lightsP = envPdf(S, sr.dir);
-            ps.nextAtt = ps.nextAtt * powerHeuristic(sr.pdf, lightsP);
-            const float3 lightDir = envSample(S, ctx.prng);
-            const float lightDirP = envPdf(S, lightDir);
-            const ScatterRec lsr = materialScatterToDirection(S, mat, ray, ps.rayRi, hr, lightDir);
-            if (lsr.pdf > 0.0f) {
-                const float weight = powerHeuristic(lightDirP, lsr.pdf);
-                ps.pendRad = (((ps.att * lsr.att) / lightDirP) * weight) * envRadiance(S, lightDir);
-                ps.walkRay.d = lightDir;
-                ps.state = ST_SHADOW_ENV;
-                advance = false;
-            }
-        }
-        /* the shadow ray and the next path segment both start at the hit point (wurblpt.hpp:203,256) */
-        ps.walkRay.o = hr.p;
-    } else if (ps.state == ST_SHADOW_HOT) {
+        return true;
+    }
+    if (ps.state == ST_SHADOW_HOT) {
         /* the chosen hot spot must be the closest hit (wurblpt.hpp:208) */
         if (hit.ref == ps.pendHot) {
             HitRec dhr = buildHitRecord<F>(S, hit, ray, h, ctx);
@@ -168,33 +133,90 @@ WPT_DEV void processHit(const DScene& S, const RenderParams& P, PathState& ps, C
                 oplAcc = ps.opl + hit.a * ps.shadowRi;
             accumulate<F>(P, ps.acc, oplAcc, hit.a, rad, isTofLight(lightMat));
         }
-        advance = true;
     } else {
         /* the environment must be visible (wurblpt.hpp:240) */
         if (hit.ref == NO_HIT)
             accumulate<F>(P, ps.acc, f4(MAXVAL), MAXVAL, ps.pendRad, false);
-        advance = true;
     }
+    advancePath(P, ps, ctx.prng, (F & F_OPL) != 0);
+    return false;
+}
 
-    if (advance) {
-        /* update attenuation and ray, then Russian roulette (wurblpt.hpp:255-273) */
-        ps.att = ps.nextAtt;
-        ps.walkRay.d = ps.nextDir;
-        if (F & F_OPL)
-            ps.rayRi = ps.nextRi;
-        ps.state = ST_MAIN;
-        const float maxAtt = vmaxcomp(ps.att);
-        if (maxAtt < P.rrThreshold && ps.pathComponent >= 5) {
-            const float q = rclamp(1.0f - maxAtt, 0.0f, 0.95f);
-            if (in01(ctx.prng) < q) {
-                ps.state = ST_NEW;
-            } else {
-                const float rrWeight = 1.0f / (1.0f - q);
-                ps.att = ps.att * rrWeight;
+/* The expensive part: hit record, emission, scatter, next-event estimation set-up (wurblpt.hpp:156-252).
+ * Leaves the slot with its next query (bounce or shadow ray) or in ST_NEW (path ended). */
+template<int F>
+WPT_DEV void surfaceShade(const DScene& S, const RenderParams& P, PathState& ps, Ctx<F>& ctx, const Hit& hit, const RayHelper& h)
+{
+    const Ray ray = ps.walkRay;
+    HitRec hr = buildHitRecord<F>(S, hit, ray, h, ctx);
+    const wpt_material* mat = resolveMaterial(S, hr.material, hr);
+    const ScatterRec sr = materialScatter(S, mat, ray, ps.rayRi, hr, ctx.prng);
+    accumulate<F>(P, ps.acc, ps.opl, (ps.pathComponent == 0 ? 0.0f : hit.a),
+            ps.att * materialEmitted(S, mat, ray, hr), isTofLight(mat));
+    if (sr.type == SCATTER_NONE) {
+        ps.state = ST_NEW;
+        return;
+    }
+    ps.nextAtt = ps.att * sr.att;
+    if (sr.type == SCATTER_RANDOM) {
+        if (sr.pdf > 0.0f)
+            ps.nextAtt = ps.nextAtt / sr.pdf;
+        else
+            ps.nextAtt = f4(0.0f);
+    }
+    ps.nextDir = sr.dir;
+    if (F & F_OPL)
+        ps.nextRi = sr.ri;
+    bool advance = true;
+    if (sr.type == SCATTER_RANDOM && S.nHot > 0) {
+        /* next event estimation towards a hot spot with MIS (wurblpt.hpp:179-220) */
+        const float hotPdf = hotSpotsPdf<F>(S, hr.p, sr.dir, ray.time, ctx);
+        ps.nextAtt = ps.nextAtt * powerHeuristic(sr.pdf, hotPdf);
+        unsigned int hotIndex = (unsigned int)(in01(ctx.prng) * float(S.nHot));
+        hotIndex = min(hotIndex, S.nHot - 1u);
+        const uint32_t hotRef = __ldg(S.hotRefs + hotIndex);
+        const float3 directDir = hotSpotDirection<F>(S, hotRef, hr.p, ctx);
+        const float directPdf = hotSpotsPdf<F>(S, hr.p, directDir, ray.time, ctx);
+        if (directPdf > 0.0f) {
+            const ScatterRec dsr = materialScatterToDirection(S, mat, ray, ps.rayRi, hr, directDir);
+            if (dsr.pdf > 0.0f) {
+                const float weight = powerHeuristic(directPdf, dsr.pdf);
+                ps.pendRad = ((ps.att * dsr.att) / directPdf) * weight;
+                ps.pendHot = hotRef;
+                if (F & F_OPL)
+                    ps.shadowRi = dsr.ri;
+                ps.walkRay.d = directDir;
+                ps.state = ST_SHADOW_HOT;
+                advance = false;
             }
         }
-        ps.pathComponent++;
+    } else if (sr.type == SCATTER_RANDOM && S.envType != WPT_ENV_NONE && S.envN > 0) {
+        /* next event estimation towards the environment map (wurblpt.hpp:221-252) */
+        const float lightsP = envPdf(S, sr.dir);
+        ps.nextAtt = ps.nextAtt * powerHeuristic(sr.pdf, lightsP);
+        const float3 lightDir = envSample(S, ctx.prng);
+        const float lightDirP = envPdf(S, lightDir);
+        const ScatterRec lsr = materialScatterToDirection(S, mat, ray, ps.rayRi, hr, lightDir);
+        if (lsr.pdf > 0.0f) {
+            const float weight = powerHeuristic(lightDirP, lsr.pdf);
+            ps.pendRad = (((ps.att * lsr.att) / lightDirP) * weight) * envRadiance(S, lightDir);
+            ps.walkRay.d = lightDir;
+            ps.state = ST_SHADOW_ENV;
+            advance = false;
+        }
     }
+    /* the shadow ray and the next path segment both start at the hit point (wurblpt.hpp:203,256) */
+    ps.walkRay.o = hr.p;
+    if (advance)
+        advancePath(P, ps, ctx.prng, (F & F_OPL) != 0);
+}
+
+/* Everything tracePath() does after a closest-hit query returned `hit` for ps.walkRay. */
+template<int F>
+WPT_DEV void processHit(const DScene& S, const RenderParams& P, PathState& ps, Ctx<F>& ctx, const Hit& hit, const RayHelper& h)
+{
+    if (processLogic<F>(S, P, ps, ctx, hit, h))
+        surfaceShade<F>(S, P, ps, ctx, hit, h);
 }
 
 /* A work item is one (pixel, sub-stream): all samples of that sub-stream, run back to back with one

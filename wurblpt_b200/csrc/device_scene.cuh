@@ -88,6 +88,7 @@ struct WaveState {
     float4* nextDirHot; /* across a shadow query: next direction xyz, chosen hot spot reference */
     float4* pendRad;    /* across a shadow query: light sample to add if visible */
     float4* opl; float4* rayRi; float4* nextRi; float4* shadowRi;  /* F_OPL only */
+    uint32_t* queue;    /* slots whose surface hit is to be shaded this round */
     uint32_t nSlots;
 };
 
@@ -125,7 +126,8 @@ struct RenderParams {
     /* output */
     float* frame;
     float* partials;                /* [pixel][sub-stream][3] partial sums when substreams > 1 */
-    unsigned long long* counters;   /* [0] item ticket, [1] samples, [2] rays, [3] nested queries, [4] slots exhausted */
+    unsigned long long* counters;   /* [0] item ticket, [1] samples, [2] rays, [3] nested queries, [4] slots exhausted,
+                                       [5] trace ticket, [6] material queue length */
     WaveState W;
     int32_t traversal;
 };

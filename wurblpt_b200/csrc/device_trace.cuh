@@ -26,7 +26,9 @@ namespace wptd {
 constexpr uint32_t NO_HIT = 0xFFFFFFFFu;
 constexpr uint32_t REF_TYPE_SHIFT = 29;
 constexpr uint32_t REF_SLOT_MASK = (1u << REF_TYPE_SHIFT) - 1u;
-constexpr uint32_t PRIM_TRIANGLE = 0, PRIM_SPHERE = 1, PRIM_MEDIUM = 2;
+constexpr uint32_t PRIM_TRIANGLE = 0, PRIM_SPHERE = 1, PRIM_MEDIUM = 2, PRIM_TRIANGLE_RUN = 3;
+constexpr uint32_t RUN_COUNT_SHIFT = 27;
+constexpr uint32_t RUN_SLOT_MASK = (1u << RUN_COUNT_SHIFT) - 1u;
 constexpr int32_t EMPTY_CHILD = 0x7FFFFFFF;
 constexpr uint32_t NO_NODE = 0xFFFFFFFFu;
 
@@ -480,6 +482,50 @@ WPT_DEV uint32_t childKey(float lox, float hix, float loy, float hiy, float loz,
     return tmin <= tmax ? ((__float_as_uint(tmin) & ~3u) | k) : 0xFFFFFFFFu;
 }
 
+/* State of the best hit so far in the wide walk, with what the near-tie rule needs. */
+struct WideBest {
+    Hit hit;
+    float Ts, det;      /* T and |det| of the best hit if it is a triangle */
+};
+
+/* One candidate of the wide walk against the current best.
+ * (Near-)ties between two triangles: the reference meets triangles in storage order, i.e. in slot
+ * order, and a later triangle Y replaces an earlier X iff T_Y <= a_X * det_Y
+ * (hitable_triangle.hpp:263-264, bvh.hpp:292-295). When this walk meets them the other way round
+ * (best = Y, candidate = X with the lower slot), that very comparison is redone with Y's stored T and
+ * det, so the reference's decision is reproduced. */
+WPT_DEV void considerHit(WideBest& best, uint32_t ref, float a, float Ts, float da)
+{
+    const bool keepBest = (best.hit.ref != NO_HIT)
+        && ((best.hit.ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE) && ((ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE)
+        && (ref < best.hit.ref) && (best.Ts <= a * best.det);
+    if (!keepBest) {
+        best.hit.a = a;
+        best.hit.ref = ref;
+        best.Ts = Ts;
+        best.det = da;
+    }
+}
+
+/* A leaf of the wide tree: one hitable, or a run of up to four consecutive triangle slots. */
+template<int F>
+WPT_DEV void wideLeaf(const DScene& S, uint32_t ref, const Ray& ray, const RayHelper& h,
+        float amin, float minHit, Ctx<F>& ctx, WideBest& best)
+{
+    float a, Ts, da;
+    if ((ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE_RUN) {
+        const uint32_t first = ref & RUN_SLOT_MASK;
+        const uint32_t count = ((ref >> RUN_COUNT_SHIFT) & 3u) + 1u;
+        for (uint32_t i = 0; i < count; i++) {
+            const uint32_t tref = (PRIM_TRIANGLE << REF_TYPE_SHIFT) | (first + i);
+            if (leafTest<F, true>(S, tref, ray, h, amin, best.hit.a, minHit, ctx, a, Ts, da))
+                considerHit(best, tref, a, Ts, da);
+        }
+    } else if (leafTest<F, true>(S, ref, ray, h, amin, best.hit.a, minHit, ctx, a, Ts, da)) {
+        considerHit(best, ref, a, Ts, da);
+    }
+}
+
 /* Closest hit under (amin, amax), amin > 0.
  *
  * "while-while" form (Aila & Laine 2009): an inner loop that only descends through inner nodes,
@@ -490,24 +536,17 @@ template<int F>
 __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
         float amin, float amax, float minHit, Ctx<F>& ctx, uint2* smStack, int smStride)
 {
-    Hit best;
-    best.a = amax;
-    best.ref = NO_HIT;
+    WideBest best;
+    best.hit.a = amax;
+    best.hit.ref = NO_HIT;
+    best.Ts = best.det = 0.0f;
     WideStack st;
     st.sm = smStack;
     st.stride = smStride;
     st.sp = 0;
-    float bestTs = 0.0f, bestDet = 0.0f;    /* T and |det| of the current best triangle */
     int32_t cur = S.root4;                  /* EMPTY_CHILD doubles as "walk finished" */
     for (;;) {
-#ifndef WPT_WHILE_WHILE
-#define WPT_WHILE_WHILE 1
-#endif
-#if WPT_WHILE_WHILE
         while (cur >= 0 && cur != EMPTY_CHILD) {
-#else
-        if (cur >= 0 && cur != EMPTY_CHILD) {
-#endif
             const float4* n = S.node4 + size_t(cur) * 8;
             const float4 lox = __ldg(n + 0), hix = __ldg(n + 1);
             const float4 loy = __ldg(n + 2), hiy = __ldg(n + 3);
@@ -515,10 +554,10 @@ __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
             const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
             if (F & F_COUNT)
                 ctx.nodes++;
-            uint32_t k0 = childKey(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ray.o, h.inv, amin, best.a, 0);
-            uint32_t k1 = childKey(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ray.o, h.inv, amin, best.a, 1);
-            uint32_t k2 = childKey(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ray.o, h.inv, amin, best.a, 2);
-            uint32_t k3 = childKey(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ray.o, h.inv, amin, best.a, 3);
+            uint32_t k0 = childKey(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ray.o, h.inv, amin, best.hit.a, 0);
+            uint32_t k1 = childKey(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ray.o, h.inv, amin, best.hit.a, 1);
+            uint32_t k2 = childKey(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ray.o, h.inv, amin, best.hit.a, 2);
+            uint32_t k3 = childKey(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ray.o, h.inv, amin, best.hit.a, 3);
             /* 5-comparator sorting network, ascending: nearest entry distance first */
             sort2(k0, k1); sort2(k2, k3); sort2(k0, k2); sort2(k1, k3); sort2(k1, k2);
             if (k0 != 0xFFFFFFFFu) {
@@ -531,36 +570,13 @@ __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
                     st.push(uint32_t(sel4i(ch, k1 & 3u)), __uint_as_float(k1 & ~3u));
                 cur = sel4i(ch, k0 & 3u);
             } else {
-                cur = popNext(st, best.a);
+                cur = popNext(st, best.hit.a);
             }
         }
         if (cur == EMPTY_CHILD)
-            return best;
-#if WPT_WHILE_WHILE
-        {
-#else
-        if (cur < 0) {
-#endif
-            const uint32_t ref = uint32_t(~cur);
-            float a, Ts, da;
-            if (leafTest<F, true>(S, ref, ray, h, amin, best.a, minHit, ctx, a, Ts, da)) {
-                /* (Near-)ties between two triangles. The reference meets triangles in storage order,
-                 * i.e. in slot order, and a later triangle Y replaces an earlier X iff
-                 * T_Y <= a_X * det_Y (hitable_triangle.hpp:263-264, bvh.hpp:292-295). When this walk
-                 * meets them the other way round (best = Y, candidate = X with the lower slot), redo
-                 * that very comparison with Y's stored T and det to decide as the reference does. */
-                const bool keepBest = (best.ref != NO_HIT)
-                    && ((best.ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE) && ((ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE)
-                    && (ref < best.ref) && (bestTs <= a * bestDet);
-                if (!keepBest) {
-                    best.a = a;
-                    best.ref = ref;
-                    bestTs = Ts;
-                    bestDet = da;
-                }
-            }
-            cur = popNext(st, best.a);
-        }
+            return best.hit;
+        wideLeaf<F>(S, uint32_t(~cur), ray, h, amin, minHit, ctx, best);
+        cur = popNext(st, best.hit.a);
     }
 }
 

@@ -40,6 +40,9 @@ namespace wptd {
 #ifndef WPT_SHADE_MIN_BLOCKS
 #define WPT_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef WPT_LEAF_MIN
+#define WPT_LEAF_MIN 12     /* lanes that must be at a leaf before the persistent trace kernel runs a leaf round */
+#endif
 constexpr int BLOCK = WPT_BLOCK;
 
 template<int F>
@@ -164,67 +167,80 @@ __global__ void resolveKernel(const __grid_constant__ RenderParams P)
 /* slot state word: item.z = state | (sub << 8); -1 (all ones) = idle */
 WPT_DEV int slotState(int word) { return word < 0 ? ST_IDLE : (word & 0xFF); }
 
-/* Shade: consume the closest hit of the slot's pending query (if any), then make sure the slot has
- * its next query ready (next bounce, shadow ray, or the camera ray of its next sample / item). */
-template<int F>
-__global__ void __launch_bounds__(BLOCK, WPT_SHADE_MIN_BLOCKS) waveShadeKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
-{
-    const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
-    if (slot == 0)
-        P.counters[5] = 0ull;       /* ticket counter of the next (persistent) trace launch */
-    if (slot >= P.W.nSlots)
-        return;
-    const int4 item = P.W.item[slot];
-    int state = slotState(item.z);
-    if (state == ST_EXHAUSTED)
-        return;
+/* ---- slot state in HBM <-> PathState in registers ---- */
 
-    Ctx<F> ctx;
-    ctx.nested = 0;
-    ctx.nodes = ctx.leaves = 0;
-    PathState ps;
-    ps.state = state;
+template<int F>
+WPT_DEV void loadItem(const RenderParams& P, unsigned int slot, const int4 item, PathState& ps, Ctx<F>& ctx)
+{
+    ps.state = slotState(item.z);
     ps.pixel = (unsigned int)item.x;
     ps.sampleIndex = (unsigned int)item.y;
     ps.sub = (item.z < 0 ? 0u : (unsigned int)(item.z >> 8));
     ps.pathComponent = (unsigned int)item.w;
-    unsigned int newSamples = 0;
-
-    if (state != ST_IDLE) {
+    if (ps.state != ST_IDLE) {
         const uint4 r = P.W.prng[slot];
         ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
         const float4 acc = P.W.acc[slot];
         ps.acc[0] = acc.x; ps.acc[1] = acc.y; ps.acc[2] = acc.z;
     }
-    if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV) {
-        const float4 o = P.W.rayO[slot], d = P.W.rayD[slot];
-        ps.walkRay.o = xyz(o); ps.walkRay.time = o.w;
-        ps.walkRay.d = xyz(d); ps.pathLength = d.w;
-        ps.att = P.W.att[slot];
-        if (F & F_OPL) {
-            ps.opl = P.W.opl[slot];
-            ps.rayRi = P.W.rayRi[slot];
-        }
-        if (state != ST_MAIN) {
-            ps.nextAtt = P.W.nextAtt[slot];
-            const float4 nd = P.W.nextDirHot[slot];
-            ps.nextDir = xyz(nd);
-            ps.pendHot = __float_as_uint(nd.w);
-            ps.pendRad = P.W.pendRad[slot];
-            if (F & F_OPL) {
-                ps.nextRi = P.W.nextRi[slot];
-                ps.shadowRi = P.W.shadowRi[slot];
-            }
-        }
-        const uint2 hw = P.W.hit[slot];
-        Hit hit;
-        hit.a = __uint_as_float(hw.x);
-        hit.ref = hw.y;
-        animationCacheInit<F>(S, ctx, ps.walkRay.time);
-        const RayHelper h = makeRayHelper(ps.walkRay);
-        processHit<F>(S, P, ps, ctx, hit, h);
+}
+
+template<int F>
+WPT_DEV void loadPath(const RenderParams& P, unsigned int slot, PathState& ps)
+{
+    const float4 o = P.W.rayO[slot], d = P.W.rayD[slot];
+    ps.walkRay.o = xyz(o); ps.walkRay.time = o.w;
+    ps.walkRay.d = xyz(d); ps.pathLength = d.w;
+    ps.att = P.W.att[slot];
+    if (F & F_OPL) {
+        ps.opl = P.W.opl[slot];
+        ps.rayRi = P.W.rayRi[slot];
     }
-    /* no query pending: start the next sample, the next item, or retire the slot */
+    if (ps.state != ST_MAIN) {
+        ps.nextAtt = P.W.nextAtt[slot];
+        const float4 nd = P.W.nextDirHot[slot];
+        ps.nextDir = xyz(nd);
+        ps.pendHot = __float_as_uint(nd.w);
+        ps.pendRad = P.W.pendRad[slot];
+        if (F & F_OPL) {
+            ps.nextRi = P.W.nextRi[slot];
+            ps.shadowRi = P.W.shadowRi[slot];
+        }
+    }
+}
+
+template<int F>
+WPT_DEV void storeSlot(const RenderParams& P, unsigned int slot, const PathState& ps, const Ctx<F>& ctx)
+{
+    P.W.item[slot] = make_int4(int(ps.pixel), int(ps.sampleIndex), ps.state | int(ps.sub << 8), int(ps.pathComponent));
+    if (ps.state == ST_EXHAUSTED)
+        return;
+    P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
+    P.W.acc[slot] = f4(ps.acc[0], ps.acc[1], ps.acc[2], 0.0f);
+    P.W.rayO[slot] = f4(ps.walkRay.o, ps.walkRay.time);
+    P.W.rayD[slot] = f4(ps.walkRay.d, ps.pathLength);
+    P.W.att[slot] = ps.att;
+    if (F & F_OPL) {
+        P.W.opl[slot] = ps.opl;
+        P.W.rayRi[slot] = ps.rayRi;
+    }
+    if (ps.state != ST_MAIN) {
+        P.W.nextAtt[slot] = ps.nextAtt;
+        P.W.nextDirHot[slot] = f4(ps.nextDir, __uint_as_float(ps.pendHot));
+        P.W.pendRad[slot] = ps.pendRad;
+        if (F & F_OPL) {
+            P.W.nextRi[slot] = ps.nextRi;
+            P.W.shadowRi[slot] = ps.shadowRi;
+        }
+    }
+}
+
+/* No query pending: start the next sample, the next item, or retire the slot. Returns the number of
+ * samples started. */
+template<int F>
+WPT_DEV unsigned int refillSlot(const DScene& S, const RenderParams& P, PathState& ps, Ctx<F>& ctx)
+{
+    unsigned int started = 0;
     while (ps.state == ST_NEW || ps.state == ST_IDLE) {
         if (ps.state == ST_IDLE) {
             const unsigned int it = (unsigned int)atomicAdd(P.counters + 0, 1ull);
@@ -237,35 +253,97 @@ __global__ void __launch_bounds__(BLOCK, WPT_SHADE_MIN_BLOCKS) waveShadeKernel(c
             if (w.valid)
                 beginItem<F>(ps, ctx, w);
         } else if (startSample<F>(S, P, ps, ctx)) {
-            newSamples++;
+            started++;
         } else {
             finishItem(P, ps);
             ps.state = ST_IDLE;
         }
     }
+    return started;
+}
 
-    /* write the slot back */
-    P.W.item[slot] = make_int4(int(ps.pixel), int(ps.sampleIndex), ps.state | int(ps.sub << 8), int(ps.pathComponent));
-    if (ps.state != ST_EXHAUSTED) {
-        P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
-        P.W.acc[slot] = f4(ps.acc[0], ps.acc[1], ps.acc[2], 0.0f);
-        P.W.rayO[slot] = f4(ps.walkRay.o, ps.walkRay.time);
-        P.W.rayD[slot] = f4(ps.walkRay.d, ps.pathLength);
-        P.W.att[slot] = ps.att;
-        if (F & F_OPL) {
-            P.W.opl[slot] = ps.opl;
-            P.W.rayRi[slot] = ps.rayRi;
-        }
-        if (ps.state != ST_MAIN) {
-            P.W.nextAtt[slot] = ps.nextAtt;
-            P.W.nextDirHot[slot] = f4(ps.nextDir, __uint_as_float(ps.pendHot));
-            P.W.pendRad[slot] = ps.pendRad;
-            if (F & F_OPL) {
-                P.W.nextRi[slot] = ps.nextRi;
-                P.W.shadowRi[slot] = ps.shadowRi;
+/* Logic: everything after a query except shading a surface hit -- rays that left the scene, shadow-ray
+ * results, Russian roulette, starting the next sample / item. Slots whose camera or bounce ray hit a
+ * surface are appended to the material queue (one atomic per warp) and left to waveMaterialKernel. */
+template<int F>
+__global__ void __launch_bounds__(BLOCK, WPT_SHADE_MIN_BLOCKS) waveLogicKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+{
+    const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    if (slot == 0)
+        P.counters[5] = 0ull;       /* ticket counter of the next (persistent) trace launch */
+    bool needSurface = false;
+    bool live = false;
+    Ctx<F> ctx;
+    ctx.nested = 0;
+    ctx.nodes = ctx.leaves = 0;
+    PathState ps;
+    unsigned int newSamples = 0;
+    if (slot < P.W.nSlots) {
+        const int4 item = P.W.item[slot];
+        if (slotState(item.z) != ST_EXHAUSTED) {
+            live = true;
+            loadItem<F>(P, slot, item, ps, ctx);
+            if (ps.state == ST_MAIN || ps.state == ST_SHADOW_HOT || ps.state == ST_SHADOW_ENV) {
+                loadPath<F>(P, slot, ps);
+                const uint2 hw = P.W.hit[slot];
+                Hit hit;
+                hit.a = __uint_as_float(hw.x);
+                hit.ref = hw.y;
+                animationCacheInit<F>(S, ctx, ps.walkRay.time);
+                const RayHelper h = makeRayHelper(ps.walkRay);
+                needSurface = processLogic<F>(S, P, ps, ctx, hit, h);
+            }
+            if (needSurface) {
+                /* only the path lengths changed */
+                P.W.rayD[slot] = f4(ps.walkRay.d, ps.pathLength);
+                if (F & F_OPL)
+                    P.W.opl[slot] = ps.opl;
+            } else {
+                newSamples = refillSlot<F>(S, P, ps, ctx);
+                storeSlot<F>(P, slot, ps, ctx);
             }
         }
     }
+    /* material queue: one atomic per warp */
+    const unsigned pushMask = __ballot_sync(0xFFFFFFFFu, needSurface);
+    if (pushMask != 0u) {
+        unsigned int base = 0;
+        if (lane == 0)
+            base = (unsigned int)atomicAdd(P.counters + 6, (unsigned long long)__popc(pushMask));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (needSurface)
+            P.W.queue[base + __popc(pushMask & ((1u << lane) - 1u))] = slot;
+    }
+    (void)live;
+    if (newSamples)
+        atomicAdd(P.counters + 1, (unsigned long long)newSamples);
+}
+
+/* Material: shade the surface hits collected in the queue (dense: every lane of a warp has one). */
+template<int F>
+__global__ void __launch_bounds__(BLOCK, WPT_SHADE_MIN_BLOCKS) waveMaterialKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+{
+    const unsigned int i = blockIdx.x * BLOCK + threadIdx.x;
+    const unsigned int count = (unsigned int)P.counters[6];
+    if (i >= count)
+        return;
+    const unsigned int slot = P.W.queue[i];
+    Ctx<F> ctx;
+    ctx.nested = 0;
+    ctx.nodes = ctx.leaves = 0;
+    PathState ps;
+    loadItem<F>(P, slot, P.W.item[slot], ps, ctx);
+    loadPath<F>(P, slot, ps);
+    const uint2 hw = P.W.hit[slot];
+    Hit hit;
+    hit.a = __uint_as_float(hw.x);
+    hit.ref = hw.y;
+    animationCacheInit<F>(S, ctx, ps.walkRay.time);
+    const RayHelper h = makeRayHelper(ps.walkRay);
+    surfaceShade<F>(S, P, ps, ctx, hit, h);
+    const unsigned int newSamples = refillSlot<F>(S, P, ps, ctx);
+    storeSlot<F>(P, slot, ps, ctx);
     if (newSamples)
         atomicAdd(P.counters + 1, (unsigned long long)newSamples);
 }
@@ -277,6 +355,8 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
     extern __shared__ uint2 smStackAll[];
     uint2* smStack = smStackAll + threadIdx.x;
     const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
+    if (slot == 0)
+        P.counters[6] = 0ull;       /* length of the material queue the next logic launch fills */
     unsigned int traced = 0;
     Ctx<F> ctx;
     ctx.nested = 0;
@@ -326,16 +406,18 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     ctx.nested = 0;
     ctx.nodes = ctx.leaves = 0;
     unsigned int traced = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        P.counters[6] = 0ull;       /* length of the material queue the next logic launch fills */
 
     unsigned int slot = 0;
     bool active = false, exhausted = false;
     Ray ray;
     ray.o = f3(0.0f); ray.d = f3(0.0f, 0.0f, 1.0f); ray.time = 0.0f;
     RayHelper h = makeRayHelper(ray);
-    Hit best;
-    best.a = MAXVAL;
-    best.ref = NO_HIT;
-    float bestTs = 0.0f, bestDet = 0.0f;
+    WideBest best;
+    best.hit.a = MAXVAL;
+    best.hit.ref = NO_HIT;
+    best.Ts = best.det = 0.0f;
     int32_t cur = EMPTY_CHILD;
     WideStack st;
     st.sm = smStackAll + threadIdx.x;
@@ -383,8 +465,8 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
                         h = makeRayHelper(ray);
                         slot = s;
                         active = true;
-                        best.a = MAXVAL;
-                        best.ref = NO_HIT;
+                        best.hit.a = MAXVAL;
+                        best.hit.ref = NO_HIT;
                         st.sp = 0;
                         cur = S.root4;
                     }
@@ -396,19 +478,29 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
         }
         if (__all_sync(FULL, exhausted))
             break;
+        /* One iteration runs EITHER the inner-node code OR the leaf code, never both: lanes that have
+         * reached a leaf wait until LEAF_MIN lanes have one (or no lane has an inner node left), then
+         * those lanes test their primitives together. Without this, the ~4 lanes that are at a leaf in
+         * any given iteration make the whole warp pay for the leaf code every time. */
+        const bool atInner = active && cur >= 0 && cur != EMPTY_CHILD;
+        const bool atLeaf = active && cur < 0;
+        const unsigned innerMask = __ballot_sync(FULL, atInner);
+        const unsigned leafMask = __ballot_sync(FULL, atLeaf);
+        const bool leafRound = (__popc(leafMask) >= WPT_LEAF_MIN) || innerMask == 0u;
         if (!active)
             continue;
 
-        if (cur >= 0 && cur != EMPTY_CHILD) {
+        if (!leafRound) {
+            if (atInner) {
             const float4* n = S.node4 + size_t(cur) * 8;
             const float4 lox = __ldg(n + 0), hix = __ldg(n + 1);
             const float4 loy = __ldg(n + 2), hiy = __ldg(n + 3);
             const float4 loz = __ldg(n + 4), hiz = __ldg(n + 5);
             const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
-            uint32_t k0 = childKey(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ray.o, h.inv, amin, best.a, 0);
-            uint32_t k1 = childKey(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ray.o, h.inv, amin, best.a, 1);
-            uint32_t k2 = childKey(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ray.o, h.inv, amin, best.a, 2);
-            uint32_t k3 = childKey(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ray.o, h.inv, amin, best.a, 3);
+            uint32_t k0 = childKey(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ray.o, h.inv, amin, best.hit.a, 0);
+            uint32_t k1 = childKey(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ray.o, h.inv, amin, best.hit.a, 1);
+            uint32_t k2 = childKey(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ray.o, h.inv, amin, best.hit.a, 2);
+            uint32_t k3 = childKey(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ray.o, h.inv, amin, best.hit.a, 3);
             sort2(k0, k1); sort2(k2, k3); sort2(k0, k2); sort2(k1, k3); sort2(k1, k2);
             if (k0 != 0xFFFFFFFFu) {
                 if (k3 != 0xFFFFFFFFu)
@@ -419,27 +511,15 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
                     st.push(uint32_t(sel4i(ch, k1 & 3u)), __uint_as_float(k1 & ~3u));
                 cur = sel4i(ch, k0 & 3u);
             } else {
-                cur = popNext(st, best.a);
+                cur = popNext(st, best.hit.a);
             }
-        } else if (cur != EMPTY_CHILD) {
-            const uint32_t ref = uint32_t(~cur);
-            float a, Ts, da;
-            if (leafTest<F, true>(S, ref, ray, h, amin, best.a, P.minHit, ctx, a, Ts, da)) {
-                /* same near-tie rule as traverseWide() */
-                const bool keepBest = (best.ref != NO_HIT)
-                    && ((best.ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE) && ((ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE)
-                    && (ref < best.ref) && (bestTs <= a * bestDet);
-                if (!keepBest) {
-                    best.a = a;
-                    best.ref = ref;
-                    bestTs = Ts;
-                    bestDet = da;
-                }
             }
-            cur = popNext(st, best.a);
+        } else if (atLeaf) {
+            wideLeaf<F>(S, uint32_t(~cur), ray, h, amin, P.minHit, ctx, best);
+            cur = popNext(st, best.hit.a);
         }
         if (cur == EMPTY_CHILD) {
-            P.W.hit[slot] = make_uint2(__float_as_uint(best.a), best.ref);
+            P.W.hit[slot] = make_uint2(__float_as_uint(best.hit.a), best.hit.ref);
             if (F & F_MEDIA)
                 P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
             active = false;
@@ -591,7 +671,7 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
     cudaError_t e = cudaMemsetAsync(P.W.item, 0xFF, size_t(P.W.nSlots) * sizeof(int4), stream);    /* all slots idle */
     if (e != cudaSuccess)
         return e;
-    waveShadeKernel<F><<<grid, BLOCK, 0, stream>>>(S, P);
+    waveLogicKernel<F><<<grid, BLOCK, 0, stream>>>(S, P);      /* gives every slot its first camera ray */
     n++;
     hostDone[0] = hostDone[1] = 0;
     for (int k = 0;; k++) {
@@ -600,9 +680,10 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
                 waveTracePersistentKernel<F><<<pgrid, BLOCK, stackBytes(), stream>>>(S, P);
             else
                 waveTraceKernel<F><<<grid, BLOCK, stackBytes(), stream>>>(S, P);
-            waveShadeKernel<F><<<grid, BLOCK, 0, stream>>>(S, P);
+            waveLogicKernel<F><<<grid, BLOCK, 0, stream>>>(S, P);
+            waveMaterialKernel<F><<<grid, BLOCK, 0, stream>>>(S, P);
         }
-        n += 2 * batch;
+        n += 3 * batch;
         e = cudaMemcpyAsync(hostDone + (k & 1), P.counters + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess)
             return e;

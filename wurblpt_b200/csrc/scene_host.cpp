@@ -492,6 +492,7 @@ struct TreeBuilder {
 struct Collapser {
     const std::vector<BNode>& b;
     std::vector<Node4>& out;
+    uint32_t maxRun = 1;            /* triangles per leaf of the wide tree (1 = like the reference) */
     uint32_t maxDepth = 0;
 
     static float area(const BNode& n)
@@ -501,11 +502,40 @@ struct Collapser {
     }
 
     /* Returns the encoded child for binary node `bi`. */
+    /* Number of leaves below binary node `bi` if they are all triangles and at most `limit`, else 0.
+     * `first` receives the lowest leaf reference (= lowest slot: slots follow storage order). */
+    uint32_t triangleRun(uint32_t bi, uint32_t limit, uint32_t& first) const
+    {
+        const BNode& n = b[bi];
+        if (n.leaf != INNER) {
+            if ((n.leaf >> REF_TYPE_SHIFT) != PRIM_TRIANGLE)
+                return 0;
+            first = n.leaf;
+            return 1;
+        }
+        uint32_t f0 = 0, f1 = 0;
+        const uint32_t c0 = triangleRun(bi + 1, limit, f0);
+        if (c0 == 0 || c0 >= limit)
+            return 0;
+        const uint32_t c1 = triangleRun(n.link, limit - c0, f1);
+        if (c1 == 0 || c0 + c1 > limit || f1 != f0 + c0)
+            return 0;
+        first = f0;
+        return c0 + c1;
+    }
+
     int32_t collapse(uint32_t bi, uint32_t depth)
     {
         const BNode& n = b[bi];
         if (n.leaf != INNER)
             return ~int32_t(n.leaf);
+        if (maxRun > 1) {
+            /* a small all-triangle subtree becomes one leaf holding a run of consecutive triangle slots */
+            uint32_t first = 0;
+            const uint32_t run = triangleRun(bi, maxRun, first);
+            if (run >= 2)
+                return ~int32_t((PRIM_TRIANGLE_RUN << REF_TYPE_SHIFT) | ((run - 1) << RUN_COUNT_SHIFT) | (first & RUN_SLOT_MASK));
+        }
         if (depth > maxDepth)
             maxDepth = depth;
         uint32_t kids[4] = { bi + 1, n.link, 0, 0 };
@@ -669,6 +699,7 @@ int HostScene::updateBvh(float t0, float t1)
     nodes4.clear();
     nodes4.reserve(topLevel.size() / 2 + 16);
     Collapser col{ bnodes, nodes4 };
+    col.maxRun = (triGlobal.size() <= RUN_SLOT_MASK ? wideLeafTriangles : 1);
     root4 = topLevel.empty() ? EMPTY_CHILD : col.collapse(0, 1);
     wideDepth = col.maxDepth;
 

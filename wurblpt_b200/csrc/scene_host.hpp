@@ -18,7 +18,10 @@
 namespace wpt {
 
 /* Leaf references used on the device: (type << 29) | slot. */
-enum : uint32_t { PRIM_TRIANGLE = 0, PRIM_SPHERE = 1, PRIM_MEDIUM = 2 };
+enum : uint32_t { PRIM_TRIANGLE = 0, PRIM_SPHERE = 1, PRIM_MEDIUM = 2, PRIM_TRIANGLE_RUN = 3 };
+/* wide-tree leaves may hold a run of up to 4 consecutive triangle slots: (3 << 29) | (count-1) << 27 | first slot */
+constexpr uint32_t RUN_COUNT_SHIFT = 27;
+constexpr uint32_t RUN_SLOT_MASK = (1u << RUN_COUNT_SHIFT) - 1u;
 constexpr uint32_t REF_TYPE_SHIFT = 29;
 constexpr uint32_t REF_SLOT_MASK = (1u << REF_TYPE_SHIFT) - 1u;
 constexpr uint32_t NO_NODE = 0xFFFFFFFFu;
@@ -87,6 +90,7 @@ struct HostScene {
     std::vector<Node4> nodes4;
     int32_t root4 = EMPTY_CHILD;            /* encoded like a Node4 child */
     uint32_t binaryDepth = 0, wideDepth = 0;
+    uint32_t wideLeafTriangles = 4;         /* max triangles per leaf of the wide tree */
     uint64_t topLevelNodes = 0;
     std::vector<uint32_t> refOfGlobal;      /* global id -> device leaf reference */
     std::vector<uint32_t> triGlobal, sphGlobal, medGlobal;  /* slot -> global id */
