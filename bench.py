@@ -114,10 +114,22 @@ def reference_timing(workload, samples_sqrt, flavour="fast"):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation, rank 0 only."""
+    """--impl reference: the reference's own CPU implementation, rank 0 only, on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # torchrun exports OMP_NUM_THREADS=1 to its children; the reference's OpenMP loop must get every
+    # core this process may run on (set before libgomp is loaded with the reference library)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    if os.environ.get("OMP_NUM_THREADS") not in (None, str(cores)) and not os.environ.get("WPT_BENCH_REEXEC"):
+        os.environ["OMP_NUM_THREADS"] = str(cores)
+        os.environ["WPT_BENCH_REEXEC"] = "1"
+        sys.stdout.flush()
+        os.execv(sys.executable, [sys.executable] + sys.argv)   # a clean process: no OpenMP runtime initialised yet
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     workload = args.workload
     spp = args.cpu_samples_sqrt
     values = []
