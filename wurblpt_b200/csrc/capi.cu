@@ -125,7 +125,8 @@ struct wpt_scene {
     DeviceBuf node4, bnode, tri, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs;
     /* per call scratch */
     DeviceBuf counters, camKeys, frame, partials, wave[15], qOrigins, qDirections, qIds, qDist, qStats;
-    cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[2] = { nullptr, nullptr };
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaStream_t stream2 = nullptr;
     unsigned long long* hostDone = nullptr;     /* pinned, 2 counters */
     wptd::DScene d;
     double uploadSeconds = 0.0;
@@ -134,8 +135,9 @@ struct wpt_scene {
     {
         if (evStart) cudaEventDestroy(evStart);
         if (evStop) cudaEventDestroy(evStop);
-        if (evWave[0]) cudaEventDestroy(evWave[0]);
-        if (evWave[1]) cudaEventDestroy(evWave[1]);
+        for (int i = 0; i < 4; i++)
+            if (evWave[i]) cudaEventDestroy(evWave[i]);
+        if (stream2) cudaStreamDestroy(stream2);
         if (hostDone) cudaFreeHost(hostDone);
     }
 
@@ -430,10 +432,11 @@ int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** out)
     s->uploadSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     WPT_CUDA(cudaEventCreate(&s->evStart), "cudaEventCreate");
     WPT_CUDA(cudaEventCreate(&s->evStop), "cudaEventCreate");
-    WPT_CUDA(cudaEventCreateWithFlags(&s->evWave[0], cudaEventDisableTiming), "cudaEventCreate");
-    WPT_CUDA(cudaEventCreateWithFlags(&s->evWave[1], cudaEventDisableTiming), "cudaEventCreate");
+    for (int i = 0; i < 4; i++)
+        WPT_CUDA(cudaEventCreateWithFlags(&s->evWave[i], cudaEventDisableTiming), "cudaEventCreate");
+    WPT_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking), "cudaStreamCreate");
     WPT_CUDA(cudaMallocHost(&s->hostDone, 2 * sizeof(unsigned long long)), "allocate pinned counters");
-    WPT_CUDA(s->counters.reserve(8 * sizeof(unsigned long long)), "allocate counters");
+    WPT_CUDA(s->counters.reserve(16 * sizeof(unsigned long long)), "allocate counters");
     *out = s.release();
     return WPT_OK;
 }
@@ -643,7 +646,7 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
         P.partials = static_cast<float*>(s->partials.p);
     }
     P.counters = static_cast<unsigned long long*>(s->counters.p);
-    WPT_CUDA(cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned long long), stream), "clear counters");
+    WPT_CUDA(cudaMemsetAsync(s->counters.p, 0, 16 * sizeof(unsigned long long), stream), "clear counters");
 
     /* pipeline */
     int pipeline = o.pipeline;
@@ -679,6 +682,9 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
         P.W.shadowRi = static_cast<float4*>(s->wave[13].p);
         WPT_CUDA(s->wave[14].reserve(n * sizeof(uint32_t)), "allocate material queue");
         P.W.queue = static_cast<uint32_t*>(s->wave[14].p);
+        P.W.group = 0;
+        if (features == 0)
+            P.W.opl = P.W.rayRi = P.W.nextRi = P.W.shadowRi = nullptr;
     }
 
     const bool timed = (stats != nullptr) || !o.frame_on_device;
@@ -687,7 +693,7 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
         WPT_CUDA(cudaEventRecord(s->evStart, stream), "cudaEventRecord");
     if (P.nLocalTiles > 0) {
         if (pipeline == WPT_PIPELINE_WAVEFRONT)
-            WPT_CUDA(wptd::launchWavefront(features, s->d, P, s->numSMs, stream, s->hostDone, s->evWave, &launches), "wavefront launch");
+            WPT_CUDA(wptd::launchWavefront(features, s->d, P, s->numSMs, stream, s->stream2, s->hostDone, s->evWave, &launches), "wavefront launch");
         else
             WPT_CUDA(wptd::launchRender(features, s->d, P, s->numSMs, stream, &launches), "render kernel launch");
     }

@@ -90,6 +90,7 @@ struct WaveState {
     float4* opl; float4* rayRi; float4* nextRi; float4* shadowRi;  /* F_OPL only */
     uint32_t* queue;    /* slots whose surface hit is to be shaded this round */
     uint32_t nSlots;
+    uint32_t group;     /* slot group (0 or 1): selects the group's trace ticket / queue length counters */
 };
 
 struct RenderParams {
@@ -127,7 +128,7 @@ struct RenderParams {
     float* frame;
     float* partials;                /* [pixel][sub-stream][3] partial sums when substreams > 1 */
     unsigned long long* counters;   /* [0] item ticket, [1] samples, [2] rays, [3] nested queries, [4] slots exhausted,
-                                       [5] trace ticket, [6] material queue length */
+                                       [5+2g] trace ticket, [6+2g] material queue length of slot group g */
     WaveState W;
     int32_t traversal;
 };

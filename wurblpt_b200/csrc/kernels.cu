@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_SHADE_MIN_BLOCKS) waveLogicKernel(c
     const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     if (slot == 0)
-        P.counters[5] = 0ull;       /* ticket counter of the next (persistent) trace launch */
+        P.counters[5 + 2 * P.W.group] = 0ull;       /* ticket counter of the next (persistent) trace launch */
     bool needSurface = false;
     bool live = false;
     Ctx<F> ctx;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_SHADE_MIN_BLOCKS) waveLogicKernel(c
     if (pushMask != 0u) {
         unsigned int base = 0;
         if (lane == 0)
-            base = (unsigned int)atomicAdd(P.counters + 6, (unsigned long long)__popc(pushMask));
+            base = (unsigned int)atomicAdd(P.counters + 6 + 2 * P.W.group, (unsigned long long)__popc(pushMask));
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (needSurface)
             P.W.queue[base + __popc(pushMask & ((1u << lane) - 1u))] = slot;
@@ -325,7 +325,7 @@ template<int F>
 __global__ void __launch_bounds__(BLOCK, WPT_SHADE_MIN_BLOCKS) waveMaterialKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
     const unsigned int i = blockIdx.x * BLOCK + threadIdx.x;
-    const unsigned int count = (unsigned int)P.counters[6];
+    const unsigned int count = (unsigned int)P.counters[6 + 2 * P.W.group];
     if (i >= count)
         return;
     const unsigned int slot = P.W.queue[i];
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
     uint2* smStack = smStackAll + threadIdx.x;
     const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
     if (slot == 0)
-        P.counters[6] = 0ull;       /* length of the material queue the next logic launch fills */
+        P.counters[6 + 2 * P.W.group] = 0ull;       /* length of the material queue the next logic launch fills */
     unsigned int traced = 0;
     Ctx<F> ctx;
     ctx.nested = 0;
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     ctx.nodes = ctx.leaves = 0;
     unsigned int traced = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0)
-        P.counters[6] = 0ull;       /* length of the material queue the next logic launch fills */
+        P.counters[6 + 2 * P.W.group] = 0ull;       /* length of the material queue the next logic launch fills */
 
     unsigned int slot = 0;
     bool active = false, exhausted = false;
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
             if (warpNext >= warpEnd && !drained) {
                 unsigned int base = 0;
                 if (lane == 0)
-                    base = (unsigned int)atomicAdd(P.counters + 5, (unsigned long long)CHUNK);
+                    base = (unsigned int)atomicAdd(P.counters + 5 + 2 * P.W.group, (unsigned long long)CHUNK);
                 base = __shfl_sync(FULL, base, 0);
                 warpNext = base;
                 warpEnd = min(base + CHUNK, P.W.nSlots);
@@ -646,50 +646,102 @@ cudaError_t launchRender(int features, const DScene& S, const RenderParams& P, i
 /* Wavefront driver. `hostDone` is pinned host memory for two counters, `events` two CUDA events.
  * Batches of (trace, shade) pairs are enqueued; the "slots exhausted" counter is copied after every
  * batch and inspected one batch late, so that a batch is always queued behind the running one. */
+static int waveGroups()
+{
+    const char* e = std::getenv("WPT_WAVE_GROUPS");         /* experiment knob: 1 = a single slot group */
+    return (e && e[0] == '1') ? 1 : 2;
+}
+
 static bool wavePlainTrace()
 {
     const char* e = std::getenv("WPT_WAVE_PLAIN_TRACE");   /* experiment knob: one ray per thread, no refill */
     return e && e[0] == '1';
 }
 
+/* Offsets every slot array of `P.W` by `first` slots and narrows it to `count` slots. */
+static RenderParams slotGroup(const RenderParams& P, uint32_t group, uint32_t first, uint32_t count)
+{
+    RenderParams G = P;
+    G.W.group = group;
+    G.W.nSlots = count;
+    G.W.item += first; G.W.prng += first; G.W.rayO += first; G.W.rayD += first; G.W.hit += first;
+    G.W.acc += first; G.W.att += first; G.W.nextAtt += first; G.W.nextDirHot += first; G.W.pendRad += first;
+    if (G.W.opl) { G.W.opl += first; G.W.rayRi += first; G.W.nextRi += first; G.W.shadowRi += first; }
+    G.W.queue += first;
+    return G;
+}
+
+/* Wavefront driver. The slots are split into two groups that run the same (trace, logic, material)
+ * rounds on two streams: while one group's kernel drains (the tail of a persistent trace launch, or
+ * the last blocks of a short shade launch) the other group's kernel fills the SMs.
+ * `hostDone` is pinned host memory for two counters, `events` four CUDA events (2 for the batch
+ * hand-shake, 2 for fork/join with the second stream). Batches of rounds are enqueued; the "slots
+ * exhausted" counter is copied after every batch and inspected one batch late, so that a batch is
+ * always queued behind the running one. */
 template<int F>
 static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream,
-        unsigned long long* hostDone, cudaEvent_t* events, int* launches)
+        cudaStream_t stream2, unsigned long long* hostDone, cudaEvent_t* events, int* launches)
 {
-    const unsigned int grid = (P.W.nSlots + BLOCK - 1) / BLOCK;
     const int batch = 16;
-    /* persistent trace kernel: as many CTAs as are resident at once */
     int perSM = 0;
-    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, waveTracePersistentKernel<F>, BLOCK, stackBytes());
-    if (eo != cudaSuccess)
-        return eo;
-    unsigned int pgrid = (unsigned int)(numSMs * (perSM < 1 ? 1 : perSM));
-    if (pgrid > grid)
-        pgrid = grid;
-    const bool persistent = (P.traversal == WPT_TRAVERSAL_WIDE) && !wavePlainTrace();
-    int n = 0;
-    cudaError_t e = cudaMemsetAsync(P.W.item, 0xFF, size_t(P.W.nSlots) * sizeof(int4), stream);    /* all slots idle */
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, waveTracePersistentKernel<F>, BLOCK, stackBytes());
     if (e != cudaSuccess)
         return e;
-    waveLogicKernel<F><<<grid, BLOCK, 0, stream>>>(S, P);      /* gives every slot its first camera ray */
-    n++;
+    const bool persistent = (P.traversal == WPT_TRAVERSAL_WIDE) && !wavePlainTrace();
+    const int nGroups = (waveGroups() >= 2 && P.W.nSlots >= 4096) ? 2 : 1;
+    RenderParams G[2];
+    unsigned int grid[2], pgrid[2];
+    cudaStream_t st[2] = { stream, stream2 };
+    const uint32_t half = (nGroups == 2 ? (P.W.nSlots / 2 + BLOCK - 1) / BLOCK * BLOCK : P.W.nSlots);
+    for (int g = 0; g < nGroups; g++) {
+        const uint32_t first = (g == 0 ? 0 : half);
+        const uint32_t count = (g == 0 ? half : P.W.nSlots - half);
+        G[g] = slotGroup(P, uint32_t(g), first, count);
+        grid[g] = (count + BLOCK - 1) / BLOCK;
+        /* persistent trace kernel: the resident CTAs are shared between the groups */
+        pgrid[g] = (unsigned int)(numSMs * (perSM < 1 ? 1 : perSM)) / (unsigned int)nGroups;
+        if (pgrid[g] > grid[g])
+            pgrid[g] = grid[g];
+        if (pgrid[g] < 1)
+            pgrid[g] = 1;
+    }
+    int n = 0;
+    e = cudaMemsetAsync(P.W.item, 0xFF, size_t(P.W.nSlots) * sizeof(int4), stream);    /* all slots idle */
+    if (e != cudaSuccess)
+        return e;
+    if (nGroups == 2) {     /* fork */
+        if ((e = cudaEventRecord(events[2], stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(stream2, events[2], 0)) != cudaSuccess) return e;
+    }
+    for (int g = 0; g < nGroups; g++)
+        waveLogicKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, G[g]);     /* gives every slot its first camera ray */
+    n += nGroups;
     hostDone[0] = hostDone[1] = 0;
     for (int k = 0;; k++) {
         for (int i = 0; i < batch; i++) {
-            if (persistent)
-                waveTracePersistentKernel<F><<<pgrid, BLOCK, stackBytes(), stream>>>(S, P);
-            else
-                waveTraceKernel<F><<<grid, BLOCK, stackBytes(), stream>>>(S, P);
-            waveLogicKernel<F><<<grid, BLOCK, 0, stream>>>(S, P);
-            waveMaterialKernel<F><<<grid, BLOCK, 0, stream>>>(S, P);
+            for (int g = 0; g < nGroups; g++) {
+                if (persistent)
+                    waveTracePersistentKernel<F><<<pgrid[g], BLOCK, stackBytes(), st[g]>>>(S, G[g]);
+                else
+                    waveTraceKernel<F><<<grid[g], BLOCK, stackBytes(), st[g]>>>(S, G[g]);
+                waveLogicKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, G[g]);
+                waveMaterialKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, G[g]);
+            }
         }
-        n += 3 * batch;
+        n += 3 * batch * nGroups;
+        if (nGroups == 2) {     /* join the second stream before reading the counter */
+            if ((e = cudaEventRecord(events[3], stream2)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(stream, events[3], 0)) != cudaSuccess) return e;
+        }
         e = cudaMemcpyAsync(hostDone + (k & 1), P.counters + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess)
             return e;
         e = cudaEventRecord(events[k & 1], stream);
         if (e != cudaSuccess)
             return e;
+        if (nGroups == 2) {     /* fork again for the next batch */
+            if ((e = cudaStreamWaitEvent(stream2, events[k & 1], 0)) != cudaSuccess) return e;
+        }
         if (k >= 1) {
             e = cudaEventSynchronize(events[(k - 1) & 1]);
             if (e != cudaSuccess)
@@ -697,6 +749,10 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
             if (hostDone[(k - 1) & 1] >= P.W.nSlots)
                 break;
         }
+    }
+    if (nGroups == 2) {     /* final join: everything queued on the second stream precedes what follows on `stream` */
+        if ((e = cudaEventRecord(events[3], stream2)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(stream, events[3], 0)) != cudaSuccess) return e;
     }
     *launches = n + (P.substreams == 1 ? 0 : 1);
     e = cudaGetLastError();
@@ -706,11 +762,11 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
 }
 
 cudaError_t launchWavefront(int features, const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream,
-        unsigned long long* hostDone, cudaEvent_t* events, int* launches)
+        cudaStream_t stream2, unsigned long long* hostDone, cudaEvent_t* events, int* launches)
 {
     if (features == 0)
-        return launchWavefrontT<0>(S, P, numSMs, stream, hostDone, events, launches);
-    return launchWavefrontT<F_MEDIA | F_ANIM | F_OPL>(S, P, numSMs, stream, hostDone, events, launches);
+        return launchWavefrontT<0>(S, P, numSMs, stream, stream2, hostDone, events, launches);
+    return launchWavefrontT<F_MEDIA | F_ANIM | F_OPL>(S, P, numSMs, stream, stream2, hostDone, events, launches);
 }
 
 cudaError_t launchQuery(int features, bool count, const DScene& S, const RenderParams& P,

@@ -11,9 +11,10 @@ namespace wptd {
  * (media, animations, optical path length tracking). */
 cudaError_t launchRender(int features, const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream, int* launches);
 
-/* Wavefront pipeline; P.W must point at allocated slot arrays. hostDone: 2 pinned counters; events: 2 events. */
+/* Wavefront pipeline; P.W must point at allocated slot arrays. stream2: an internal second stream;
+ * hostDone: 2 pinned counters; events: 4 events. */
 cudaError_t launchWavefront(int features, const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream,
-        unsigned long long* hostDone, cudaEvent_t* events, int* launches);
+        cudaStream_t stream2, unsigned long long* hostDone, cudaEvent_t* events, int* launches);
 
 /* origins == nullptr: pixel-centre camera rays of P (width*height rays). */
 cudaError_t launchQuery(int features, bool count, const DScene& S, const RenderParams& P,
