@@ -317,7 +317,7 @@ uint32_t waveSlotLimit()
 {
     const char* e = std::getenv("WPT_WAVE_SLOTS");
     long v = e ? std::atol(e) : 0;
-    return v > 0 ? uint32_t(v) : (1u << 20);
+    return v > 0 ? uint32_t(v) : (1u << 23);
 }
 
 int sceneFeatures(const wpt_scene* s, bool needOpl)

@@ -652,6 +652,12 @@ static int waveGroups()
     return (e && e[0] == '1') ? 1 : 2;
 }
 
+static bool wavePgridFull()
+{
+    const char* e = std::getenv("WPT_WAVE_PGRID_FULL");    /* experiment knob: 0 = the groups' trace launches share the resident CTAs */
+    return !(e && e[0] == '0');
+}
+
 static bool wavePlainTrace()
 {
     const char* e = std::getenv("WPT_WAVE_PLAIN_TRACE");   /* experiment knob: one ray per thread, no refill */
@@ -699,7 +705,7 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
         G[g] = slotGroup(P, uint32_t(g), first, count);
         grid[g] = (count + BLOCK - 1) / BLOCK;
         /* persistent trace kernel: the resident CTAs are shared between the groups */
-        pgrid[g] = (unsigned int)(numSMs * (perSM < 1 ? 1 : perSM)) / (unsigned int)nGroups;
+        pgrid[g] = (unsigned int)(numSMs * (perSM < 1 ? 1 : perSM)) / (unsigned int)(wavePgridFull() ? 1 : nGroups);
         if (pgrid[g] > grid[g])
             pgrid[g] = grid[g];
         if (pgrid[g] < 1)
