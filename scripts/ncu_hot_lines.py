@@ -1,12 +1,13 @@
 """Summarise `ncu --page source --print-source cuda,sass --csv` output: hottest source lines.
-usage: python scripts/ncu_hot_lines.py report.ncu-rep [top]"""
+usage: python scripts/ncu_hot_lines.py report.ncu-rep [top] [kernel-name regex]"""
 import csv
 import subprocess
 import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
+sel = ["--kernel-name", "regex:" + sys.argv[3], "--launch-count", "1"] if len(sys.argv) > 3 else []
+out = subprocess.run(["ncu", "-i", rep] + sel + ["--page", "source", "--print-source", "cuda,sass", "--csv"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur_file = "?"

@@ -35,6 +35,7 @@ SCENES = [
     ("furnace", 1.0, (64, 64), (64, 64, 10)),
     ("mixed", 1.0, (96, 64), (96, 64, 12)),
     ("synth", 0.004, (128, 72), (96, 54, 8)),
+    ("synth360", 0.004, (128, 128), (64, 64, 8)),     # C4: 360 degree top-bottom stereo camera
 ]
 
 
@@ -43,9 +44,21 @@ def raw(struct):
 
 
 def main():
+    if not sys.argv[1:]:
+        write_prng_kat()
+    write_scenes()
+
+
+def write_prng_kat():
     kat_seeds = np.array([0, 1, 42, 4095, 262143, 2073599, 0xFFFFFFFF], dtype=np.uint32)
     np.savez_compressed(os.path.join(OUT, "prng_kat.npz"), seeds=kat_seeds, values=refapi.prng_kat(kat_seeds, 16))
+
+
+def write_scenes():
+    only = sys.argv[1:]        # optional: regenerate just these scenes
     for name, scale, (hw, hh), (rw, rh, spp) in SCENES:
+        if only and name not in only:
+            continue
         view = refapi.View(name)
         scene = refapi.RefScene(name, scale, 0)
         scene.update_bvh(view.t0, view.t1)

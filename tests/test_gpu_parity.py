@@ -41,8 +41,16 @@ def test_primary_hits_reference_walk_is_bit_exact(gpu, name):
     h, w = g.z["hit_ids"].shape
     ids, dist = s.primary_hits(g.camera, w, h, g.t0, g.params.min_hit_distance, gpu.make_opts(traversal=REFERENCE))
     c = compare_hits(ids, dist, g.z["hit_ids"], g.z["hit_dist"])
-    assert c["wrong"] == 0 and c["near"] == 0 and c["ties"] == 0, c
     hit = g.z["hit_ids"] >= 0
+    if g.camera.surround_mode != 0:
+        # 180/360 degree cameras build the ray direction with sin/cos (camera.hpp:160-169); CUDA's sinf/cosf
+        # and glibc's differ by up to 2 ulp, so the rays are not bit-identical: same closest hits wherever the
+        # ray is not within rounding of a silhouette (allowed: 0.1 % of the rays), distances within 2e-5 relative
+        assert c["wrong"] + c["near"] + c["ties"] <= c["total"] // 1000, c
+        same = hit & (ids == g.z["hit_ids"])
+        assert np.allclose(dist[same], g.z["hit_dist"][same], rtol=2e-5, atol=0.0)
+        return
+    assert c["wrong"] == 0 and c["near"] == 0 and c["ties"] == 0, c
     assert np.array_equal(dist[hit].view(np.uint32), g.z["hit_dist"][hit].view(np.uint32))
 
 
@@ -54,11 +62,15 @@ def test_primary_hits_wide_walk(gpu, name):
     h, w = g.z["hit_ids"].shape
     ids, dist = s.primary_hits(g.camera, w, h, g.t0, g.params.min_hit_distance, gpu.make_opts(traversal=WIDE))
     c = compare_hits(ids, dist, g.z["hit_ids"], g.z["hit_dist"])
-    assert c["wrong"] == 0, c
     print(name, "wide walk vs reference:", c)
-    assert c["ties"] + c["near"] <= max(4, c["total"] // 500), c
     same = ids == g.z["hit_ids"]
     hit = same & (ids >= 0)
+    if g.camera.surround_mode != 0:      # sin/cos in the camera, see the reference-walk test
+        assert c["wrong"] + c["near"] + c["ties"] <= c["total"] // 1000, c
+        assert np.allclose(dist[hit], g.z["hit_dist"][hit], rtol=2e-5, atol=0.0)
+        return
+    assert c["wrong"] == 0, c
+    assert c["ties"] + c["near"] <= max(4, c["total"] // 500), c
     assert np.array_equal(dist[hit].view(np.uint32), g.z["hit_dist"][hit].view(np.uint32))
 
 

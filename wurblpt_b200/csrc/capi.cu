@@ -436,7 +436,7 @@ int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** out)
         WPT_CUDA(cudaEventCreateWithFlags(&s->evWave[i], cudaEventDisableTiming), "cudaEventCreate");
     WPT_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking), "cudaStreamCreate");
     WPT_CUDA(cudaMallocHost(&s->hostDone, 2 * sizeof(unsigned long long)), "allocate pinned counters");
-    WPT_CUDA(s->counters.reserve(16 * sizeof(unsigned long long)), "allocate counters");
+    WPT_CUDA(s->counters.reserve(wptd::CTR_WORDS * sizeof(unsigned long long)), "allocate counters");
     *out = s.release();
     return WPT_OK;
 }
@@ -646,7 +646,7 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
         P.partials = static_cast<float*>(s->partials.p);
     }
     P.counters = static_cast<unsigned long long*>(s->counters.p);
-    WPT_CUDA(cudaMemsetAsync(s->counters.p, 0, 16 * sizeof(unsigned long long), stream), "clear counters");
+    WPT_CUDA(cudaMemsetAsync(s->counters.p, 0, wptd::CTR_WORDS * sizeof(unsigned long long), stream), "clear counters");
 
     /* pipeline */
     int pipeline = o.pipeline;
@@ -702,14 +702,14 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
     if (!o.frame_on_device)
         WPT_CUDA(cudaMemcpyAsync(frame, s->frame.p, frameBytes, cudaMemcpyDeviceToHost, stream), "copy frame to host");
     if (timed) {
-        unsigned long long c[4] = { 0, 0, 0, 0 };
+        unsigned long long c[wptd::CTR_NESTED + 1] = { 0 };
         WPT_CUDA(cudaMemcpyAsync(c, s->counters.p, sizeof(c), cudaMemcpyDeviceToHost, stream), "copy counters");
         WPT_CUDA(cudaStreamSynchronize(stream), "render kernel");
         if (stats) {
             std::memset(stats, 0, sizeof(*stats));
-            stats->samples = c[1];
-            stats->rays = c[2];
-            stats->nested_queries = c[3];
+            stats->samples = c[wptd::CTR_SAMPLES];
+            stats->rays = c[wptd::CTR_RAYS];
+            stats->nested_queries = c[wptd::CTR_NESTED];
             stats->tiles = P.nLocalTiles;
             cudaEventElapsedTime(&stats->kernel_ms, s->evStart, s->evStop);
             stats->launches = uint32_t(launches);

@@ -88,9 +88,25 @@ struct WaveState {
     float4* nextDirHot; /* across a shadow query: next direction xyz, chosen hot spot reference */
     float4* pendRad;    /* across a shadow query: light sample to add if visible */
     float4* opl; float4* rayRi; float4* nextRi; float4* shadowRi;  /* F_OPL only */
-    uint32_t* queue;    /* slots whose surface hit is to be shaded this round */
+    uint32_t* queue;    /* nSlots entries filled by the trace kernel: slots whose surface hit is to be shaded from
+                           the front (material queue), all other answered queries from the back (logic queue) */
     uint32_t nSlots;
     uint32_t group;     /* slot group (0 or 1): selects the group's trace ticket / queue length counters */
+    uint32_t parity;    /* round parity: selects which of the two queue length counter sets this round fills */
+};
+
+/* Counter words (64 bit). Every hot counter has a 128-byte line of its own so that atomics on different
+ * counters do not meet in one L2 sector. */
+enum : int {
+    CTR_ITEM = 0,           /* work item ticket */
+    CTR_SAMPLES = 16,       /* samples started */
+    CTR_RAYS = 32,          /* closest-hit queries */
+    CTR_NESTED = 48,        /* nested medium boundary queries */
+    CTR_DONE = 64,          /* wavefront slots that found no item left */
+    CTR_TICKET = 80,        /* + 16 * group: slot ticket of the persistent trace kernel */
+    CTR_MATERIAL = 112,     /* + 16 * (2 * group + parity): material queue length */
+    CTR_LOGIC = 176,        /* + 16 * (2 * group + parity): logic queue length */
+    CTR_WORDS = 256
 };
 
 struct RenderParams {
@@ -127,8 +143,7 @@ struct RenderParams {
     /* output */
     float* frame;
     float* partials;                /* [pixel][sub-stream][3] partial sums when substreams > 1 */
-    unsigned long long* counters;   /* [0] item ticket, [1] samples, [2] rays, [3] nested queries, [4] slots exhausted,
-                                       [5+2g] trace ticket, [6+2g] material queue length of slot group g */
+    unsigned long long* counters;   /* CTR_WORDS words, see CTR_* */
     WaveState W;
     int32_t traversal;
 };

@@ -40,6 +40,12 @@ namespace wptd {
 #ifndef WPT_SHADE_MIN_BLOCKS
 #define WPT_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef WPT_LOGIC_MIN_BLOCKS
+#define WPT_LOGIC_MIN_BLOCKS WPT_SHADE_MIN_BLOCKS
+#endif
+#ifndef WPT_MATERIAL_MIN_BLOCKS
+#define WPT_MATERIAL_MIN_BLOCKS WPT_SHADE_MIN_BLOCKS
+#endif
 #ifndef WPT_LEAF_MIN
 #define WPT_LEAF_MIN 12     /* lanes that must be at a leaf before the persistent trace kernel runs a leaf round */
 #endif
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_MIN_BLOCKS) renderKernel(const __gr
             const int leader = __ffs(wantMask) - 1;
             unsigned int base = 0;
             if (int(lane) == leader)
-                base = (unsigned int)atomicAdd(P.counters + 0, (unsigned long long)__popc(wantMask));
+                base = (unsigned int)atomicAdd(P.counters + CTR_ITEM, (unsigned long long)__popc(wantMask));
             base = __shfl_sync(FULL, base, leader);
             if (ps.state == ST_IDLE && !exhausted) {
                 const unsigned int item = base + __popc(wantMask & laneBelow);
@@ -131,9 +137,9 @@ __global__ void __launch_bounds__(BLOCK, WPT_MIN_BLOCKS) renderKernel(const __gr
         nNested += __shfl_xor_sync(FULL, nNested, off);
     }
     if (lane == 0) {
-        atomicAdd(P.counters + 1, nSamples);
-        atomicAdd(P.counters + 2, nRays);
-        atomicAdd(P.counters + 3, nNested);
+        atomicAdd(P.counters + CTR_SAMPLES, nSamples);
+        atomicAdd(P.counters + CTR_RAYS, nRays);
+        atomicAdd(P.counters + CTR_NESTED, nNested);
     }
 }
 
@@ -243,10 +249,10 @@ WPT_DEV unsigned int refillSlot(const DScene& S, const RenderParams& P, PathStat
     unsigned int started = 0;
     while (ps.state == ST_NEW || ps.state == ST_IDLE) {
         if (ps.state == ST_IDLE) {
-            const unsigned int it = (unsigned int)atomicAdd(P.counters + 0, 1ull);
+            const unsigned int it = (unsigned int)atomicAdd(P.counters + CTR_ITEM, 1ull);
             if (it >= P.nItems) {
                 ps.state = ST_EXHAUSTED;
-                atomicAdd(P.counters + 4, 1ull);
+                atomicAdd(P.counters + CTR_DONE, 1ull);
                 break;
             }
             const WorkItem w = decodeItem(P, it);
@@ -262,90 +268,129 @@ WPT_DEV unsigned int refillSlot(const DScene& S, const RenderParams& P, PathStat
     return started;
 }
 
-/* Logic: everything after a query except shading a surface hit -- rays that left the scene, shadow-ray
- * results, Russian roulette, starting the next sample / item. Slots whose camera or bounce ray hit a
- * surface are appended to the material queue (one atomic per warp) and left to waveMaterialKernel. */
-template<int F>
-__global__ void __launch_bounds__(BLOCK, WPT_SHADE_MIN_BLOCKS) waveLogicKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+/* ---- per-group counters of the running round ---- */
+WPT_DEV unsigned long long* ctrTicket(const RenderParams& P) { return P.counters + CTR_TICKET + 16 * P.W.group; }
+WPT_DEV unsigned long long* ctrMaterial(const RenderParams& P, uint32_t parity) { return P.counters + CTR_MATERIAL + 16 * (2 * P.W.group + parity); }
+WPT_DEV unsigned long long* ctrLogic(const RenderParams& P, uint32_t parity) { return P.counters + CTR_LOGIC + 16 * (2 * P.W.group + parity); }
+
+/* Which kernel finishes an answered query: a camera or bounce ray that hit a surface which is still to
+ * be shaded goes to waveMaterialKernel (the case in which processLogic() returns true), everything
+ * else to waveLogicKernel. */
+enum { QUEUE_NONE = 0, QUEUE_MATERIAL = 1, QUEUE_LOGIC = 2 };
+WPT_DEV int queueOf(const RenderParams& P, int state, unsigned int pathComponent, uint32_t hitRef)
 {
-    const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
-    if (slot == 0)
-        P.counters[5 + 2 * P.W.group] = 0ull;       /* ticket counter of the next (persistent) trace launch */
-    bool needSurface = false;
-    bool live = false;
-    Ctx<F> ctx;
-    ctx.nested = 0;
-    ctx.nodes = ctx.leaves = 0;
-    PathState ps;
-    unsigned int newSamples = 0;
-    if (slot < P.W.nSlots) {
-        const int4 item = P.W.item[slot];
-        if (slotState(item.z) != ST_EXHAUSTED) {
-            live = true;
-            loadItem<F>(P, slot, item, ps, ctx);
-            if (ps.state == ST_MAIN || ps.state == ST_SHADOW_HOT || ps.state == ST_SHADOW_ENV) {
-                loadPath<F>(P, slot, ps);
-                const uint2 hw = P.W.hit[slot];
-                Hit hit;
-                hit.a = __uint_as_float(hw.x);
-                hit.ref = hw.y;
-                animationCacheInit<F>(S, ctx, ps.walkRay.time);
-                const RayHelper h = makeRayHelper(ps.walkRay);
-                needSurface = processLogic<F>(S, P, ps, ctx, hit, h);
-            }
-            if (needSurface) {
-                /* only the path lengths changed */
-                P.W.rayD[slot] = f4(ps.walkRay.d, ps.pathLength);
-                if (F & F_OPL)
-                    P.W.opl[slot] = ps.opl;
-            } else {
-                newSamples = refillSlot<F>(S, P, ps, ctx);
-                storeSlot<F>(P, slot, ps, ctx);
-            }
-        }
-    }
-    /* material queue: one atomic per warp */
-    const unsigned pushMask = __ballot_sync(0xFFFFFFFFu, needSurface);
-    if (pushMask != 0u) {
-        unsigned int base = 0;
-        if (lane == 0)
-            base = (unsigned int)atomicAdd(P.counters + 6 + 2 * P.W.group, (unsigned long long)__popc(pushMask));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (needSurface)
-            P.W.queue[base + __popc(pushMask & ((1u << lane) - 1u))] = slot;
-    }
-    (void)live;
-    if (newSamples)
-        atomicAdd(P.counters + 1, (unsigned long long)newSamples);
+    return (state == ST_MAIN && hitRef != NO_HIT && pathComponent + 1 < P.maxPathComponents) ? QUEUE_MATERIAL : QUEUE_LOGIC;
 }
 
-/* Material: shade the surface hits collected in the queue (dense: every lane of a warp has one). */
+/* Appends the lanes' slots to the round's queues: material entries grow from the front of P.W.queue,
+ * logic entries from its back. One atomic per warp and queue. Called by all 32 lanes. */
+WPT_DEV void pushQueues(const RenderParams& P, unsigned lane, int kind, unsigned int slot)
+{
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const unsigned matMask = __ballot_sync(FULL, kind == QUEUE_MATERIAL);
+    const unsigned logMask = __ballot_sync(FULL, kind == QUEUE_LOGIC);
+    const unsigned below = (1u << lane) - 1u;
+    if (matMask != 0u) {
+        unsigned int base = 0;
+        if (lane == 0)
+            base = (unsigned int)atomicAdd(ctrMaterial(P, P.W.parity), (unsigned long long)__popc(matMask));
+        base = __shfl_sync(FULL, base, 0);
+        if (kind == QUEUE_MATERIAL)
+            P.W.queue[base + __popc(matMask & below)] = slot;
+    }
+    if (logMask != 0u) {
+        unsigned int base = 0;
+        if (lane == 0)
+            base = (unsigned int)atomicAdd(ctrLogic(P, P.W.parity), (unsigned long long)__popc(logMask));
+        base = __shfl_sync(FULL, base, 0);
+        if (kind == QUEUE_LOGIC)
+            P.W.queue[P.W.nSlots - 1u - (base + __popc(logMask & below))] = slot;
+    }
+}
+
+WPT_DEV void countSamples(const RenderParams& P, unsigned int newSamples)
+{
+    const unsigned int n = __reduce_add_sync(0xFFFFFFFFu, newSamples);
+    if ((threadIdx.x & 31u) == 0u && n != 0u)
+        atomicAdd(P.counters + CTR_SAMPLES, (unsigned long long)n);
+}
+
+/* First launch of a frame: every slot fetches a work item and its first camera ray. */
 template<int F>
-__global__ void __launch_bounds__(BLOCK, WPT_SHADE_MIN_BLOCKS) waveMaterialKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+__global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveInitKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+{
+    const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
+    unsigned int newSamples = 0;
+    if (slot < P.W.nSlots) {
+        Ctx<F> ctx;
+        ctx.nested = 0;
+        ctx.nodes = ctx.leaves = 0;
+        PathState ps;
+        loadItem<F>(P, slot, make_int4(-1, -1, -1, -1), ps, ctx);
+        newSamples = refillSlot<F>(S, P, ps, ctx);
+        storeSlot<F>(P, slot, ps, ctx);
+    }
+    countSamples(P, newSamples);
+}
+
+/* Logic: everything after a query except shading a surface hit -- rays that left the scene, shadow-ray
+ * results, Russian roulette -- then the next sample / item for slots whose path ended. Works through
+ * the logic queue the trace kernel filled (dense: every lane of a warp has an entry). */
+template<int F>
+__global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveLogicKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
     const unsigned int i = blockIdx.x * BLOCK + threadIdx.x;
-    const unsigned int count = (unsigned int)P.counters[6 + 2 * P.W.group];
-    if (i >= count)
-        return;
-    const unsigned int slot = P.W.queue[i];
-    Ctx<F> ctx;
-    ctx.nested = 0;
-    ctx.nodes = ctx.leaves = 0;
-    PathState ps;
-    loadItem<F>(P, slot, P.W.item[slot], ps, ctx);
-    loadPath<F>(P, slot, ps);
-    const uint2 hw = P.W.hit[slot];
-    Hit hit;
-    hit.a = __uint_as_float(hw.x);
-    hit.ref = hw.y;
-    animationCacheInit<F>(S, ctx, ps.walkRay.time);
-    const RayHelper h = makeRayHelper(ps.walkRay);
-    surfaceShade<F>(S, P, ps, ctx, hit, h);
-    const unsigned int newSamples = refillSlot<F>(S, P, ps, ctx);
-    storeSlot<F>(P, slot, ps, ctx);
-    if (newSamples)
-        atomicAdd(P.counters + 1, (unsigned long long)newSamples);
+    if (i == 0)
+        *ctrTicket(P) = 0ull;       /* slot ticket of the next (persistent) trace launch */
+    const unsigned int count = (unsigned int)*ctrLogic(P, P.W.parity);
+    unsigned int newSamples = 0;
+    if (i < count) {
+        const unsigned int slot = P.W.queue[P.W.nSlots - 1u - i];
+        Ctx<F> ctx;
+        ctx.nested = 0;
+        ctx.nodes = ctx.leaves = 0;
+        PathState ps;
+        loadItem<F>(P, slot, P.W.item[slot], ps, ctx);
+        loadPath<F>(P, slot, ps);
+        const uint2 hw = P.W.hit[slot];
+        Hit hit;
+        hit.a = __uint_as_float(hw.x);
+        hit.ref = hw.y;
+        animationCacheInit<F>(S, ctx, ps.walkRay.time);
+        const RayHelper h = makeRayHelper(ps.walkRay);
+        processLogic<F>(S, P, ps, ctx, hit, h);
+        newSamples = refillSlot<F>(S, P, ps, ctx);
+        storeSlot<F>(P, slot, ps, ctx);
+    }
+    countSamples(P, newSamples);
+}
+
+/* Material: shade the surface hits collected in the material queue (dense as well). */
+template<int F>
+__global__ void __launch_bounds__(BLOCK, WPT_MATERIAL_MIN_BLOCKS) waveMaterialKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+{
+    const unsigned int i = blockIdx.x * BLOCK + threadIdx.x;
+    const unsigned int count = (unsigned int)*ctrMaterial(P, P.W.parity);
+    unsigned int newSamples = 0;
+    if (i < count) {
+        const unsigned int slot = P.W.queue[i];
+        Ctx<F> ctx;
+        ctx.nested = 0;
+        ctx.nodes = ctx.leaves = 0;
+        PathState ps;
+        loadItem<F>(P, slot, P.W.item[slot], ps, ctx);
+        loadPath<F>(P, slot, ps);
+        const uint2 hw = P.W.hit[slot];
+        Hit hit;
+        hit.a = __uint_as_float(hw.x);
+        hit.ref = hw.y;
+        animationCacheInit<F>(S, ctx, ps.walkRay.time);
+        const RayHelper h = makeRayHelper(ps.walkRay);
+        processHit<F>(S, P, ps, ctx, hit, h);
+        newSamples = refillSlot<F>(S, P, ps, ctx);
+        storeSlot<F>(P, slot, ps, ctx);
+    }
+    countSamples(P, newSamples);
 }
 
 /* Trace: the closest-hit query of every slot that has one pending. */
@@ -355,14 +400,18 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
     extern __shared__ uint2 smStackAll[];
     uint2* smStack = smStackAll + threadIdx.x;
     const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
-    if (slot == 0)
-        P.counters[6 + 2 * P.W.group] = 0ull;       /* length of the material queue the next logic launch fills */
+    if (slot == 0) {        /* the queue lengths the NEXT round counts in (this round's were cleared a round ago) */
+        *ctrMaterial(P, P.W.parity ^ 1u) = 0ull;
+        *ctrLogic(P, P.W.parity ^ 1u) = 0ull;
+    }
     unsigned int traced = 0;
+    int kind = QUEUE_NONE;
     Ctx<F> ctx;
     ctx.nested = 0;
     ctx.nodes = ctx.leaves = 0;
     if (slot < P.W.nSlots) {
-        const int state = slotState(P.W.item[slot].z);
+        const int4 item = P.W.item[slot];
+        const int state = slotState(item.z);
         if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV) {
             const float4 o = P.W.rayO[slot], d = P.W.rayD[slot];
             Ray ray;
@@ -378,16 +427,18 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
             if (F & F_MEDIA)
                 P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
             traced = 1;
+            kind = queueOf(P, state, (unsigned int)item.w, hit.ref);
         }
     }
+    pushQueues(P, threadIdx.x & 31u, kind, slot);
     /* statistics: one atomic per warp */
     const unsigned int n = __reduce_add_sync(0xFFFFFFFFu, traced);
     const unsigned int q = __reduce_add_sync(0xFFFFFFFFu, ctx.nested);
     if ((threadIdx.x & 31) == 0) {
         if (n)
-            atomicAdd(P.counters + 2, (unsigned long long)n);
+            atomicAdd(P.counters + CTR_RAYS, (unsigned long long)n);
         if (q)
-            atomicAdd(P.counters + 3, (unsigned long long)q);
+            atomicAdd(P.counters + CTR_NESTED, (unsigned long long)q);
     }
 }
 
@@ -406,10 +457,15 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     ctx.nested = 0;
     ctx.nodes = ctx.leaves = 0;
     unsigned int traced = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        P.counters[6 + 2 * P.W.group] = 0ull;       /* length of the material queue the next logic launch fills */
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  /* the queue lengths the NEXT round counts in */
+        *ctrMaterial(P, P.W.parity ^ 1u) = 0ull;
+        *ctrLogic(P, P.W.parity ^ 1u) = 0ull;
+    }
 
     unsigned int slot = 0;
+    int pending = QUEUE_NONE;       /* answered query not yet entered in a queue */
+    int state = ST_IDLE;
+    unsigned int pathComponent = 0;
     bool active = false, exhausted = false;
     Ray ray;
     ray.o = f3(0.0f); ray.d = f3(0.0f, 0.0f, 1.0f); ray.time = 0.0f;
@@ -436,10 +492,13 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
         const unsigned wantMask = __ballot_sync(FULL, !active && !exhausted);
         const unsigned busyMask = __ballot_sync(FULL, active);
         if (wantMask != 0u && (__popc(wantMask) >= REFILL_MIN || busyMask == 0u)) {
+            /* the lanes that finished since the last refill enter their slots in the shade queues */
+            pushQueues(P, lane, pending, slot);
+            pending = QUEUE_NONE;
             if (warpNext >= warpEnd && !drained) {
                 unsigned int base = 0;
                 if (lane == 0)
-                    base = (unsigned int)atomicAdd(P.counters + 5 + 2 * P.W.group, (unsigned long long)CHUNK);
+                    base = (unsigned int)atomicAdd(ctrTicket(P), (unsigned long long)CHUNK);
                 base = __shfl_sync(FULL, base, 0);
                 warpNext = base;
                 warpEnd = min(base + CHUNK, P.W.nSlots);
@@ -453,7 +512,9 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
             if (!active && !exhausted) {
                 if (rank < avail) {
                     const unsigned int s = warpNext + rank;
-                    const int state = slotState(P.W.item[s].z);
+                    const int4 item = P.W.item[s];
+                    state = slotState(item.z);
+                    pathComponent = (unsigned int)item.w;
                     if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV) {
                         const float4 o = P.W.rayO[s], d = P.W.rayD[s];
                         ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
@@ -523,6 +584,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
             if (F & F_MEDIA)
                 P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
             active = false;
+            pending = queueOf(P, state, pathComponent, best.hit.ref);
             traced++;
         }
     }
@@ -530,9 +592,9 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     const unsigned int q = __reduce_add_sync(FULL, ctx.nested);
     if (lane == 0) {
         if (n)
-            atomicAdd(P.counters + 2, (unsigned long long)n);
+            atomicAdd(P.counters + CTR_RAYS, (unsigned long long)n);
         if (q)
-            atomicAdd(P.counters + 3, (unsigned long long)q);
+            atomicAdd(P.counters + CTR_NESTED, (unsigned long long)q);
     }
 }
 
@@ -695,14 +757,16 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
         return e;
     const bool persistent = (P.traversal == WPT_TRAVERSAL_WIDE) && !wavePlainTrace();
     const int nGroups = (waveGroups() >= 2 && P.W.nSlots >= 4096) ? 2 : 1;
-    RenderParams G[2];
+    RenderParams G[2][2];       /* [group][round parity] */
     unsigned int grid[2], pgrid[2];
     cudaStream_t st[2] = { stream, stream2 };
     const uint32_t half = (nGroups == 2 ? (P.W.nSlots / 2 + BLOCK - 1) / BLOCK * BLOCK : P.W.nSlots);
     for (int g = 0; g < nGroups; g++) {
         const uint32_t first = (g == 0 ? 0 : half);
         const uint32_t count = (g == 0 ? half : P.W.nSlots - half);
-        G[g] = slotGroup(P, uint32_t(g), first, count);
+        G[g][0] = G[g][1] = slotGroup(P, uint32_t(g), first, count);
+        G[g][0].W.parity = 0;
+        G[g][1].W.parity = 1;
         grid[g] = (count + BLOCK - 1) / BLOCK;
         /* persistent trace kernel: the resident CTAs are shared between the groups */
         pgrid[g] = (unsigned int)(numSMs * (perSM < 1 ? 1 : perSM)) / (unsigned int)(wavePgridFull() ? 1 : nGroups);
@@ -720,18 +784,19 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
         if ((e = cudaStreamWaitEvent(stream2, events[2], 0)) != cudaSuccess) return e;
     }
     for (int g = 0; g < nGroups; g++)
-        waveLogicKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, G[g]);     /* gives every slot its first camera ray */
+        waveInitKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, G[g][0]);   /* gives every slot its first camera ray */
     n += nGroups;
     hostDone[0] = hostDone[1] = 0;
     for (int k = 0;; k++) {
         for (int i = 0; i < batch; i++) {
             for (int g = 0; g < nGroups; g++) {
+                const RenderParams& R = G[g][i & 1];    /* `batch` is even: the round parity is i & 1 */
                 if (persistent)
-                    waveTracePersistentKernel<F><<<pgrid[g], BLOCK, stackBytes(), st[g]>>>(S, G[g]);
+                    waveTracePersistentKernel<F><<<pgrid[g], BLOCK, stackBytes(), st[g]>>>(S, R);
                 else
-                    waveTraceKernel<F><<<grid[g], BLOCK, stackBytes(), st[g]>>>(S, G[g]);
-                waveLogicKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, G[g]);
-                waveMaterialKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, G[g]);
+                    waveTraceKernel<F><<<grid[g], BLOCK, stackBytes(), st[g]>>>(S, R);
+                waveLogicKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, R);
+                waveMaterialKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, R);
             }
         }
         n += 3 * batch * nGroups;
@@ -739,7 +804,7 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
             if ((e = cudaEventRecord(events[3], stream2)) != cudaSuccess) return e;
             if ((e = cudaStreamWaitEvent(stream, events[3], 0)) != cudaSuccess) return e;
         }
-        e = cudaMemcpyAsync(hostDone + (k & 1), P.counters + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+        e = cudaMemcpyAsync(hostDone + (k & 1), P.counters + CTR_DONE, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
         if (e != cudaSuccess)
             return e;
         e = cudaEventRecord(events[k & 1], stream);
