@@ -252,6 +252,7 @@ void refreshDeviceScene(wpt_scene* s)
     d.envMs = s->envMs.as<int32_t>();
     d.envMcs = s->envMcs.as<float>();
     d.root4 = h.root4;
+    d.prefetchLeaves = (h.triData.size() * sizeof(float) > (128u << 10)) ? 1 : 0;
     d.nHot = uint32_t(h.hotSpotRefs.size());
     d.nAnimations = uint32_t(h.animations.size());
     d.envType = h.env.type;
@@ -680,7 +681,7 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
         P.W.rayRi = static_cast<float4*>(s->wave[11].p);
         P.W.nextRi = static_cast<float4*>(s->wave[12].p);
         P.W.shadowRi = static_cast<float4*>(s->wave[13].p);
-        WPT_CUDA(s->wave[14].reserve(n * sizeof(uint32_t)), "allocate material queue");
+        WPT_CUDA(s->wave[14].reserve(n * sizeof(uint32_t)), "allocate shade queues");
         P.W.queue = static_cast<uint32_t*>(s->wave[14].p);
         P.W.group = 0;
         if (features == 0)

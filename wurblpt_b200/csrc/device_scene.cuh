@@ -66,6 +66,7 @@ struct DScene {
     const int32_t* envMs;
     const float* envMcs;
     int32_t root4;              /* encoded child of the 4-wide tree */
+    int32_t prefetchLeaves;     /* triangle data is larger than an SM's L1: ask for a leaf's triangles on arrival */
     uint32_t nHot;
     uint32_t nAnimations;
     int32_t envType, envCompat, envN;
@@ -88,11 +89,10 @@ struct WaveState {
     float4* nextDirHot; /* across a shadow query: next direction xyz, chosen hot spot reference */
     float4* pendRad;    /* across a shadow query: light sample to add if visible */
     float4* opl; float4* rayRi; float4* nextRi; float4* shadowRi;  /* F_OPL only */
-    uint32_t* queue;    /* nSlots entries filled by the trace kernel: slots whose surface hit is to be shaded from
+    uint32_t* queue;    /* nSlots entries filled by the sort kernel: slots whose surface hit is to be shaded from
                            the front (material queue), all other answered queries from the back (logic queue) */
     uint32_t nSlots;
     uint32_t group;     /* slot group (0 or 1): selects the group's trace ticket / queue length counters */
-    uint32_t parity;    /* round parity: selects which of the two queue length counter sets this round fills */
 };
 
 /* Counter words (64 bit). Every hot counter has a 128-byte line of its own so that atomics on different
@@ -104,9 +104,9 @@ enum : int {
     CTR_NESTED = 48,        /* nested medium boundary queries */
     CTR_DONE = 64,          /* wavefront slots that found no item left */
     CTR_TICKET = 80,        /* + 16 * group: slot ticket of the persistent trace kernel */
-    CTR_MATERIAL = 112,     /* + 16 * (2 * group + parity): material queue length */
-    CTR_LOGIC = 176,        /* + 16 * (2 * group + parity): logic queue length */
-    CTR_WORDS = 256
+    CTR_MATERIAL = 112,     /* + 16 * group: material queue length */
+    CTR_LOGIC = 144,        /* + 16 * group: logic queue length */
+    CTR_WORDS = 176
 };
 
 struct RenderParams {

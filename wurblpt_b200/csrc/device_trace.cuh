@@ -526,6 +526,20 @@ WPT_DEV void wideLeaf(const DScene& S, uint32_t ref, const Ray& ray, const RayHe
     }
 }
 
+/* Asks for the triangle data of a leaf the walk has just arrived at; the lanes of the persistent trace
+ * kernel then wait a few iterations for their leaf round (see there), which covers the fetch. */
+WPT_DEV void prefetchLeaf(const DScene& S, uint32_t ref)
+{
+    const uint32_t type = ref >> REF_TYPE_SHIFT;
+    if (type == PRIM_TRIANGLE_RUN || type == PRIM_TRIANGLE) {
+        const uint32_t first = (type == PRIM_TRIANGLE_RUN ? (ref & RUN_SLOT_MASK) : (ref & REF_SLOT_MASK));
+        const uint32_t count = (type == PRIM_TRIANGLE_RUN ? ((ref >> RUN_COUNT_SHIFT) & 3u) + 1u : 1u);
+        const float4* p = S.tri + size_t(first) * 3;
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 3u * count - 1u));
+    }
+}
+
 /* Closest hit under (amin, amax), amin > 0.
  *
  * "while-while" form (Aila & Laine 2009): an inner loop that only descends through inner nodes,

@@ -46,6 +46,9 @@ namespace wptd {
 #ifndef WPT_MATERIAL_MIN_BLOCKS
 #define WPT_MATERIAL_MIN_BLOCKS WPT_SHADE_MIN_BLOCKS
 #endif
+#ifndef WPT_PREFETCH_LEAF
+#define WPT_PREFETCH_LEAF 1
+#endif
 #ifndef WPT_LEAF_MIN
 #define WPT_LEAF_MIN 12     /* lanes that must be at a leaf before the persistent trace kernel runs a leaf round */
 #endif
@@ -268,44 +271,72 @@ WPT_DEV unsigned int refillSlot(const DScene& S, const RenderParams& P, PathStat
     return started;
 }
 
-/* ---- per-group counters of the running round ---- */
+/* ---- per-group counters ---- */
 WPT_DEV unsigned long long* ctrTicket(const RenderParams& P) { return P.counters + CTR_TICKET + 16 * P.W.group; }
-WPT_DEV unsigned long long* ctrMaterial(const RenderParams& P, uint32_t parity) { return P.counters + CTR_MATERIAL + 16 * (2 * P.W.group + parity); }
-WPT_DEV unsigned long long* ctrLogic(const RenderParams& P, uint32_t parity) { return P.counters + CTR_LOGIC + 16 * (2 * P.W.group + parity); }
+WPT_DEV unsigned long long* ctrMaterial(const RenderParams& P) { return P.counters + CTR_MATERIAL + 16 * P.W.group; }
+WPT_DEV unsigned long long* ctrLogic(const RenderParams& P) { return P.counters + CTR_LOGIC + 16 * P.W.group; }
 
 /* Which kernel finishes an answered query: a camera or bounce ray that hit a surface which is still to
  * be shaded goes to waveMaterialKernel (the case in which processLogic() returns true), everything
  * else to waveLogicKernel. */
 enum { QUEUE_NONE = 0, QUEUE_MATERIAL = 1, QUEUE_LOGIC = 2 };
-WPT_DEV int queueOf(const RenderParams& P, int state, unsigned int pathComponent, uint32_t hitRef)
+WPT_DEV int queueOf(const RenderParams& P, int4 item, uint32_t hitRef)
 {
-    return (state == ST_MAIN && hitRef != NO_HIT && pathComponent + 1 < P.maxPathComponents) ? QUEUE_MATERIAL : QUEUE_LOGIC;
+    const int state = slotState(item.z);
+    if (state != ST_MAIN && state != ST_SHADOW_HOT && state != ST_SHADOW_ENV)
+        return QUEUE_NONE;      /* idle or retired slot: no query was pending */
+    return (state == ST_MAIN && hitRef != NO_HIT && (unsigned int)item.w + 1u < P.maxPathComponents) ? QUEUE_MATERIAL : QUEUE_LOGIC;
 }
 
-/* Appends the lanes' slots to the round's queues: material entries grow from the front of P.W.queue,
- * logic entries from its back. One atomic per warp and queue. Called by all 32 lanes. */
-WPT_DEV void pushQueues(const RenderParams& P, unsigned lane, int kind, unsigned int slot)
+/* Sort: after the trace kernel, every warp looks at a window of consecutive slots and appends the ones
+ * with an answered query to the material queue (front of W.queue) or the logic queue (back of
+ * W.queue). Entries stay in slot order inside a window, so a warp of a shade kernel reads near
+ * neighbours in the slot arrays (whole sectors) and every one of its lanes has work. Two atomics per
+ * window. */
+constexpr unsigned int SORT_WINDOW = 256;       /* slots per warp */
+constexpr unsigned int SORT_BLOCK = 128;
+
+__global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_constant__ RenderParams P)
 {
+    __shared__ uint32_t lists[SORT_BLOCK / 32][2][SORT_WINDOW];
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    const unsigned matMask = __ballot_sync(FULL, kind == QUEUE_MATERIAL);
-    const unsigned logMask = __ballot_sync(FULL, kind == QUEUE_LOGIC);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned below = (1u << lane) - 1u;
-    if (matMask != 0u) {
-        unsigned int base = 0;
-        if (lane == 0)
-            base = (unsigned int)atomicAdd(ctrMaterial(P, P.W.parity), (unsigned long long)__popc(matMask));
-        base = __shfl_sync(FULL, base, 0);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        *ctrTicket(P) = 0ull;       /* slot ticket of the next (persistent) trace launch */
+    uint32_t* matList = lists[warp][0];
+    uint32_t* logList = lists[warp][1];
+    const unsigned int windowBase = (blockIdx.x * (SORT_BLOCK / 32u) + warp) * SORT_WINDOW;
+    unsigned int nMat = 0, nLog = 0;
+#pragma unroll
+    for (unsigned int k = 0; k < SORT_WINDOW / 32u; k++) {
+        const unsigned int slot = windowBase + k * 32u + lane;
+        int kind = QUEUE_NONE;
+        if (slot < P.W.nSlots)
+            kind = queueOf(P, P.W.item[slot], P.W.hit[slot].y);
+        const unsigned matMask = __ballot_sync(FULL, kind == QUEUE_MATERIAL);
+        const unsigned logMask = __ballot_sync(FULL, kind == QUEUE_LOGIC);
         if (kind == QUEUE_MATERIAL)
-            P.W.queue[base + __popc(matMask & below)] = slot;
-    }
-    if (logMask != 0u) {
-        unsigned int base = 0;
-        if (lane == 0)
-            base = (unsigned int)atomicAdd(ctrLogic(P, P.W.parity), (unsigned long long)__popc(logMask));
-        base = __shfl_sync(FULL, base, 0);
+            matList[nMat + __popc(matMask & below)] = slot;
         if (kind == QUEUE_LOGIC)
-            P.W.queue[P.W.nSlots - 1u - (base + __popc(logMask & below))] = slot;
+            logList[nLog + __popc(logMask & below)] = slot;
+        nMat += __popc(matMask);
+        nLog += __popc(logMask);
     }
+    __syncwarp();
+    unsigned int matBase = 0, logBase = 0;
+    if (lane == 0) {
+        if (nMat)
+            matBase = (unsigned int)atomicAdd(ctrMaterial(P), (unsigned long long)nMat);
+        if (nLog)
+            logBase = (unsigned int)atomicAdd(ctrLogic(P), (unsigned long long)nLog);
+    }
+    matBase = __shfl_sync(FULL, matBase, 0);
+    logBase = __shfl_sync(FULL, logBase, 0);
+    for (unsigned int e = lane; e < nMat; e += 32u)
+        P.W.queue[matBase + e] = matList[e];
+    for (unsigned int e = lane; e < nLog; e += 32u)
+        P.W.queue[P.W.nSlots - 1u - (logBase + e)] = logList[e];
 }
 
 WPT_DEV void countSamples(const RenderParams& P, unsigned int newSamples)
@@ -334,15 +365,13 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveInitKernel(co
 }
 
 /* Logic: everything after a query except shading a surface hit -- rays that left the scene, shadow-ray
- * results, Russian roulette -- then the next sample / item for slots whose path ended. Works through
- * the logic queue the trace kernel filled (dense: every lane of a warp has an entry). */
+ * results, Russian roulette -- then the next sample / item for slots whose path ended. One thread per
+ * entry of the logic queue. */
 template<int F>
 __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveLogicKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
     const unsigned int i = blockIdx.x * BLOCK + threadIdx.x;
-    if (i == 0)
-        *ctrTicket(P) = 0ull;       /* slot ticket of the next (persistent) trace launch */
-    const unsigned int count = (unsigned int)*ctrLogic(P, P.W.parity);
+    const unsigned int count = (unsigned int)*ctrLogic(P);
     unsigned int newSamples = 0;
     if (i < count) {
         const unsigned int slot = P.W.queue[P.W.nSlots - 1u - i];
@@ -365,12 +394,12 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveLogicKernel(c
     countSamples(P, newSamples);
 }
 
-/* Material: shade the surface hits collected in the material queue (dense as well). */
+/* Material: shade the surface hits of camera and bounce rays. One thread per entry of the material queue. */
 template<int F>
 __global__ void __launch_bounds__(BLOCK, WPT_MATERIAL_MIN_BLOCKS) waveMaterialKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
     const unsigned int i = blockIdx.x * BLOCK + threadIdx.x;
-    const unsigned int count = (unsigned int)*ctrMaterial(P, P.W.parity);
+    const unsigned int count = (unsigned int)*ctrMaterial(P);
     unsigned int newSamples = 0;
     if (i < count) {
         const unsigned int slot = P.W.queue[i];
@@ -400,18 +429,16 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
     extern __shared__ uint2 smStackAll[];
     uint2* smStack = smStackAll + threadIdx.x;
     const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
-    if (slot == 0) {        /* the queue lengths the NEXT round counts in (this round's were cleared a round ago) */
-        *ctrMaterial(P, P.W.parity ^ 1u) = 0ull;
-        *ctrLogic(P, P.W.parity ^ 1u) = 0ull;
+    if (slot == 0) {        /* queue lengths of this round (the sort kernel that follows counts them up) */
+        *ctrMaterial(P) = 0ull;
+        *ctrLogic(P) = 0ull;
     }
     unsigned int traced = 0;
-    int kind = QUEUE_NONE;
     Ctx<F> ctx;
     ctx.nested = 0;
     ctx.nodes = ctx.leaves = 0;
     if (slot < P.W.nSlots) {
-        const int4 item = P.W.item[slot];
-        const int state = slotState(item.z);
+        const int state = slotState(P.W.item[slot].z);
         if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV) {
             const float4 o = P.W.rayO[slot], d = P.W.rayD[slot];
             Ray ray;
@@ -427,10 +454,8 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
             if (F & F_MEDIA)
                 P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
             traced = 1;
-            kind = queueOf(P, state, (unsigned int)item.w, hit.ref);
         }
     }
-    pushQueues(P, threadIdx.x & 31u, kind, slot);
     /* statistics: one atomic per warp */
     const unsigned int n = __reduce_add_sync(0xFFFFFFFFu, traced);
     const unsigned int q = __reduce_add_sync(0xFFFFFFFFu, ctx.nested);
@@ -457,15 +482,12 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     ctx.nested = 0;
     ctx.nodes = ctx.leaves = 0;
     unsigned int traced = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  /* the queue lengths the NEXT round counts in */
-        *ctrMaterial(P, P.W.parity ^ 1u) = 0ull;
-        *ctrLogic(P, P.W.parity ^ 1u) = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  /* queue lengths of this round (the sort kernel that follows counts them up) */
+        *ctrMaterial(P) = 0ull;
+        *ctrLogic(P) = 0ull;
     }
 
     unsigned int slot = 0;
-    int pending = QUEUE_NONE;       /* answered query not yet entered in a queue */
-    int state = ST_IDLE;
-    unsigned int pathComponent = 0;
     bool active = false, exhausted = false;
     Ray ray;
     ray.o = f3(0.0f); ray.d = f3(0.0f, 0.0f, 1.0f); ray.time = 0.0f;
@@ -492,9 +514,6 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
         const unsigned wantMask = __ballot_sync(FULL, !active && !exhausted);
         const unsigned busyMask = __ballot_sync(FULL, active);
         if (wantMask != 0u && (__popc(wantMask) >= REFILL_MIN || busyMask == 0u)) {
-            /* the lanes that finished since the last refill enter their slots in the shade queues */
-            pushQueues(P, lane, pending, slot);
-            pending = QUEUE_NONE;
             if (warpNext >= warpEnd && !drained) {
                 unsigned int base = 0;
                 if (lane == 0)
@@ -512,9 +531,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
             if (!active && !exhausted) {
                 if (rank < avail) {
                     const unsigned int s = warpNext + rank;
-                    const int4 item = P.W.item[s];
-                    state = slotState(item.z);
-                    pathComponent = (unsigned int)item.w;
+                    const int state = slotState(P.W.item[s].z);
                     if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV) {
                         const float4 o = P.W.rayO[s], d = P.W.rayD[s];
                         ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
@@ -579,12 +596,15 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
             wideLeaf<F>(S, uint32_t(~cur), ray, h, amin, P.minHit, ctx, best);
             cur = popNext(st, best.hit.a);
         }
+#if WPT_PREFETCH_LEAF
+        if (S.prefetchLeaves && cur < 0 && ((!leafRound && atInner) || (leafRound && atLeaf)))
+            prefetchLeaf(S, uint32_t(~cur));
+#endif
         if (cur == EMPTY_CHILD) {
             P.W.hit[slot] = make_uint2(__float_as_uint(best.hit.a), best.hit.ref);
             if (F & F_MEDIA)
                 P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
             active = false;
-            pending = queueOf(P, state, pathComponent, best.hit.ref);
             traced++;
         }
     }
@@ -757,16 +777,15 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
         return e;
     const bool persistent = (P.traversal == WPT_TRAVERSAL_WIDE) && !wavePlainTrace();
     const int nGroups = (waveGroups() >= 2 && P.W.nSlots >= 4096) ? 2 : 1;
-    RenderParams G[2][2];       /* [group][round parity] */
-    unsigned int grid[2], pgrid[2];
+    RenderParams G[2];
+    unsigned int grid[2], sgrid[2], pgrid[2];
     cudaStream_t st[2] = { stream, stream2 };
     const uint32_t half = (nGroups == 2 ? (P.W.nSlots / 2 + BLOCK - 1) / BLOCK * BLOCK : P.W.nSlots);
     for (int g = 0; g < nGroups; g++) {
         const uint32_t first = (g == 0 ? 0 : half);
         const uint32_t count = (g == 0 ? half : P.W.nSlots - half);
-        G[g][0] = G[g][1] = slotGroup(P, uint32_t(g), first, count);
-        G[g][0].W.parity = 0;
-        G[g][1].W.parity = 1;
+        G[g] = slotGroup(P, uint32_t(g), first, count);
+        sgrid[g] = (count + SORT_WINDOW * (SORT_BLOCK / 32u) - 1u) / (SORT_WINDOW * (SORT_BLOCK / 32u));   /* sort kernel */
         grid[g] = (count + BLOCK - 1) / BLOCK;
         /* persistent trace kernel: the resident CTAs are shared between the groups */
         pgrid[g] = (unsigned int)(numSMs * (perSM < 1 ? 1 : perSM)) / (unsigned int)(wavePgridFull() ? 1 : nGroups);
@@ -784,22 +803,23 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
         if ((e = cudaStreamWaitEvent(stream2, events[2], 0)) != cudaSuccess) return e;
     }
     for (int g = 0; g < nGroups; g++)
-        waveInitKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, G[g][0]);   /* gives every slot its first camera ray */
+        waveInitKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, G[g]);   /* gives every slot its first camera ray */
     n += nGroups;
     hostDone[0] = hostDone[1] = 0;
     for (int k = 0;; k++) {
         for (int i = 0; i < batch; i++) {
             for (int g = 0; g < nGroups; g++) {
-                const RenderParams& R = G[g][i & 1];    /* `batch` is even: the round parity is i & 1 */
+                const RenderParams& R = G[g];
                 if (persistent)
                     waveTracePersistentKernel<F><<<pgrid[g], BLOCK, stackBytes(), st[g]>>>(S, R);
                 else
                     waveTraceKernel<F><<<grid[g], BLOCK, stackBytes(), st[g]>>>(S, R);
+                waveSortKernel<<<sgrid[g], SORT_BLOCK, 0, st[g]>>>(R);
                 waveLogicKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, R);
                 waveMaterialKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, R);
             }
         }
-        n += 3 * batch * nGroups;
+        n += 4 * batch * nGroups;
         if (nGroups == 2) {     /* join the second stream before reading the counter */
             if ((e = cudaEventRecord(events[3], stream2)) != cudaSuccess) return e;
             if ((e = cudaStreamWaitEvent(stream, events[3], 0)) != cudaSuccess) return e;
