@@ -4,8 +4,12 @@
 
 #include <tgd/array.hpp>
 
+#include <memory>
+
 #include "gvm.hpp"
 #include "color.hpp"
+#include "optics.hpp"
+#include "texture_image.hpp"
 
 namespace WurblPT {
 
@@ -50,6 +54,56 @@ inline TGD::Array<float> uniformRationalQuantization(const TGD::Array<float>& im
         }
     }
     return r;
+}
+
+/* Distance image (e.g. SensorTofAmcw::result()) -> camera space coordinates (reference
+ * postproc.hpp:252-287): the distance is looked up at the distorted image position of each pixel
+ * centre and put along the undistorted viewing direction; z points away from the camera. */
+inline TGD::Array<float> cameraSpaceDistanceToCoords(
+        const TGD::Array<float>& distances /* first component must contain distance */,
+        const Projection& projection,
+        const LensDistortion& distortion)
+{
+    std::unique_ptr<Texture> lookup(createTextureImage(distances, LinearizeSRGB_Off));
+    TGD::Array<float> coords(distances.dimensions(), 3);
+    coords.globalTagList() = distances.globalTagList();
+    static const char* axes[3] = { "x", "y", "z" };
+    for (size_t c = 0; c < 3; c++)
+        coords.componentTagList(c).set("INTERPRETATION", axes[c]);
+    const unsigned int width = distances.dimension(0);
+    const unsigned int height = distances.dimension(1);
+    const float invWidth = 1.0f / width;
+    const float invHeight = 1.0f / height;
+    const LensDistortion::Helper helper = distortion.getHelper(projection, width, height);
+    for (size_t y = 0; y < height; y++) {
+        for (size_t x = 0; x < width; x++) {
+            const float p = (x + 0.5f) * invWidth;
+            const float q = (y + 0.5f) * invHeight;
+            float dp = p, dq = q;
+            distortion.distort(dp, dq, helper);
+            const float distance = lookup->value(vec2(dp, dq)).r();
+            const vec2 uv = (vec2(p, q) - projection.center()) * projection.inverseFocalLength();
+            const vec3 xyz = normalize(vec3(uv, 1.0f)) * distance;
+            coords.set({ x, y }, { xyz.x(), xyz.y(), -xyz.z() });
+        }
+    }
+    return coords;
+}
+
+/* Camera space (y up, looking along -z) -> PMD sensor space (y down, z forward) (postproc.hpp:289-309) */
+inline TGD::Array<float> cameraSpaceToPMDSpace(const TGD::Array<float>& coords /* first 3 components must be x,y,z */)
+{
+    TGD::Array<float> pmd(coords.dimensions(), 3);
+    pmd.globalTagList() = coords.globalTagList();
+    static const char* axes[3] = { "x", "y", "z" };
+    for (size_t c = 0; c < 3; c++)
+        pmd.componentTagList(c).set("INTERPRETATION", axes[c]);
+    for (size_t e = 0; e < pmd.elementCount(); e++) {
+        pmd[e][0] = coords[e][0];
+        pmd[e][1] = -coords[e][1];
+        pmd[e][2] = -coords[e][2];
+    }
+    return pmd;
 }
 
 }

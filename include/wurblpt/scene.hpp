@@ -323,6 +323,21 @@ public:
     /* device handle (valid after updateBVH) */
     wpt_scene* deviceScene() const { return _device; }
 
+    /* Scene::materialIndex() of every material of the flattened description (-1: a material that is only
+     * reachable through another one and was never given to take()); for getGroundTruth() */
+    std::vector<int32_t> materialIdsOfDescription() const
+    {
+        std::vector<int32_t> ids(_flat ? _flat->materials.size() : 0, -1);
+        if (_flat) {
+            for (const auto& kv : _flat->materialIndex) {
+                auto it = _materialMap.find(kv.first);
+                if (it != _materialMap.end())
+                    ids[kv.second] = it->second;
+            }
+        }
+        return ids;
+    }
+
     /* the flattened description of the last updateBVH() (for inspection and tests) */
     const Flattener* flattened() const { return _flat.get(); }
 

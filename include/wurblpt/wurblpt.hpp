@@ -139,4 +139,144 @@ inline void mcpt(
     mcpt(mpiCoordinator, sensor, camera, scene, samplesSqrt, t0, t1, params);
 }
 
+/* Ground truth images (reference wurblpt.hpp:453-769): per pixel, the hit record of the pixel-centre
+ * ray. Same class layout (public members and bit constants) as the reference; filled by one device
+ * kernel through wpt_get_ground_truth(). */
+class GroundTruth
+{
+private:
+    struct ImageSpec {
+        TGD::Array<float> GroundTruth::* member;
+        unsigned int components;
+        const char* tags[3];
+    };
+    static const ImageSpec* specs()
+    {
+        /* in bit order; the tags are the reference's INTERPRETATION strings */
+        static const ImageSpec table[WPT_GT_FLOAT_IMAGES] = {
+            { &GroundTruth::worldSpacePositions, 3, { "x", "y", "z" } },
+            { &GroundTruth::worldSpaceGeometryNormals, 3, { "nx", "ny", "nz" } },
+            { &GroundTruth::worldSpaceGeometryTangents, 3, { "tx", "ty", "tz" } },
+            { &GroundTruth::worldSpaceMaterialNormals, 3, { "nx", "ny", "nz" } },
+            { &GroundTruth::worldSpaceMaterialTangents, 3, { "tx", "ty", "tz" } },
+            { &GroundTruth::cameraSpacePositions, 3, { "x", "y", "z" } },
+            { &GroundTruth::cameraSpaceGeometryNormals, 3, { "nx", "ny", "nz" } },
+            { &GroundTruth::cameraSpaceGeometryTangents, 3, { "tx", "ty", "tz" } },
+            { &GroundTruth::cameraSpaceMaterialNormals, 3, { "nx", "ny", "nz" } },
+            { &GroundTruth::cameraSpaceMaterialTangents, 3, { "tx", "ty", "tz" } },
+            { &GroundTruth::cameraSpaceDepths, 1, { "depth", nullptr, nullptr } },
+            { &GroundTruth::cameraSpaceDistances, 1, { "distance", nullptr, nullptr } },
+            { &GroundTruth::texCoords, 2, { "u", "v", nullptr } },
+            { &GroundTruth::worldSpaceOffsetToPrev, 3, { "dx", "dy", "dz" } },
+            { &GroundTruth::worldSpaceOffsetToNext, 3, { "dx", "dy", "dz" } },
+            { &GroundTruth::cameraSpaceOffsetToPrev, 3, { "dx", "dy", "dz" } },
+            { &GroundTruth::cameraSpaceOffsetToNext, 3, { "dx", "dy", "dz" } },
+            { &GroundTruth::pixelSpaceOffsetToPrev, 2, { "dx", "dy", nullptr } },
+            { &GroundTruth::pixelSpaceOffsetToNext, 2, { "dx", "dy", nullptr } },
+        };
+        return table;
+    }
+
+public:
+    static constexpr unsigned int WorldSpacePositions         = WPT_GT_WORLD_POSITIONS;
+    static constexpr unsigned int WorldSpaceGeometryNormals   = WPT_GT_WORLD_GEOMETRY_NORMALS;
+    static constexpr unsigned int WorldSpaceGeometryTangents  = WPT_GT_WORLD_GEOMETRY_TANGENTS;
+    static constexpr unsigned int WorldSpaceMaterialNormals   = WPT_GT_WORLD_MATERIAL_NORMALS;
+    static constexpr unsigned int WorldSpaceMaterialTangents  = WPT_GT_WORLD_MATERIAL_TANGENTS;
+    static constexpr unsigned int CameraSpacePositions        = WPT_GT_CAMERA_POSITIONS;
+    static constexpr unsigned int CameraSpaceGeometryNormals  = WPT_GT_CAMERA_GEOMETRY_NORMALS;
+    static constexpr unsigned int CameraSpaceGeometryTangents = WPT_GT_CAMERA_GEOMETRY_TANGENTS;
+    static constexpr unsigned int CameraSpaceMaterialNormals  = WPT_GT_CAMERA_MATERIAL_NORMALS;
+    static constexpr unsigned int CameraSpaceMaterialTangents = WPT_GT_CAMERA_MATERIAL_TANGENTS;
+    static constexpr unsigned int CameraSpaceDepths           = WPT_GT_CAMERA_DEPTHS;
+    static constexpr unsigned int CameraSpaceDistances        = WPT_GT_CAMERA_DISTANCES;
+    static constexpr unsigned int TexCoords                   = WPT_GT_TEXCOORDS;
+    static constexpr unsigned int WorldSpaceOffsetToPrev      = WPT_GT_WORLD_OFFSET_TO_PREV;
+    static constexpr unsigned int WorldSpaceOffsetToNext      = WPT_GT_WORLD_OFFSET_TO_NEXT;
+    static constexpr unsigned int CameraSpaceOffsetToPrev     = WPT_GT_CAMERA_OFFSET_TO_PREV;
+    static constexpr unsigned int CameraSpaceOffsetToNext     = WPT_GT_CAMERA_OFFSET_TO_NEXT;
+    static constexpr unsigned int PixelSpaceOffsetToPrev      = WPT_GT_PIXEL_OFFSET_TO_PREV;
+    static constexpr unsigned int PixelSpaceOffsetToNext      = WPT_GT_PIXEL_OFFSET_TO_NEXT;
+    static constexpr unsigned int Materials                   = WPT_GT_MATERIALS;
+    static constexpr unsigned int All                         = WPT_GT_ALL;
+
+    unsigned int bits;
+    TGD::Array<float> worldSpacePositions, worldSpaceGeometryNormals, worldSpaceGeometryTangents;
+    TGD::Array<float> worldSpaceMaterialNormals, worldSpaceMaterialTangents;
+    TGD::Array<float> cameraSpacePositions, cameraSpaceGeometryNormals, cameraSpaceGeometryTangents;
+    TGD::Array<float> cameraSpaceMaterialNormals, cameraSpaceMaterialTangents;
+    TGD::Array<float> cameraSpaceDepths;        /* == -cameraSpacePosition.z */
+    TGD::Array<float> cameraSpaceDistances;     /* == length(cameraSpacePosition) */
+    TGD::Array<float> texCoords;
+    TGD::Array<float> worldSpaceOffsetToPrev, worldSpaceOffsetToNext;
+    TGD::Array<float> cameraSpaceOffsetToPrev, cameraSpaceOffsetToNext;
+    TGD::Array<float> pixelSpaceOffsetToPrev, pixelSpaceOffsetToNext;
+    TGD::Array<int> materials;
+
+    GroundTruth() : bits(0)
+    {
+    }
+
+    GroundTruth(unsigned int width, unsigned int height, unsigned int bits = All) : bits(bits)
+    {
+        const ImageSpec* table = specs();
+        for (int i = 0; i < WPT_GT_FLOAT_IMAGES; i++) {
+            if (!(bits & (1u << i)))
+                continue;
+            TGD::Array<float>& image = this->*(table[i].member);
+            image = TGD::Array<float>({ width, height }, table[i].components);
+            for (unsigned int c = 0; c < table[i].components; c++)
+                image.componentTagList(c).set("INTERPRETATION", table[i].tags[c]);
+        }
+        if (bits & Materials) {
+            materials = TGD::Array<int>({ width, height }, 1);
+            materials.componentTagList(0).set("INTERPRETATION", "material");
+        }
+    }
+
+    /* the C-ABI view of the selected images */
+    wpt_ground_truth describe()
+    {
+        wpt_ground_truth out;
+        const ImageSpec* table = specs();
+        for (int i = 0; i < WPT_GT_FLOAT_IMAGES; i++)
+            out.aov[i] = (bits & (1u << i)) ? static_cast<float*>((this->*(table[i].member)).data()) : nullptr;
+        out.materials = (bits & Materials) ? static_cast<int32_t*>(materials.data()) : nullptr;
+        return out;
+    }
+};
+
+inline GroundTruth getGroundTruth(const Sensor& sensor, const Camera& camera, const Scene& scene,
+        float t0, float tPrev, float tNext,
+        unsigned int groundTruthBits = GroundTruth::All,
+        const Parameters& params = Parameters())
+{
+    /* the reference asserts tPrev <= t0 <= tNext and !scene.bvhNeedsUpdate(t0, t0) (wurblpt.hpp:648-651) */
+    if (scene.bvhNeedsUpdate(t0, t0) || !scene.deviceScene())
+        detail::die("getGroundTruth", "Scene::updateBVH(t0, t0) must be called first");
+    wpt_camera_desc cameraDesc;
+    std::vector<wpt_keyframe> cameraKeyframes;
+    if (!camera.flatten(cameraDesc, cameraKeyframes))
+        detail::die("getGroundTruth", "only AnimationKeyframes camera animations can be evaluated on the device");
+    const unsigned int width = sensor.width();
+    const unsigned int height = sensor.height();
+    GroundTruth gt(width, height, groundTruthBits);
+    fprintf(stderr, "Getting ground truth for %ux%u pixels at %.3fs... ", width, height, t0);
+    const std::vector<int32_t> materialIds = scene.materialIdsOfDescription();
+    const wpt_ground_truth out = gt.describe();
+    if (wpt_get_ground_truth(scene.deviceScene(), &cameraDesc, width, height, t0, tPrev, tNext, params.minHitDistance,
+                groundTruthBits, materialIds.data(), materialIds.size(), nullptr, &out) != WPT_OK)
+        detail::die("getGroundTruth", wpt_last_error());
+    fprintf(stderr, "done\n");
+    return gt;
+}
+
+inline GroundTruth getGroundTruth(const Sensor& sensor, const Camera& camera, const Scene& scene,
+        float t0 = 0.0f,
+        unsigned int groundTruthBits = GroundTruth::All,
+        const Parameters& params = Parameters())
+{
+    return getGroundTruth(sensor, camera, scene, t0, t0, t0, groundTruthBits, params);
+}
+
 }

@@ -412,6 +412,39 @@ int wpt_primary_hits(wpt_scene* scene, const wpt_camera_desc* camera,
         uint32_t width, uint32_t height, float t, float min_hit_distance,
         const wpt_render_opts* opts, int32_t* ids, float* a, uint64_t* counters);
 
+/* getGroundTruth() (wurblpt.hpp:643-759): per pixel, the hit record of the pixel-centre ray at time t0 as
+ * a set of images. `bits` selects them (the GroundTruth::* constants, wurblpt.hpp:458-478, same bit
+ * positions); out->aov[i] receives the image of bit i, WPT_GT_COMPONENTS[i] floats per pixel, pixel
+ * index y*width+x like the frame; bit 19 (materials) goes to out->materials, one int32 per pixel:
+ * Scene::materialIndex() of the hitable's material, taken from material_ids[description material index]
+ * when material_ids is not NULL (else the description index itself), -1 where nothing was hit.
+ * Pixels without a hit hold zeros. Host pointers; pointers of unselected bits are not touched.
+ * Offsets to the previous / next frame need t_prev <= t0 <= t_next and, for the pixel-space ones, a
+ * perspective camera (camera.hpp:205-217). The BVH must have been updated for (t0, t0). */
+enum {
+    WPT_GT_WORLD_POSITIONS = 1 << 0, WPT_GT_WORLD_GEOMETRY_NORMALS = 1 << 1, WPT_GT_WORLD_GEOMETRY_TANGENTS = 1 << 2,
+    WPT_GT_WORLD_MATERIAL_NORMALS = 1 << 3, WPT_GT_WORLD_MATERIAL_TANGENTS = 1 << 4,
+    WPT_GT_CAMERA_POSITIONS = 1 << 5, WPT_GT_CAMERA_GEOMETRY_NORMALS = 1 << 6, WPT_GT_CAMERA_GEOMETRY_TANGENTS = 1 << 7,
+    WPT_GT_CAMERA_MATERIAL_NORMALS = 1 << 8, WPT_GT_CAMERA_MATERIAL_TANGENTS = 1 << 9,
+    WPT_GT_CAMERA_DEPTHS = 1 << 10, WPT_GT_CAMERA_DISTANCES = 1 << 11, WPT_GT_TEXCOORDS = 1 << 12,
+    WPT_GT_WORLD_OFFSET_TO_PREV = 1 << 13, WPT_GT_WORLD_OFFSET_TO_NEXT = 1 << 14,
+    WPT_GT_CAMERA_OFFSET_TO_PREV = 1 << 15, WPT_GT_CAMERA_OFFSET_TO_NEXT = 1 << 16,
+    WPT_GT_PIXEL_OFFSET_TO_PREV = 1 << 17, WPT_GT_PIXEL_OFFSET_TO_NEXT = 1 << 18,
+    WPT_GT_MATERIALS = 1 << 19, WPT_GT_ALL = (1 << 20) - 1
+};
+#define WPT_GT_FLOAT_IMAGES 19
+static const uint32_t WPT_GT_COMPONENTS[WPT_GT_FLOAT_IMAGES] = { 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 1, 1, 2, 3, 3, 3, 3, 2, 2 };
+
+typedef struct wpt_ground_truth {
+    float* aov[WPT_GT_FLOAT_IMAGES];
+    int32_t* materials;
+} wpt_ground_truth;
+
+int wpt_get_ground_truth(wpt_scene* scene, const wpt_camera_desc* camera, uint32_t width, uint32_t height,
+        float t0, float t_prev, float t_next, float min_hit_distance, uint32_t bits,
+        const int32_t* material_ids, uint32_t n_material_ids,
+        const wpt_render_opts* opts, const wpt_ground_truth* out);
+
 /* Closest-hit queries for caller-supplied rays (origin xyz, unit direction xyz per ray;
  * host pointers). Used to check BVH::hit() parity on secondary-ray distributions. */
 int wpt_trace_rays(wpt_scene* scene, const float* origins, const float* directions, uint64_t n_rays,

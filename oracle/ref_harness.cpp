@@ -824,6 +824,48 @@ int ref_primary_hits(int h, const wpt_camera_desc* cam, uint32_t width, uint32_t
     return 0;
 }
 
+/* getGroundTruth() of the reference (wurblpt.hpp:643-759), all images. out->aov[i] / out->materials as in
+ * wpt_get_ground_truth(); every pointer must be valid. The BVH must have been updated for (t0, t0). */
+int ref_ground_truth(int h, const wpt_camera_desc* cam, uint32_t width, uint32_t height,
+        float t0, float tPrev, float tNext, float minHitDistance, const wpt_ground_truth* out)
+{
+    RefScene* rs = getScene(h);
+    if (!rs)
+        return -1;
+    Camera camera = makeRefCamera(*cam);
+    Parameters p;
+    p.minHitDistance = minHitDistance;
+    SensorRGB sensor(width, height);
+    FILE* devnull = std::fopen("/dev/null", "w");
+    FILE* savedStderr = stderr;
+    if (devnull && !std::getenv("WPT_REF_VERBOSE"))
+        stderr = devnull;       // progress text
+    unsigned int bits = GroundTruth::All;
+    if (cam->surround_mode != WPT_SURROUND_OFF || cam->stereoscopic_distance > 0.0f)
+        bits &= ~(GroundTruth::PixelSpaceOffsetToPrev | GroundTruth::PixelSpaceOffsetToNext);   // asserts, camera.hpp:207-208
+    GroundTruth gt = getGroundTruth(sensor, camera, rs->scene, t0, tPrev, tNext, bits, p);
+    stderr = savedStderr;
+    if (devnull)
+        std::fclose(devnull);
+    const TGD::Array<float>* images[WPT_GT_FLOAT_IMAGES] = {
+        &gt.worldSpacePositions, &gt.worldSpaceGeometryNormals, &gt.worldSpaceGeometryTangents,
+        &gt.worldSpaceMaterialNormals, &gt.worldSpaceMaterialTangents,
+        &gt.cameraSpacePositions, &gt.cameraSpaceGeometryNormals, &gt.cameraSpaceGeometryTangents,
+        &gt.cameraSpaceMaterialNormals, &gt.cameraSpaceMaterialTangents,
+        &gt.cameraSpaceDepths, &gt.cameraSpaceDistances, &gt.texCoords,
+        &gt.worldSpaceOffsetToPrev, &gt.worldSpaceOffsetToNext, &gt.cameraSpaceOffsetToPrev, &gt.cameraSpaceOffsetToNext,
+        &gt.pixelSpaceOffsetToPrev, &gt.pixelSpaceOffsetToNext };
+    const size_t pixels = size_t(width) * height;
+    for (int i = 0; i < WPT_GT_FLOAT_IMAGES; i++) {
+        if (bits & (1u << i))
+            std::memcpy(out->aov[i], images[i]->data(), pixels * WPT_GT_COMPONENTS[i] * sizeof(float));
+        else
+            std::memset(out->aov[i], 0, pixels * WPT_GT_COMPONENTS[i] * sizeof(float));
+    }
+    std::memcpy(out->materials, gt.materials.data(), pixels * sizeof(int));
+    return 0;
+}
+
 /* BVH::hit() (bvh.hpp:277-311) for caller-supplied rays. Directions must be unit length. */
 int ref_trace_rays(int h, const float* origins, const float* directions, uint64_t n, float time,
         float minHitDistance, int32_t* ids, float* a)

@@ -40,6 +40,8 @@ def load(flavour="strict"):
                                C.POINTER(abi.wpt_params), C.c_uint32, C.c_float, C.c_float, C.c_void_p]
     lib.ref_primary_hits.argtypes = [C.c_int, C.POINTER(abi.wpt_camera_desc), C.c_uint32, C.c_uint32,
                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib.ref_ground_truth.argtypes = [C.c_int, C.POINTER(abi.wpt_camera_desc), C.c_uint32, C.c_uint32, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, C.POINTER(abi.wpt_ground_truth)]
     lib.ref_trace_rays.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_float,
                                    C.c_void_p, C.c_void_p]
     lib.ref_camera_rays.argtypes = [C.POINTER(abi.wpt_camera_desc), C.c_uint32, C.c_uint32, C.c_float, C.c_void_p]
@@ -105,6 +107,15 @@ class RefScene:
         a = np.zeros((height, width), dtype=np.float32)
         self.lib.ref_primary_hits(self.h, C.byref(camera), width, height, t, min_hit, ids.ctypes.data, a.ctypes.data)
         return ids, a
+
+    def ground_truth(self, camera, width, height, t0=0.0, t_prev=None, t_next=None, min_hit=1e-5):
+        """getGroundTruth() of the reference, all images (pixel offsets are zero for surround / stereo cameras)."""
+        images, out = abi.ground_truth_buffers(width, height)
+        rc = self.lib.ref_ground_truth(self.h, C.byref(camera), width, height, t0, t0 if t_prev is None else t_prev,
+                                       t0 if t_next is None else t_next, min_hit, C.byref(out))
+        if rc != 0:
+            raise RuntimeError("ref_ground_truth failed")
+        return images
 
     def trace_rays(self, origins, directions, time=0.0, min_hit=1e-5):
         origins = np.ascontiguousarray(origins, dtype=np.float32)

@@ -39,6 +39,13 @@ SCENES = [
 ]
 
 
+# getGroundTruth() fixtures: name, scale, (width, height), (t0, tPrev, tNext)
+GROUND_TRUTH = [
+    ("tof", 1.0, (44, 36), (1.0, 0.96, 1.04)),       # animated hitables: the flow images are non-zero
+    ("mixed", 1.0, (48, 32), (0.0, 0.0, 0.0)),       # spheres, textures, two-sided materials
+]
+
+
 def raw(struct):
     return np.frombuffer(bytes(struct), dtype=np.uint8).copy()
 
@@ -47,6 +54,23 @@ def main():
     if not sys.argv[1:]:
         write_prng_kat()
     write_scenes()
+    write_ground_truth()
+
+
+def write_ground_truth():
+    only = sys.argv[1:]
+    for name, scale, (w, h), (t0, tp, tn) in GROUND_TRUTH:
+        if only and ("gt_" + name) not in only:
+            continue
+        view = refapi.View(name)
+        scene = refapi.RefScene(name, scale, 0)
+        scene.update_bvh(t0, t0)
+        images = scene.ground_truth(view.camera, w, h, t0, tp, tn, view.params.min_hit_distance)
+        path = os.path.join(OUT, "gt_" + name + ".npz")
+        np.savez_compressed(path, times=np.array([t0, tp, tn], dtype=np.float32), scale=np.float32(scale), **images)
+        print("gt_%-7s %7.1f KiB  %dx%d, %d pixels hit" % (name, os.path.getsize(path) / 1024, w, h,
+                                                         int((images["materials"] >= 0).sum())))
+        scene.close()
 
 
 def write_prng_kat():

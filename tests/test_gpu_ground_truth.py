@@ -1,0 +1,123 @@
+"""GPU parity tests (-m gpu) for getGroundTruth() (reference wurblpt.hpp:643-759): the device kernel
+behind wpt_get_ground_truth() against the compiled reference (live, and committed fixtures).
+
+The images are deterministic (pixel-centre rays, no sampling). Triangle hit records use the same
+un-contracted FP32 arithmetic as the reference and must match bit for bit; sphere hit records and
+surround cameras go through atan2/asin/sin/cos, where CUDA's libm and glibc differ by a few ulp, so
+those are compared with the tolerance written below.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from wurblpt_b200 import abi
+from util import GOLDEN, Golden, read_wptarray
+
+pytestmark = pytest.mark.gpu
+
+REFERENCE = abi.WPT_TRAVERSAL_REFERENCE
+WIDE = abi.WPT_TRAVERSAL_WIDE
+RTOL, ATOL = 1e-4, 2e-5     # transcendental functions (see the module docstring)
+
+
+@pytest.fixture(scope="module")
+def gpu(capi):
+    if capi.device_count() == 0:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box (there is no CPU fallback)")
+    return capi
+
+
+def compare_images(got, want, exact, allowed_mismatch=0):
+    """Every image of `got` against `want`. Pixels where the two disagree about the hitable's material are
+    silhouette pixels decided by a rounding difference in the camera ray; at most `allowed_mismatch` of them."""
+    same = got["materials"] == want["materials"]
+    assert (~same).sum() <= allowed_mismatch, int((~same).sum())
+    for name, comps in zip(abi.WPT_GT_NAMES, abi.WPT_GT_COMPONENTS):
+        if name not in got:
+            continue
+        a, b = got[name][same], want[name][same]
+        assert a.shape[-1] == comps
+        if exact:
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), name
+        else:
+            assert np.allclose(a, b, rtol=RTOL, atol=ATOL), (name, float(np.abs(a - b).max()))
+
+
+@pytest.mark.parametrize("name,scale,exact", [
+    ("cornell", 1.0, True), ("tof", 1.0, True), ("synth", 0.004, True),
+    ("rtiow", 1.0, False), ("mixed", 1.0, False), ("media", 1.0, False), ("synth360", 0.004, False)])
+@pytest.mark.parametrize("mode", [REFERENCE, WIDE])
+def test_ground_truth_against_live_reference(gpu, ref, name, scale, exact, mode):
+    view = ref.View(name)
+    t0, tp, tn = (1.0, 0.96, 1.04) if name == "tof" else (view.t0, view.t0, view.t0)
+    r = ref.RefScene(name, scale, 0)
+    r.update_bvh(t0, t0)
+    s = gpu.Scene(r.desc, device=0).update_bvh(t0, t0)
+    w, h = 160, 120
+    min_hit = view.params.min_hit_distance
+    want = r.ground_truth(view.camera, w, h, t0, tp, tn, min_hit)
+    bits = abi.WPT_GT_ALL
+    if view.camera.surround_mode != 0 or view.camera.stereoscopic_distance > 0:
+        bits &= ~abi.WPT_GT_PIXEL_OFFSETS        # the reference asserts (camera.hpp:207-208)
+    got = s.ground_truth(view.camera, w, h, t0, tp, tn, min_hit, bits, opts=gpu.make_opts(traversal=mode))
+    assert (want["materials"] >= 0).any()
+    # exact ties between two hitables may be settled differently by the ordered walk (counted)
+    allowed = 0 if (exact and mode == REFERENCE) else w * h // 500
+    compare_images(got, want, exact and mode == REFERENCE, allowed)
+    if name == "tof":
+        assert np.abs(got["world_offset_to_next"]).max() > 1e-3      # the animated quad moves
+        assert np.abs(got["pixel_offset_to_prev"]).max() > 1e-2
+
+
+@pytest.mark.parametrize("name", ["tof", "mixed"])
+def test_ground_truth_against_committed_fixture(gpu, name):
+    g = Golden(name)
+    with np.load(os.path.join(GOLDEN, "gt_" + name + ".npz")) as z:
+        want = {k: z[k] for k in z.files}
+    t0, tp, tn = [float(v) for v in want["times"]]
+    h, w = want["materials"].shape
+    s = gpu.Scene(g.desc, device=0).update_bvh(t0, t0)
+    got = s.ground_truth(g.camera, w, h, t0, tp, tn, g.params.min_hit_distance,
+                         opts=gpu.make_opts(traversal=REFERENCE))
+    compare_images(got, want, exact=(name == "tof"))
+
+
+def test_ground_truth_selects_images_and_maps_material_ids(gpu):
+    g = Golden("cornell")
+    s = gpu.Scene(g.desc, device=0).update_bvh(0.0, 0.0)
+    bits = (1 << 0) | (1 << 11) | abi.WPT_GT_MATERIALS
+    ids = np.arange(g.desc.n_materials, dtype=np.int32) + 100
+    got = s.ground_truth(g.camera, 64, 48, bits=bits, material_ids=ids)
+    assert sorted(got) == ["camera_distances", "materials", "world_positions"]
+    hit = got["materials"] >= 0
+    assert hit.any() and (got["materials"][hit] >= 100).all()
+    assert (got["camera_distances"][hit] > 0).all() and (got["camera_distances"][~hit] == 0).all()
+    with pytest.raises(gpu.WptError):
+        s.ground_truth(g.camera, 64, 48, t0=1.0, t_prev=2.0)        # t_prev <= t0 is required
+
+
+def test_reference_tof_example_app_runs_unchanged(gpu, tmp_path):
+    """wurblpt-tof-example.cpp, compiled unchanged against include/wurblpt: 4 phase images per frame, then
+    getGroundTruth() with flow images (wurblpt-tof-example.cpp:125-151). The app renders 5 s of video; the
+    first frames are enough here."""
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "apps", "_bin", "wurblpt-tof-example")
+    if not os.path.exists(exe):
+        pytest.skip("apps/_bin/wurblpt-tof-example not built")
+    log = ""
+    try:
+        log = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=120).stderr
+    except subprocess.TimeoutExpired as e:
+        log = (e.stderr or b"").decode(errors="replace") if isinstance(e.stderr, bytes) else (e.stderr or "")
+    assert (tmp_path / "frame0000-groundtruth-distances.tgd").exists(), log[-3000:]
+    dist = read_wptarray(str(tmp_path / "frame0000-groundtruth-distances.tgd"))
+    result = read_wptarray(str(tmp_path / "frame0000-results.tgd"))
+    flow = read_wptarray(str(tmp_path / "frame0000-groundtruth-psflow-forward.tgd"))
+    assert dist.shape[:2] == (288, 352) and flow.shape[2] == 2
+    # the simulated ToF distance agrees with the ground truth distance on the diffuse background wall
+    measured = result[..., 0]
+    ok = (dist[..., 0] > 0) & np.isfinite(measured) & (measured > 0)
+    rel = np.abs(measured[ok] - dist[..., 0][ok]) / dist[..., 0][ok]
+    assert np.median(rel) < 0.05
+    assert np.abs(flow).max() > 0.01

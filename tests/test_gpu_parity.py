@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from wurblpt_b200 import abi
-from util import Golden, GOLDEN_SCENES, GOLDEN, box_downsample, compare_hits, rel_rmse
+from util import Golden, GOLDEN_SCENES, GOLDEN, box_downsample, compare_hits, read_wptarray, rel_rmse
 
 pytestmark = pytest.mark.gpu
 
@@ -253,18 +253,6 @@ def test_tof_phase_images_give_plausible_distance(gpu):
     dist = (299792458.0 / sensor.modulation_frequency) * phase_shift / (4 * np.pi)
     corner = dist[:8, :8]
     assert 1.9 < np.median(corner) < 3.2
-
-
-def read_wptarray(path):
-    """Reader for the container the libtgd stand-in writes (include/tgd/io.hpp)."""
-    with open(path, "rb") as f:
-        header = f.readline().decode().split()
-        assert header[0] == "WPTARRAY"
-        dtype = {"float32": np.float32, "uint8": np.uint8}[header[1]]
-        comps, ndims = int(header[2]), int(header[3])
-        dims = [int(x) for x in header[4:4 + ndims]]
-        data = np.frombuffer(f.read(), dtype=dtype)
-    return data.reshape(dims[1], dims[0], comps)
 
 
 def test_reference_furnace_app_runs_unchanged(gpu, tmp_path):

@@ -75,3 +75,15 @@ def compare_hits(ids, dist, ref_ids, ref_dist):
     same = ids.size - n_diff
     bit_equal_dist = int((dist[~diff].view(np.int32) == ref_dist[~diff].view(np.int32)).sum())
     return dict(total=int(ids.size), same=same, ties=ties, near=near, wrong=wrong, dist_bit_equal=bit_equal_dist)
+
+
+def read_wptarray(path):
+    """Reader for the container the libtgd stand-in writes (include/tgd/io.hpp)."""
+    with open(path, "rb") as f:
+        header = f.readline().decode().split()
+        assert header[0] == "WPTARRAY"
+        dtype = {"float32": np.float32, "uint8": np.uint8}[header[1]]
+        comps, ndims = int(header[2]), int(header[3])
+        dims = [int(x) for x in header[4:4 + ndims]]
+        data = np.frombuffer(f.read(), dtype=dtype)
+    return data.reshape(dims[1], dims[0], comps)

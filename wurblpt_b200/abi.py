@@ -141,6 +141,38 @@ class wpt_scene_info(C.Structure):
                 ("device_bytes", u64), ("build_seconds", C.c_double), ("upload_seconds", C.c_double)]
 
 
+# getGroundTruth() images: bit i selects image i (GroundTruth::*, reference wurblpt.hpp:458-478)
+WPT_GT_NAMES = ["world_positions", "world_geometry_normals", "world_geometry_tangents", "world_material_normals",
+                "world_material_tangents", "camera_positions", "camera_geometry_normals", "camera_geometry_tangents",
+                "camera_material_normals", "camera_material_tangents", "camera_depths", "camera_distances", "texcoords",
+                "world_offset_to_prev", "world_offset_to_next", "camera_offset_to_prev", "camera_offset_to_next",
+                "pixel_offset_to_prev", "pixel_offset_to_next"]
+WPT_GT_COMPONENTS = [3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 1, 1, 2, 3, 3, 3, 3, 2, 2]
+WPT_GT_FLOAT_IMAGES = 19
+WPT_GT_MATERIALS = 1 << 19
+WPT_GT_ALL = (1 << 20) - 1
+WPT_GT_PIXEL_OFFSETS = (1 << 17) | (1 << 18)
+
+
+class wpt_ground_truth(C.Structure):
+    _fields_ = [("aov", C.c_void_p * WPT_GT_FLOAT_IMAGES), ("materials", C.c_void_p)]
+
+
+def ground_truth_buffers(width, height, bits=WPT_GT_ALL):
+    """numpy images for the selected bits and the wpt_ground_truth that points at them."""
+    import numpy as np
+    images = {}
+    out = wpt_ground_truth()
+    for i, (name, comps) in enumerate(zip(WPT_GT_NAMES, WPT_GT_COMPONENTS)):
+        if bits & (1 << i):
+            images[name] = np.zeros((height, width, comps), dtype=np.float32)
+            out.aov[i] = images[name].ctypes.data
+    if bits & WPT_GT_MATERIALS:
+        images["materials"] = np.full((height, width), -1, dtype=np.int32)
+        out.materials = images["materials"].ctypes.data
+    return images, out
+
+
 STRUCTS = [wpt_keyframe, wpt_animation, wpt_texture, wpt_material, wpt_mesh, wpt_instance,
            wpt_sphere, wpt_medium, wpt_component, wpt_envmap, wpt_scene_desc, wpt_camera_desc,
            wpt_sensor_desc, wpt_params, wpt_render_opts, wpt_stats, wpt_scene_info]

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("WPT_LIB") or os.path.join(_HERE, "lib", "libwurblpt_b
 
 EXPORTS = ["wpt_version", "wpt_last_error", "wpt_device_count", "wpt_abi_sizeof", "wpt_scene_create",
            "wpt_scene_update_bvh", "wpt_scene_get_info", "wpt_scene_destroy", "wpt_scene_get_binary_nodes",
-           "wpt_render", "wpt_primary_hits", "wpt_trace_rays", "wpt_prng_kat"]
+           "wpt_render", "wpt_primary_hits", "wpt_get_ground_truth", "wpt_trace_rays", "wpt_prng_kat"]
 
 _lib = None
 
@@ -52,6 +52,9 @@ def lib():
                              C.POINTER(abi.wpt_render_opts), C.c_void_p, C.POINTER(abi.wpt_stats)]
     L.wpt_primary_hits.argtypes = [C.c_void_p, C.POINTER(abi.wpt_camera_desc), C.c_uint32, C.c_uint32, C.c_float,
                                    C.c_float, C.POINTER(abi.wpt_render_opts), C.c_void_p, C.c_void_p, C.c_void_p]
+    L.wpt_get_ground_truth.argtypes = [C.c_void_p, C.POINTER(abi.wpt_camera_desc), C.c_uint32, C.c_uint32, C.c_float,
+                                       C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_void_p, C.c_uint32,
+                                       C.POINTER(abi.wpt_render_opts), C.POINTER(abi.wpt_ground_truth)]
     L.wpt_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_float,
                                  C.POINTER(abi.wpt_render_opts), C.c_void_p, C.c_void_p, C.c_void_p]
     L.wpt_prng_kat.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
@@ -137,6 +140,18 @@ class Scene:
         if count:
             return ids, a, dict(nodes=counters[0], leaves=counters[1], nested=counters[2])
         return ids, a
+
+    def ground_truth(self, camera, width, height, t0=0.0, t_prev=None, t_next=None, min_hit=1e-5,
+                     bits=abi.WPT_GT_ALL, material_ids=None, opts=None):
+        """getGroundTruth(): dict of images (abi.WPT_GT_NAMES + "materials") for the selected bits."""
+        images, out = abi.ground_truth_buffers(width, height, bits)
+        ids = None if material_ids is None else np.ascontiguousarray(material_ids, dtype=np.int32)
+        _check(lib().wpt_get_ground_truth(self._h, C.byref(camera), width, height, t0,
+                                          t0 if t_prev is None else t_prev, t0 if t_next is None else t_next,
+                                          min_hit, bits, None if ids is None else ids.ctypes.data,
+                                          0 if ids is None else ids.size,
+                                          C.byref(opts) if opts is not None else None, C.byref(out)))
+        return images
 
     def trace_rays(self, origins, directions, time=0.0, min_hit=1e-5, opts=None, count=False):
         origins = np.ascontiguousarray(origins, dtype=np.float32)

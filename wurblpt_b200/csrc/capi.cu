@@ -124,7 +124,7 @@ struct wpt_scene {
     /* per updateBVH */
     DeviceBuf node4, bnode, tri, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs;
     /* per call scratch */
-    DeviceBuf counters, camKeys, frame, partials, wave[15], qOrigins, qDirections, qIds, qDist, qStats;
+    DeviceBuf counters, camKeys, frame, partials, wave[15], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds;
     cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaStream_t stream2 = nullptr;
     unsigned long long* hostDone = nullptr;     /* pinned, 2 counters */
@@ -789,6 +789,96 @@ int wpt_primary_hits(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width
     if (!camera || width == 0 || height == 0)
         return fail(WPT_E_INVALID, "invalid camera or image size");
     return runQuery(s, camera, width, height, nullptr, nullptr, 0, t, minHitDistance, opts, ids, a, counters);
+}
+
+int wpt_get_ground_truth(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width, uint32_t height,
+        float t0, float tPrev, float tNext, float minHitDistance, uint32_t bits,
+        const int32_t* materialIds, uint32_t nMaterialIds, const wpt_render_opts* opts, const wpt_ground_truth* out)
+{
+    int rc = checkReady(s);
+    if (rc != WPT_OK)
+        return rc;
+    if (!camera || width == 0 || height == 0 || !out)
+        return fail(WPT_E_INVALID, "invalid camera, image size or output");
+    if (!(tPrev <= t0) || !(t0 <= tNext))
+        return fail(WPT_E_INVALID, "getGroundTruth needs t_prev <= t0 <= t_next (wurblpt.hpp:648-649)");
+    bits &= uint32_t(WPT_GT_ALL);
+    if ((bits & (WPT_GT_PIXEL_OFFSET_TO_PREV | WPT_GT_PIXEL_OFFSET_TO_NEXT))
+            && (camera->surround_mode != WPT_SURROUND_OFF || camera->stereoscopic_distance > 0.0f))
+        return fail(WPT_E_UNSUPPORTED, "pixel space offsets exist for perspective, non-stereoscopic cameras only (camera.hpp:207-208)");
+    for (int i = 0; i < WPT_GT_FLOAT_IMAGES; i++)
+        if ((bits & (1u << i)) && !out->aov[i])
+            return fail(WPT_E_INVALID, "a selected ground truth image has a null pointer");
+    if ((bits & WPT_GT_MATERIALS) && !out->materials)
+        return fail(WPT_E_INVALID, "the material image has a null pointer");
+    wpt_render_opts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts)
+        o = *opts;
+    cudaStream_t stream = static_cast<cudaStream_t>(o.stream);
+    wptd::RenderParams P;
+    std::memset(&P, 0, sizeof(P));
+    rc = fillCamera(s, camera, t0, width, height, P, stream);
+    if (rc != WPT_OK)
+        return rc;
+    P.t0 = P.t1 = t0;
+    P.minHit = minHitDistance;
+    P.traversal = o.traversal;
+    if (o.traversal == WPT_TRAVERSAL_WIDE && (!(minHitDistance > 0.0f) || 3 * s->host.wideDepth + 1 > uint32_t(12 + 84)))
+        P.traversal = WPT_TRAVERSAL_REFERENCE;
+
+    wptd::GroundTruthParams G;
+    std::memset(&G, 0, sizeof(G));
+    const float times[3] = { t0, tPrev, tNext };
+    for (int i = 0; i < 3; i++) {
+        /* inverse(camera.at(t)) (transformation.hpp:157-163); only rotation and translation are used */
+        const wpt::Trs T = cameraPose(camera, times[i]);
+        const wpt::Quat invR = wpt::Quat{ -T.r.x, -T.r.y, -T.r.z, T.r.w };
+        const wpt::V3 invS = wpt::v3(1.0f / T.s.x, 1.0f / T.s.y, 1.0f / T.s.z);
+        const wpt::V3 invT = wpt::rotate(invR, wpt::v3(-T.t.x * invS.x, -T.t.y * invS.y, -T.t.z * invS.z));
+        G.invCamR[i] = make_float4(invR.x, invR.y, invR.z, invR.w);
+        G.invCamT[i] = make_float3(invT.x, invT.y, invT.z);
+    }
+    G.tPrev = tPrev;
+    G.tNext = tNext;
+    G.P00 = 2.0f / (camera->r - camera->l);
+    G.P11 = 2.0f / (camera->t - camera->b);
+    G.P03 = (camera->r + camera->l) / (camera->r - camera->l);
+    G.P13 = (camera->t + camera->b) / (camera->t - camera->b);
+    G.bits = bits;
+    const size_t pixels = size_t(width) * height;
+    size_t words = 0;
+    for (int i = 0; i < WPT_GT_FLOAT_IMAGES; i++)
+        if (bits & (1u << i))
+            words += pixels * WPT_GT_COMPONENTS[i];
+    if (bits & WPT_GT_MATERIALS)
+        words += pixels;
+    if (words == 0)
+        return WPT_OK;
+    WPT_CUDA(s->gtImages.reserve(words * sizeof(float)), "allocate ground truth images");
+    float* cursor = static_cast<float*>(s->gtImages.p);
+    for (int i = 0; i < WPT_GT_FLOAT_IMAGES; i++) {
+        if (bits & (1u << i)) {
+            G.aov[i] = cursor;
+            cursor += pixels * WPT_GT_COMPONENTS[i];
+        }
+    }
+    if (bits & WPT_GT_MATERIALS)
+        G.materials = reinterpret_cast<int32_t*>(cursor);
+    if (materialIds && nMaterialIds > 0) {
+        WPT_CUDA(s->gtMaterialIds.upload(materialIds, size_t(nMaterialIds) * sizeof(int32_t), stream), "upload material ids");
+        G.materialIds = s->gtMaterialIds.as<int32_t>();
+        G.nMaterialIds = nMaterialIds;
+    }
+    WPT_CUDA(wptd::launchGroundTruth(sceneFeatures(s, false), s->d, P, G, stream), "ground truth kernel launch");
+    for (int i = 0; i < WPT_GT_FLOAT_IMAGES; i++)
+        if (bits & (1u << i))
+            WPT_CUDA(cudaMemcpyAsync(out->aov[i], G.aov[i], pixels * WPT_GT_COMPONENTS[i] * sizeof(float),
+                        cudaMemcpyDeviceToHost, stream), "copy ground truth image");
+    if (bits & WPT_GT_MATERIALS)
+        WPT_CUDA(cudaMemcpyAsync(out->materials, G.materials, pixels * sizeof(int32_t), cudaMemcpyDeviceToHost, stream), "copy material image");
+    WPT_CUDA(cudaStreamSynchronize(stream), "ground truth kernel");
+    return WPT_OK;
 }
 
 int wpt_trace_rays(wpt_scene* s, const float* origins, const float* directions, uint64_t nRays,

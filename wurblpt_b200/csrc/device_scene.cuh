@@ -148,6 +148,19 @@ struct RenderParams {
     int32_t traversal;
 };
 
+/* getGroundTruth() launch parameters (wurblpt.hpp:643-663) */
+struct GroundTruthParams {
+    float4 invCamR[3];          /* inverse(camera.at(t)).rotation for t0, tPrev, tNext */
+    float3 invCamT[3];          /* ... .translation */
+    float tPrev, tNext;
+    float P00, P11, P03, P13;   /* Camera::ImageSpaceHelper (camera.hpp:194-203) */
+    uint32_t bits;
+    float* aov[WPT_GT_FLOAT_IMAGES];
+    int32_t* materials;
+    const int32_t* materialIds; /* description material index -> Scene::materialIndex(), or nullptr */
+    uint32_t nMaterialIds;
+};
+
 /* counters for the ray-query kernels */
 struct TraceStats {
     unsigned long long nodes, leaves, nested;

@@ -669,6 +669,143 @@ __global__ void __launch_bounds__(BLOCK) queryKernel(const __grid_constant__ DSc
     }
 }
 
+/* Animation index of a hitable (Hitable::animationIndex(), hitable.hpp:131): -1 = not animated. */
+WPT_DEV int hitAnimationIndex(const DScene& S, uint32_t ref)
+{
+    const uint32_t type = ref >> REF_TYPE_SHIFT, slot = ref & REF_SLOT_MASK;
+    uint32_t anim = 0;
+    if (type == PRIM_TRIANGLE)
+        anim = __float_as_uint(__ldg(S.tri + size_t(slot) * 3 + 2).w);
+    else if (type == PRIM_SPHERE)
+        anim = __float_as_uint(__ldg(S.sph + size_t(slot) * 3 + 2).y);
+    return int(anim) - 1;
+}
+
+/* inverse(Transformation) (transformation.hpp:157-163) */
+WPT_DEV Trs trsInverse(const Trs& T)
+{
+    const float3 invT = -T.t;
+    const float4 invR = f4(-T.r.x, -T.r.y, -T.r.z, T.r.w);
+    const float3 invS = 1.0f / T.s;
+    Trs R;
+    R.t = qrotate(invR, invT * invS);
+    R.r = invR;
+    R.s = invS;
+    return R;
+}
+
+/* Camera::cameraSpaceToImageSpace (camera.hpp:205-217), times the image size */
+WPT_DEV float2 cameraToPixelSpace(const RenderParams& P, const GroundTruthParams& G, float3 p)
+{
+    const float px = G.P00 * p.x + G.P03 * p.z, py = G.P11 * p.y + G.P13 * p.z, pw = -p.z;
+    float ix = 0.5f * (px / pw) + 0.5f;
+    float iy = 0.5f * (py / pw) + 0.5f;
+    lensDistort(P, ix, iy);
+    return make_float2(ix * float(P.width), iy * float(P.height));
+}
+
+WPT_DEV void store3(float* image, size_t pixel, float3 v)
+{
+    image[pixel * 3 + 0] = v.x; image[pixel * 3 + 1] = v.y; image[pixel * 3 + 2] = v.z;
+}
+
+/* getGroundTruth() (wurblpt.hpp:656-755): one thread per pixel. */
+template<int F>
+__global__ void __launch_bounds__(BLOCK) groundTruthKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P,
+        const __grid_constant__ GroundTruthParams G)
+{
+    extern __shared__ uint2 smStackAll[];
+    uint2* smStack = smStackAll + threadIdx.x;
+    const size_t pixel = blockIdx.x * size_t(BLOCK) + threadIdx.x;
+    if (pixel >= size_t(P.width) * P.height)
+        return;
+    Ctx<F> ctx;
+    ctx.nested = 0;
+    ctx.nodes = ctx.leaves = 0;
+    ctx.prng = prngInit((unsigned int)pixel);
+    const unsigned int x = (unsigned int)(pixel % P.width), y = (unsigned int)(pixel / P.width);
+    const float invWidth = 1.0f / float(P.width), invHeight = 1.0f / float(P.height);
+    const float2 pixelCoord = make_float2((float(x) + 0.5f) * invWidth, (float(y) + 0.5f) * invHeight);
+    const Ray ray = cameraRay(P, pixelCoord.x, pixelCoord.y, ctx.prng, false);
+    animationCacheInit<F>(S, ctx, ray.time);
+    const RayHelper h = makeRayHelper(ray);
+    const Hit hit = closestHit<F>(S, P, ray, h, ctx, smStack);
+
+    float3 wsPos = f3(0.0f), wsGNrm = f3(0.0f), wsGTan = f3(0.0f), wsMNrm = f3(0.0f), wsMTan = f3(0.0f);
+    float3 csPos = f3(0.0f), csGNrm = f3(0.0f), csGTan = f3(0.0f), csMNrm = f3(0.0f), csMTan = f3(0.0f);
+    float csDepth = 0.0f, csDist = 0.0f;
+    float2 txCor = make_float2(0.0f, 0.0f);
+    float3 wsOP = f3(0.0f), wsON = f3(0.0f), csOP = f3(0.0f), csON = f3(0.0f);
+    float2 psOP = make_float2(0.0f, 0.0f), psON = make_float2(0.0f, 0.0f);
+    int matInd = -1;
+    if (hit.ref != NO_HIT) {
+        const HitRec hr = buildHitRecord<F>(S, hit, ray, h, ctx);
+        wsPos = hr.p;
+        wsGNrm = hr.n;
+        wsGTan = hr.t;
+        TangentSpace ts;
+        if (hr.material >= 0)
+            ts = tangentSpaceAt(S, S.materials + hr.material, hr);
+        else
+            ts = (dot(hr.t, hr.t) > EPSILON ? tangentSpace(hr.n, hr.t) : tangentSpace(hr.n));
+        wsMNrm = ts.normal;
+        wsMTan = ts.tangent;
+        csPos = qrotate(G.invCamR[0], wsPos) + G.invCamT[0];
+        csGNrm = qrotate(G.invCamR[0], wsGNrm);
+        csGTan = qrotate(G.invCamR[0], wsGTan);
+        csMNrm = qrotate(G.invCamR[0], wsMNrm);
+        csMTan = qrotate(G.invCamR[0], wsMTan);
+        csDepth = -csPos.z;
+        csDist = sqrtf(dot(csPos, csPos));
+        txCor = hr.tc;
+        float3 wsPosPrev = wsPos, wsPosNext = wsPos;
+        const int anim = hitAnimationIndex(S, hit.ref);
+        if (anim >= 0 && uint32_t(anim) < S.nAnimations) {
+            const wpt_animation an = S.animations[anim];
+            const wpt_keyframe* kf = S.keyframes + an.first_keyframe;
+            const float3 posOrig = trsApply(trsInverse(keyframesAt(kf, an.keyframe_count, ray.time)), wsPos);
+            wsPosPrev = trsApply(keyframesAt(kf, an.keyframe_count, G.tPrev), posOrig);
+            wsPosNext = trsApply(keyframesAt(kf, an.keyframe_count, G.tNext), posOrig);
+        }
+        wsOP = wsPosPrev - wsPos;
+        wsON = wsPosNext - wsPos;
+        const float3 csPosPrev = qrotate(G.invCamR[1], wsPosPrev) + G.invCamT[1];
+        const float3 csPosNext = qrotate(G.invCamR[2], wsPosNext) + G.invCamT[2];
+        csOP = csPosPrev - csPos;
+        csON = csPosNext - csPos;
+        if (G.bits & (WPT_GT_PIXEL_OFFSET_TO_PREV | WPT_GT_PIXEL_OFFSET_TO_NEXT)) {
+            const float2 psPos = make_float2(pixelCoord.x * float(P.width), pixelCoord.y * float(P.height));
+            const float2 psPrev = cameraToPixelSpace(P, G, csPosPrev);
+            const float2 psNext = cameraToPixelSpace(P, G, csPosNext);
+            psOP = make_float2(psPrev.x - psPos.x, psPrev.y - psPos.y);
+            psON = make_float2(psNext.x - psPos.x, psNext.y - psPos.y);
+        }
+        matInd = hr.material;
+        if (G.materialIds && matInd >= 0)
+            matInd = (uint32_t(matInd) < G.nMaterialIds ? G.materialIds[matInd] : -1);
+    }
+    if (G.bits & WPT_GT_WORLD_POSITIONS) store3(G.aov[0], pixel, wsPos);
+    if (G.bits & WPT_GT_WORLD_GEOMETRY_NORMALS) store3(G.aov[1], pixel, wsGNrm);
+    if (G.bits & WPT_GT_WORLD_GEOMETRY_TANGENTS) store3(G.aov[2], pixel, wsGTan);
+    if (G.bits & WPT_GT_WORLD_MATERIAL_NORMALS) store3(G.aov[3], pixel, wsMNrm);
+    if (G.bits & WPT_GT_WORLD_MATERIAL_TANGENTS) store3(G.aov[4], pixel, wsMTan);
+    if (G.bits & WPT_GT_CAMERA_POSITIONS) store3(G.aov[5], pixel, csPos);
+    if (G.bits & WPT_GT_CAMERA_GEOMETRY_NORMALS) store3(G.aov[6], pixel, csGNrm);
+    if (G.bits & WPT_GT_CAMERA_GEOMETRY_TANGENTS) store3(G.aov[7], pixel, csGTan);
+    if (G.bits & WPT_GT_CAMERA_MATERIAL_NORMALS) store3(G.aov[8], pixel, csMNrm);
+    if (G.bits & WPT_GT_CAMERA_MATERIAL_TANGENTS) store3(G.aov[9], pixel, csMTan);
+    if (G.bits & WPT_GT_CAMERA_DEPTHS) G.aov[10][pixel] = csDepth;
+    if (G.bits & WPT_GT_CAMERA_DISTANCES) G.aov[11][pixel] = csDist;
+    if (G.bits & WPT_GT_TEXCOORDS) { G.aov[12][pixel * 2] = txCor.x; G.aov[12][pixel * 2 + 1] = txCor.y; }
+    if (G.bits & WPT_GT_WORLD_OFFSET_TO_PREV) store3(G.aov[13], pixel, wsOP);
+    if (G.bits & WPT_GT_WORLD_OFFSET_TO_NEXT) store3(G.aov[14], pixel, wsON);
+    if (G.bits & WPT_GT_CAMERA_OFFSET_TO_PREV) store3(G.aov[15], pixel, csOP);
+    if (G.bits & WPT_GT_CAMERA_OFFSET_TO_NEXT) store3(G.aov[16], pixel, csON);
+    if (G.bits & WPT_GT_PIXEL_OFFSET_TO_PREV) { G.aov[17][pixel * 2] = psOP.x; G.aov[17][pixel * 2 + 1] = psOP.y; }
+    if (G.bits & WPT_GT_PIXEL_OFFSET_TO_NEXT) { G.aov[18][pixel * 2] = psON.x; G.aov[18][pixel * 2 + 1] = psON.y; }
+    if (G.bits & WPT_GT_MATERIALS) G.materials[pixel] = matInd;
+}
+
 __global__ void prngKernel(const uint32_t* seeds, uint32_t nSeeds, uint32_t nDraws, float* out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -775,6 +912,11 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, waveTracePersistentKernel<F>, BLOCK, stackBytes());
     if (e != cudaSuccess)
         return e;
+    if (const char* ev = std::getenv("WPT_TRACE_CTAS")) {   /* experiment knob: resident trace CTAs per SM */
+        const int v = std::atoi(ev);
+        if (v >= 1 && v < perSM)
+            perSM = v;
+    }
     const bool persistent = (P.traversal == WPT_TRAVERSAL_WIDE) && !wavePlainTrace();
     const int nGroups = (waveGroups() >= 2 && P.W.nSlots >= 4096) ? 2 : 1;
     RenderParams G[2];
@@ -879,6 +1021,19 @@ cudaError_t launchQuery(int features, bool count, const DScene& S, const RenderP
         else
             queryKernel<0><<<grid, BLOCK, stackBytes(), stream>>>(S, P, origins, directions, nRays, time, ids, dist, nullptr);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launchGroundTruth(int features, const DScene& S, const RenderParams& P, const GroundTruthParams& G, cudaStream_t stream)
+{
+    const unsigned long long pixels = (unsigned long long)P.width * P.height;
+    const unsigned int grid = (unsigned int)((pixels + BLOCK - 1) / BLOCK);
+    if (grid == 0)
+        return cudaSuccess;
+    if (features != 0)
+        groundTruthKernel<F_MEDIA | F_ANIM><<<grid, BLOCK, stackBytes(), stream>>>(S, P, G);
+    else
+        groundTruthKernel<0><<<grid, BLOCK, stackBytes(), stream>>>(S, P, G);
     return cudaGetLastError();
 }
 

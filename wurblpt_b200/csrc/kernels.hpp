@@ -21,6 +21,9 @@ cudaError_t launchQuery(int features, bool count, const DScene& S, const RenderP
         const float* origins, const float* directions, unsigned long long nRays, float time,
         int32_t* ids, float* dist, TraceStats* stats, cudaStream_t stream);
 
+/* getGroundTruth(): the images selected by G.bits for P.width x P.height pixels (device pointers in G). */
+cudaError_t launchGroundTruth(int features, const DScene& S, const RenderParams& P, const GroundTruthParams& G, cudaStream_t stream);
+
 cudaError_t launchPrng(const uint32_t* seeds, uint32_t nSeeds, uint32_t nDraws, float* out, cudaStream_t stream);
 
 }
