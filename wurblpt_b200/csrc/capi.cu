@@ -120,9 +120,10 @@ struct wpt_scene {
     bool sceneHasMedia = false, sceneHasAnimation = false;
     /* time-independent arrays */
     DeviceBuf materials, instances, meshes, vertices, indices, textures, texels;
-    DeviceBuf animations, keyframes, envM, envMs, envMcs;
+    DeviceBuf animations, keyframes, envM, envMs, envMcs, envGuide;
+    int envGuideBits = 0;
     /* per updateBVH */
-    DeviceBuf node4, bnode, tri, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs;
+    DeviceBuf node4, bnode, tri, triShade, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs;
     /* per call scratch */
     DeviceBuf counters, camKeys, frame, partials, wave[15], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds;
     cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -144,7 +145,7 @@ struct wpt_scene {
     uint64_t deviceBytes() const
     {
         const DeviceBuf* all[] = { &materials, &instances, &meshes, &vertices, &indices, &textures, &texels,
-            &animations, &keyframes, &envM, &envMs, &envMcs, &node4, &bnode, &tri, &sph, &med,
+            &animations, &keyframes, &envM, &envMs, &envMcs, &envGuide, &node4, &bnode, &tri, &triShade, &sph, &med,
             &triGlobal, &sphGlobal, &medGlobal, &hotRefs };
         uint64_t n = 0;
         for (const DeviceBuf* b : all)
@@ -182,6 +183,28 @@ int uploadStatic(wpt_scene* s)
     WPT_CUDA(s->envM.upload(h.envM.data(), h.envM.size() * sizeof(float)), "upload envmap M");
     WPT_CUDA(s->envMs.upload(h.envMs.data(), h.envMs.size() * sizeof(int32_t)), "upload envmap Ms");
     WPT_CUDA(s->envMcs.upload(h.envMcs.data(), h.envMcs.size() * sizeof(float)), "upload envmap Mcs");
+    /* Guide table for EnvironmentMap::d's search in Mcs (envmap.hpp:190-203): entry j is the first bin whose
+     * cumulative sum is >= j / 2^bits, so a draw r only has to search between entries floor(r 2^bits) and
+     * the next one. Same answer as the full bisection as long as Mcs never decreases (checked here). */
+    s->envGuideBits = 0;
+    if (!h.envMcs.empty()) {
+        bool monotone = true;
+        for (size_t i = 1; i < h.envMcs.size() && monotone; i++)
+            monotone = (h.envMcs[i] >= h.envMcs[i - 1]);
+        if (monotone) {
+            const int bits = 16;
+            std::vector<uint32_t> guide((size_t(1) << bits) + 1);
+            size_t i = 0;
+            for (size_t j = 0; j < guide.size(); j++) {
+                const float r = float(j) / float(1u << bits);   /* exact */
+                while (i + 1 < h.envMcs.size() && h.envMcs[i] < r)
+                    i++;
+                guide[j] = uint32_t(i);
+            }
+            WPT_CUDA(s->envGuide.upload(guide.data(), guide.size() * sizeof(uint32_t)), "upload envmap guide table");
+            s->envGuideBits = bits;
+        }
+    }
 
     /* textures: descriptors + image texels decoded once to RGBA float (16-byte texel fetches) */
     std::vector<wptd::DTexture> dt(h.textures.size());
@@ -233,6 +256,7 @@ void refreshDeviceScene(wpt_scene* s)
     d.node4 = s->node4.as<float4>();
     d.bnode = s->bnode.as<float4>();
     d.tri = s->tri.as<float4>();
+    d.triShade = s->triShade.as<uint4>();
     d.sph = s->sph.as<float4>();
     d.med = s->med.as<float4>();
     d.triGlobal = s->triGlobal.as<uint32_t>();
@@ -251,6 +275,8 @@ void refreshDeviceScene(wpt_scene* s)
     d.envM = s->envM.as<float>();
     d.envMs = s->envMs.as<int32_t>();
     d.envMcs = s->envMcs.as<float>();
+    d.envGuide = s->envGuide.as<uint32_t>();
+    d.envGuideBits = s->envGuideBits;
     d.root4 = h.root4;
     d.prefetchLeaves = (h.triData.size() * sizeof(float) > (128u << 10)) ? 1 : 0;
     d.nHot = uint32_t(h.hotSpotRefs.size());
@@ -458,6 +484,7 @@ int wpt_scene_update_bvh(wpt_scene* s, float t0, float t1)
     WPT_CUDA(s->node4.upload(h.nodes4.data(), h.nodes4.size() * sizeof(wpt::Node4)), "upload wide nodes");
     WPT_CUDA(s->bnode.upload(h.bnodes.data(), h.bnodes.size() * sizeof(wpt::BNode)), "upload binary nodes");
     WPT_CUDA(s->tri.upload(h.triData.data(), h.triData.size() * sizeof(float)), "upload triangles");
+    WPT_CUDA(s->triShade.upload(h.triShade.data(), h.triShade.size() * sizeof(uint32_t)), "upload triangle shading records");
     WPT_CUDA(s->sph.upload(h.sphData.data(), h.sphData.size() * sizeof(float)), "upload spheres");
     WPT_CUDA(s->med.upload(h.medData.data(), h.medData.size() * sizeof(float)), "upload media");
     WPT_CUDA(s->triGlobal.upload(h.triGlobal.data(), h.triGlobal.size() * sizeof(uint32_t)), "upload triangle ids");

@@ -47,6 +47,7 @@ struct DScene {
     const float4* node4;
     const float4* bnode;
     const float4* tri;
+    const uint4* triShade;      /* per triangle slot: float offsets of the 3 vertex attribute blocks in `vertices`, mesh flags */
     const float4* sph;
     const float4* med;
     const uint32_t* triGlobal;
@@ -65,6 +66,8 @@ struct DScene {
     const float* envM;
     const int32_t* envMs;
     const float* envMcs;
+    const uint32_t* envGuide;   /* 2^envGuideBits + 1 entries: first bin with Mcs >= j / 2^envGuideBits */
+    int32_t envGuideBits;       /* 0: no guide table */
     int32_t root4;              /* encoded child of the 4-wide tree */
     int32_t prefetchLeaves;     /* triangle data is larger than an SM's L1: ask for a leaf's triangles on arrival */
     uint32_t nHot;

@@ -56,15 +56,13 @@ WPT_DEV HitRec triangleHitRecord(const DScene& S, uint32_t slot, const Ray& ray,
     const bool backfacing = (det < 0.0f);
     const float b0 = invDet * U, b1 = invDet * V, b2 = invDet * W;
 
+    /* vertex attribute blocks and mesh flags were resolved per slot at updateBVH time (scene_host.cpp) */
+    const uint4 sh = __ldg(S.triShade + slot);
     const wpt_instance* inst = S.instances + instIdx;
-    const int32_t meshIdx = inst->mesh;
-    const wpt_mesh* mesh = S.meshes + meshIdx;
-    const uint32_t stride = mesh->vertex_stride;
-    const uint32_t* ix = S.indices + mesh->index_offset + size_t(triIdx) * 3;
-    const float* base = S.vertices + mesh->vertex_offset;
-    const float* p0 = base + size_t(ix[0]) * stride;
-    const float* p1 = base + size_t(ix[1]) * stride;
-    const float* p2 = base + size_t(ix[2]) * stride;
+    const float* p0 = S.vertices + sh.x;
+    const float* p1 = S.vertices + sh.y;
+    const float* p2 = S.vertices + sh.z;
+    const uint32_t meshFlags = sh.w;
     const bool transform = inst->has_transform != 0;
 
     HitRec hr;
@@ -84,12 +82,12 @@ WPT_DEV HitRec triangleHitRecord(const DScene& S, uint32_t slot, const Ray& ray,
     hr.n = n;
 
     hr.tc = make_float2(0.0f, 0.0f);
-    if (mesh->flags & WPT_MESHF_TEXCOORDS) {
+    if (meshFlags & WPT_MESHF_TEXCOORDS) {
         hr.tc.x = (b0 * p0[6] + b1 * p1[6]) + b2 * p2[6];
         hr.tc.y = (b0 * p0[7] + b1 * p1[7]) + b2 * p2[7];
     }
     hr.t = f3(0.0f);
-    if (mesh->flags & WPT_MESHF_TANGENTS) {
+    if (meshFlags & WPT_MESHF_TANGENTS) {
         float3 t = (b0 * f3(p0[8], p0[9], p0[10]) + b1 * f3(p1[8], p1[9], p1[10])) + b2 * f3(p2[8], p2[9], p2[10]);
         if (dot(t, t) > 0.0f) {
             if (transform)
@@ -753,16 +751,33 @@ WPT_DEV float3 envSample(const DScene& S, Prng& prng)
 {
     const int N = S.envN;
     const float r = in01(prng);
-    int a = 0;
-    int b = N * N - 1;
-    while (b > a + 1) {
-        const int c = (a + b) / 2;
-        if (__ldg(S.envMcs + c) < r)
-            a = c;
-        else
-            b = c;
+    int bin;
+    if (S.envGuideBits > 0) {
+        /* the first bin with Mcs >= r (the last bin if there is none), looked for between two entries of
+         * the guide table: the bin the reference's bisection over all N*N bins ends at */
+        const uint32_t j = uint32_t(r * float(1u << S.envGuideBits));
+        int a = int(__ldg(S.envGuide + j));
+        int b = int(__ldg(S.envGuide + j + 1));
+        while (a < b) {
+            const int c = (a + b) / 2;
+            if (__ldg(S.envMcs + c) < r)
+                a = c + 1;
+            else
+                b = c;
+        }
+        bin = a;
+    } else {
+        int a = 0;
+        int b = N * N - 1;
+        while (b > a + 1) {
+            const int c = (a + b) / 2;
+            if (__ldg(S.envMcs + c) < r)
+                a = c;
+            else
+                b = c;
+        }
+        bin = (__ldg(S.envMcs + a) >= r ? a : b);
     }
-    int bin = (__ldg(S.envMcs + a) >= r ? a : b);
     bin = __ldg(S.envMs + bin);
     const int x = bin % N;
     const int y = bin / N;

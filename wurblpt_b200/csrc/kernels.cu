@@ -194,18 +194,22 @@ WPT_DEV void loadItem(const RenderParams& P, unsigned int slot, const int4 item,
     }
 }
 
-template<int F>
-WPT_DEV void loadPath(const RenderParams& P, unsigned int slot, PathState& ps)
+/* Everything a shade kernel needs of a slot with an answered query, as independent loads (none of them
+ * waits for the slot's state word): SHADOW = the slot may be in a shadow-ray state. */
+template<int F, bool SHADOW>
+WPT_DEV Hit loadAnswered(const RenderParams& P, unsigned int slot, PathState& ps, Ctx<F>& ctx)
 {
+    const int4 item = P.W.item[slot];
+    const uint4 r = P.W.prng[slot];
+    const float4 acc = P.W.acc[slot];
     const float4 o = P.W.rayO[slot], d = P.W.rayD[slot];
-    ps.walkRay.o = xyz(o); ps.walkRay.time = o.w;
-    ps.walkRay.d = xyz(d); ps.pathLength = d.w;
-    ps.att = P.W.att[slot];
+    const float4 att = P.W.att[slot];
+    const uint2 hw = P.W.hit[slot];
     if (F & F_OPL) {
         ps.opl = P.W.opl[slot];
         ps.rayRi = P.W.rayRi[slot];
     }
-    if (ps.state != ST_MAIN) {
+    if (SHADOW) {
         ps.nextAtt = P.W.nextAtt[slot];
         const float4 nd = P.W.nextDirHot[slot];
         ps.nextDir = xyz(nd);
@@ -216,6 +220,20 @@ WPT_DEV void loadPath(const RenderParams& P, unsigned int slot, PathState& ps)
             ps.shadowRi = P.W.shadowRi[slot];
         }
     }
+    ps.state = slotState(item.z);
+    ps.pixel = (unsigned int)item.x;
+    ps.sampleIndex = (unsigned int)item.y;
+    ps.sub = (unsigned int)(item.z >> 8);
+    ps.pathComponent = (unsigned int)item.w;
+    ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
+    ps.acc[0] = acc.x; ps.acc[1] = acc.y; ps.acc[2] = acc.z;
+    ps.walkRay.o = xyz(o); ps.walkRay.time = o.w;
+    ps.walkRay.d = xyz(d); ps.pathLength = d.w;
+    ps.att = att;
+    Hit hit;
+    hit.a = __uint_as_float(hw.x);
+    hit.ref = hw.y;
+    return hit;
 }
 
 template<int F>
@@ -379,12 +397,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveLogicKernel(c
         ctx.nested = 0;
         ctx.nodes = ctx.leaves = 0;
         PathState ps;
-        loadItem<F>(P, slot, P.W.item[slot], ps, ctx);
-        loadPath<F>(P, slot, ps);
-        const uint2 hw = P.W.hit[slot];
-        Hit hit;
-        hit.a = __uint_as_float(hw.x);
-        hit.ref = hw.y;
+        const Hit hit = loadAnswered<F, true>(P, slot, ps, ctx);
         animationCacheInit<F>(S, ctx, ps.walkRay.time);
         const RayHelper h = makeRayHelper(ps.walkRay);
         processLogic<F>(S, P, ps, ctx, hit, h);
@@ -407,12 +420,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_MATERIAL_MIN_BLOCKS) waveMaterialKe
         ctx.nested = 0;
         ctx.nodes = ctx.leaves = 0;
         PathState ps;
-        loadItem<F>(P, slot, P.W.item[slot], ps, ctx);
-        loadPath<F>(P, slot, ps);
-        const uint2 hw = P.W.hit[slot];
-        Hit hit;
-        hit.a = __uint_as_float(hw.x);
-        hit.ref = hw.y;
+        const Hit hit = loadAnswered<F, false>(P, slot, ps, ctx);   /* material entries are camera / bounce rays */
         animationCacheInit<F>(S, ctx, ps.walkRay.time);
         const RayHelper h = makeRayHelper(ps.walkRay);
         processHit<F>(S, P, ps, ctx, hit, h);

@@ -717,6 +717,22 @@ int HostScene::updateBvh(float t0, float t1)
         d[4] = v[1].x; d[5] = v[1].y; d[6] = v[1].z; d[7] = bits(p.tri);
         d[8] = v[2].x; d[9] = v[2].y; d[10] = v[2].z; d[11] = bits(uint32_t(in.animation + 1));
     }
+    /* what the hit record needs per triangle, resolved once: mesh -> index buffer -> vertex blocks */
+    if (vertices.size() >= (size_t(1) << 32)) {
+        error = "more than 2^32 vertex attribute floats";
+        return WPT_E_UNSUPPORTED;
+    }
+    triShade.resize(triGlobal.size() * 4);
+    #pragma omp parallel for schedule(static)
+    for (size_t s = 0; s < triGlobal.size(); s++) {
+        const Prim& p = prims[triGlobal[s]];
+        const wpt_mesh& mesh = meshes[instances[p.ref].mesh];
+        const uint32_t* ix = indices.data() + mesh.index_offset + size_t(p.tri) * 3;
+        uint32_t* d = triShade.data() + s * 4;
+        for (int k = 0; k < 3; k++)
+            d[k] = uint32_t(mesh.vertex_offset + size_t(ix[k]) * mesh.vertex_stride);
+        d[3] = mesh.flags;
+    }
     sphData.resize(sphGlobal.size() * 12);
     for (size_t s = 0; s < sphGlobal.size(); s++) {
         const wpt_sphere& sp = spheres[prims[sphGlobal[s]].ref];

@@ -95,6 +95,8 @@ struct HostScene {
     std::vector<uint32_t> refOfGlobal;      /* global id -> device leaf reference */
     std::vector<uint32_t> triGlobal, sphGlobal, medGlobal;  /* slot -> global id */
     std::vector<float> triData;             /* 12 floats per triangle slot */
+    std::vector<uint32_t> triShade;         /* 4 words per triangle slot: offsets of the three vertices' attribute
+                                               blocks in `vertices` (floats), mesh flags */
     std::vector<float> sphData;             /* 12 floats per sphere slot */
     std::vector<float> medData;             /* 4 floats per medium slot */
     std::vector<uint32_t> hotSpotRefs;      /* device leaf references of the hot spots */
