@@ -37,8 +37,11 @@ constexpr int F_ANIM = 2;       /* scene contains animated hitables */
 constexpr int F_OPL = 4;        /* track optical path length / refractive index (ToF sensor, gated RGB) */
 constexpr int F_COUNT = 8;      /* count node visits and leaf tests (query kernels only) */
 
-constexpr int SM_STACK = 12;    /* shared-memory stack entries per thread */
-constexpr int LOCAL_STACK = 84; /* spill entries per thread (local memory, touched only when deep) */
+#ifndef WPT_SM_STACK
+#define WPT_SM_STACK 12
+#endif
+constexpr int SM_STACK = WPT_SM_STACK;          /* shared-memory stack entries per thread */
+constexpr int LOCAL_STACK = 96 - SM_STACK;      /* spill entries per thread (local memory, touched only when deep) */
 constexpr int BINARY_STACK = 128;   /* BVH::maxTreeDepth, bvh.hpp:230 */
 
 struct Ray {
