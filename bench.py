@@ -304,11 +304,15 @@ def main():
     if work:
         algo_bytes = rays_rank * work["bytes_per_query"]
         achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-        traffic = load_json(os.path.join(ROOT, "profiles", "r1_dram_traffic.json"), {}).get(scene_name)
+        # DRAM bytes per closest-hit query from the committed ncu capture (all kernels of the step), scaled to
+        # this launch's query count like `achieved`; None for workloads without a capture
+        measured = load_json(os.path.join(ROOT, "profiles", "r1_dram_traffic.json"), {}).get(scene_name)
+        traffic = rays_rank * measured["bytes_per_query"] if (measured and launches_per_step > 2) else None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "kernel": "renderKernel (megakernel)" if launches_per_step <= 2 else
-                    "waveTracePersistentKernel + waveLogicKernel + waveMaterialKernel (one mcpt = %d launches)" % launches_per_step,
+                    "one mcpt() = %d launches of waveTracePersistentKernel (dominant, ~66 %% of the time), waveSortKernel, "
+                    "waveLogicKernel, waveMaterialKernel; timed as a whole" % launches_per_step,
                     "kernel_ms": kernel_ms,
                     "queries_per_launch": rays_rank, "bytes_per_query": work["bytes_per_query"],
                     "nodes_per_query": work["nodes_per_query"], "leaves_per_query": work["leaves_per_query"],
