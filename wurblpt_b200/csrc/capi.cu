@@ -125,7 +125,7 @@ struct wpt_scene {
     /* per updateBVH */
     DeviceBuf node4, bnode, tri, triShade, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs;
     /* per call scratch */
-    DeviceBuf counters, camKeys, frame, partials, wave[15], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds;
+    DeviceBuf counters, camKeys, frame, partials, wave[17], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds;
     cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaStream_t stream2 = nullptr;
     unsigned long long* hostDone = nullptr;     /* pinned, 2 counters */
@@ -689,27 +689,35 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
             slots = P.nItems;
         P.W.nSlots = slots;
         const size_t n = slots;
-        const size_t sizes[14] = { sizeof(int4), sizeof(uint4), sizeof(float4), sizeof(float4), sizeof(uint2), sizeof(float4),
-            sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4) };
+        /* wave[1], [2], [8] hold interleaved pairs (see WaveState); [3], [5], [9] are unused */
+        const size_t sizes[14] = { sizeof(int4), 2 * sizeof(uint4), 2 * sizeof(float4), 0, sizeof(uint2), 0,
+            sizeof(float4), sizeof(float4), 2 * sizeof(float4), 0, sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4) };
         const int used = (features != 0 ? 14 : 10);
         for (int k = 0; k < used; k++)
-            WPT_CUDA(s->wave[k].reserve(n * sizes[k]), "allocate wavefront state");
+            if (sizes[k])
+                WPT_CUDA(s->wave[k].reserve(n * sizes[k]), "allocate wavefront state");
         P.W.item = static_cast<int4*>(s->wave[0].p);
         P.W.prng = static_cast<uint4*>(s->wave[1].p);
+        P.W.acc = static_cast<float4*>(s->wave[1].p) + 1;
         P.W.rayO = static_cast<float4*>(s->wave[2].p);
-        P.W.rayD = static_cast<float4*>(s->wave[3].p);
+        P.W.rayD = static_cast<float4*>(s->wave[2].p) + 1;
         P.W.hit = static_cast<uint2*>(s->wave[4].p);
-        P.W.acc = static_cast<float4*>(s->wave[5].p);
         P.W.att = static_cast<float4*>(s->wave[6].p);
         P.W.nextAtt = static_cast<float4*>(s->wave[7].p);
         P.W.nextDirHot = static_cast<float4*>(s->wave[8].p);
-        P.W.pendRad = static_cast<float4*>(s->wave[9].p);
+        P.W.pendRad = static_cast<float4*>(s->wave[8].p) + 1;
         P.W.opl = static_cast<float4*>(s->wave[10].p);
         P.W.rayRi = static_cast<float4*>(s->wave[11].p);
         P.W.nextRi = static_cast<float4*>(s->wave[12].p);
         P.W.shadowRi = static_cast<float4*>(s->wave[13].p);
         WPT_CUDA(s->wave[14].reserve(n * sizeof(uint32_t)), "allocate shade queues");
         P.W.queue = static_cast<uint32_t*>(s->wave[14].p);
+        WPT_CUDA(s->wave[15].reserve(n * sizeof(uint32_t)), "allocate trace queue");
+        P.W.traceQueue = static_cast<uint32_t*>(s->wave[15].p);
+        const size_t windows = (n + wptd::WAVE_WINDOW - 1) / wptd::WAVE_WINDOW + 2;
+        WPT_CUDA(s->wave[16].reserve(windows * sizeof(uint2)), "allocate window state");
+        WPT_CUDA(cudaMemsetAsync(s->wave[16].p, 0, windows * sizeof(uint2), stream), "clear window state");
+        P.W.window = static_cast<uint2*>(s->wave[16].p);
         P.W.group = 0;
         if (features == 0)
             P.W.opl = P.W.rayRi = P.W.nextRi = P.W.shadowRi = nullptr;

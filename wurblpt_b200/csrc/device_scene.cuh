@@ -78,8 +78,10 @@ struct DScene {
 
 constexpr int MAX_CACHED_ANIMATIONS = 4;    /* per-thread animation cache entries (AnimationCache) */
 
-/* Wavefront slot arrays (structure of arrays, one element per slot; thread i <-> slot i, so every
- * access is a coalesced 8- or 16-byte load/store). */
+/* Wavefront slot arrays (structure of arrays). The kernels reach the slots through queues, i.e. in
+ * scattered order, so fields that are always used together are interleaved in pairs that fill one
+ * 32-byte sector: (rayO, rayD), (prng, acc), (nextDirHot, pendRad) are indexed [2 * slot]; the second
+ * pointer of a pair is the first plus one element. The other arrays are indexed [slot]. */
 struct WaveState {
     int4* item;         /* pixel, sampleIndex, state | sub << 8 (all ones = idle), pathComponent */
     uint4* prng;        /* xoshiro128+ state of the item's stream */
@@ -94,9 +96,13 @@ struct WaveState {
     float4* opl; float4* rayRi; float4* nextRi; float4* shadowRi;  /* F_OPL only */
     uint32_t* queue;    /* nSlots entries filled by the sort kernel: slots whose surface hit is to be shaded from
                            the front (material queue), all other answered queries from the back (logic queue) */
+    uint32_t* traceQueue;   /* nSlots entries filled by the generate kernel: slots with a new camera ray from the
+                               front, slots with a bounce or shadow ray from the back */
+    uint2* window;      /* per window of WAVE_WINDOW slots: the block of work items it hands out (next, end) */
     uint32_t nSlots;
     uint32_t group;     /* slot group (0 or 1): selects the group's trace ticket / queue length counters */
 };
+constexpr uint32_t WAVE_WINDOW = 256;       /* slots per window = work items per block */
 
 /* Counter words (64 bit). Every hot counter has a 128-byte line of its own so that atomics on different
  * counters do not meet in one L2 sector. */
@@ -109,7 +115,9 @@ enum : int {
     CTR_TICKET = 80,        /* + 16 * group: slot ticket of the persistent trace kernel */
     CTR_MATERIAL = 112,     /* + 16 * group: material queue length */
     CTR_LOGIC = 144,        /* + 16 * group: logic queue length */
-    CTR_WORDS = 176
+    CTR_TRACE_CAMERA = 176, /* + 16 * group: trace queue, camera rays */
+    CTR_TRACE_OTHER = 208,  /* + 16 * group: trace queue, bounce and shadow rays */
+    CTR_WORDS = 240
 };
 
 struct RenderParams {

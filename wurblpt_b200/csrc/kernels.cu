@@ -49,6 +49,9 @@ namespace wptd {
 #ifndef WPT_PREFETCH_LEAF
 #define WPT_PREFETCH_LEAF 1
 #endif
+#ifndef WPT_CAMERA_REFILL_MIN
+#define WPT_CAMERA_REFILL_MIN 32
+#endif
 #ifndef WPT_LEAF_MIN
 #define WPT_LEAF_MIN 12     /* lanes that must be at a leaf before the persistent trace kernel runs a leaf round */
 #endif
@@ -187,9 +190,9 @@ WPT_DEV void loadItem(const RenderParams& P, unsigned int slot, const int4 item,
     ps.sub = (item.z < 0 ? 0u : (unsigned int)(item.z >> 8));
     ps.pathComponent = (unsigned int)item.w;
     if (ps.state != ST_IDLE) {
-        const uint4 r = P.W.prng[slot];
+        const uint4 r = P.W.prng[2 * slot];
         ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
-        const float4 acc = P.W.acc[slot];
+        const float4 acc = P.W.acc[2 * slot];
         ps.acc[0] = acc.x; ps.acc[1] = acc.y; ps.acc[2] = acc.z;
     }
 }
@@ -200,9 +203,9 @@ template<int F, bool SHADOW>
 WPT_DEV Hit loadAnswered(const RenderParams& P, unsigned int slot, PathState& ps, Ctx<F>& ctx)
 {
     const int4 item = P.W.item[slot];
-    const uint4 r = P.W.prng[slot];
-    const float4 acc = P.W.acc[slot];
-    const float4 o = P.W.rayO[slot], d = P.W.rayD[slot];
+    const uint4 r = P.W.prng[2 * slot];
+    const float4 acc = P.W.acc[2 * slot];
+    const float4 o = P.W.rayO[2 * slot], d = P.W.rayD[2 * slot];
     const float4 att = P.W.att[slot];
     const uint2 hw = P.W.hit[slot];
     if (F & F_OPL) {
@@ -211,10 +214,10 @@ WPT_DEV Hit loadAnswered(const RenderParams& P, unsigned int slot, PathState& ps
     }
     if (SHADOW) {
         ps.nextAtt = P.W.nextAtt[slot];
-        const float4 nd = P.W.nextDirHot[slot];
+        const float4 nd = P.W.nextDirHot[2 * slot];
         ps.nextDir = xyz(nd);
         ps.pendHot = __float_as_uint(nd.w);
-        ps.pendRad = P.W.pendRad[slot];
+        ps.pendRad = P.W.pendRad[2 * slot];
         if (F & F_OPL) {
             ps.nextRi = P.W.nextRi[slot];
             ps.shadowRi = P.W.shadowRi[slot];
@@ -242,10 +245,12 @@ WPT_DEV void storeSlot(const RenderParams& P, unsigned int slot, const PathState
     P.W.item[slot] = make_int4(int(ps.pixel), int(ps.sampleIndex), ps.state | int(ps.sub << 8), int(ps.pathComponent));
     if (ps.state == ST_EXHAUSTED)
         return;
-    P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
-    P.W.acc[slot] = f4(ps.acc[0], ps.acc[1], ps.acc[2], 0.0f);
-    P.W.rayO[slot] = f4(ps.walkRay.o, ps.walkRay.time);
-    P.W.rayD[slot] = f4(ps.walkRay.d, ps.pathLength);
+    P.W.prng[2 * slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
+    P.W.acc[2 * slot] = f4(ps.acc[0], ps.acc[1], ps.acc[2], 0.0f);
+    if (ps.state == ST_NEW)
+        return;     /* path ended: the generate kernel starts the next sample */
+    P.W.rayO[2 * slot] = f4(ps.walkRay.o, ps.walkRay.time);
+    P.W.rayD[2 * slot] = f4(ps.walkRay.d, ps.pathLength);
     P.W.att[slot] = ps.att;
     if (F & F_OPL) {
         P.W.opl[slot] = ps.opl;
@@ -253,8 +258,8 @@ WPT_DEV void storeSlot(const RenderParams& P, unsigned int slot, const PathState
     }
     if (ps.state != ST_MAIN) {
         P.W.nextAtt[slot] = ps.nextAtt;
-        P.W.nextDirHot[slot] = f4(ps.nextDir, __uint_as_float(ps.pendHot));
-        P.W.pendRad[slot] = ps.pendRad;
+        P.W.nextDirHot[2 * slot] = f4(ps.nextDir, __uint_as_float(ps.pendHot));
+        P.W.pendRad[2 * slot] = ps.pendRad;
         if (F & F_OPL) {
             P.W.nextRi[slot] = ps.nextRi;
             P.W.shadowRi[slot] = ps.shadowRi;
@@ -262,37 +267,25 @@ WPT_DEV void storeSlot(const RenderParams& P, unsigned int slot, const PathState
     }
 }
 
-/* No query pending: start the next sample, the next item, or retire the slot. Returns the number of
- * samples started. */
-template<int F>
-WPT_DEV unsigned int refillSlot(const DScene& S, const RenderParams& P, PathState& ps, Ctx<F>& ctx)
-{
-    unsigned int started = 0;
-    while (ps.state == ST_NEW || ps.state == ST_IDLE) {
-        if (ps.state == ST_IDLE) {
-            const unsigned int it = (unsigned int)atomicAdd(P.counters + CTR_ITEM, 1ull);
-            if (it >= P.nItems) {
-                ps.state = ST_EXHAUSTED;
-                atomicAdd(P.counters + CTR_DONE, 1ull);
-                break;
-            }
-            const WorkItem w = decodeItem(P, it);
-            if (w.valid)
-                beginItem<F>(ps, ctx, w);
-        } else if (startSample<F>(S, P, ps, ctx)) {
-            started++;
-        } else {
-            finishItem(P, ps);
-            ps.state = ST_IDLE;
-        }
-    }
-    return started;
-}
-
 /* ---- per-group counters ---- */
 WPT_DEV unsigned long long* ctrTicket(const RenderParams& P) { return P.counters + CTR_TICKET + 16 * P.W.group; }
 WPT_DEV unsigned long long* ctrMaterial(const RenderParams& P) { return P.counters + CTR_MATERIAL + 16 * P.W.group; }
 WPT_DEV unsigned long long* ctrLogic(const RenderParams& P) { return P.counters + CTR_LOGIC + 16 * P.W.group; }
+WPT_DEV unsigned long long* ctrTraceCamera(const RenderParams& P) { return P.counters + CTR_TRACE_CAMERA + 16 * P.W.group; }
+WPT_DEV unsigned long long* ctrTraceOther(const RenderParams& P) { return P.counters + CTR_TRACE_OTHER + 16 * P.W.group; }
+
+/* Entry p of the trace queue (camera rays from the front, the others from the back). */
+WPT_DEV unsigned int traceQueueSlot(const RenderParams& P, unsigned int p, unsigned int nCamera)
+{
+    return p < nCamera ? P.W.traceQueue[p] : P.W.traceQueue[P.W.nSlots - 1u - (p - nCamera)];
+}
+
+WPT_DEV void countSamples(const RenderParams& P, unsigned int newSamples)
+{
+    const unsigned int n = __reduce_add_sync(0xFFFFFFFFu, newSamples);
+    if ((threadIdx.x & 31u) == 0u && n != 0u)
+        atomicAdd(P.counters + CTR_SAMPLES, (unsigned long long)n);
+}
 
 /* Which kernel finishes an answered query: a camera or bounce ray that hit a surface which is still to
  * be shaded goes to waveMaterialKernel (the case in which processLogic() returns true), everything
@@ -320,8 +313,11 @@ __global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_consta
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned below = (1u << lane) - 1u;
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        *ctrTicket(P) = 0ull;       /* slot ticket of the next (persistent) trace launch */
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *ctrTicket(P) = 0ull;       /* ticket of the next (persistent) trace launch */
+        *ctrTraceCamera(P) = 0ull;  /* trace queue lengths: the trace kernel is done with them, the generate kernel */
+        *ctrTraceOther(P) = 0ull;   /* of this round counts them up again */
+    }
     uint32_t* matList = lists[warp][0];
     uint32_t* logList = lists[warp][1];
     const unsigned int windowBase = (blockIdx.x * (SORT_BLOCK / 32u) + warp) * SORT_WINDOW;
@@ -357,29 +353,123 @@ __global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_consta
         P.W.queue[P.W.nSlots - 1u - (logBase + e)] = logList[e];
 }
 
-WPT_DEV void countSamples(const RenderParams& P, unsigned int newSamples)
-{
-    const unsigned int n = __reduce_add_sync(0xFFFFFFFFu, newSamples);
-    if ((threadIdx.x & 31u) == 0u && n != 0u)
-        atomicAdd(P.counters + CTR_SAMPLES, (unsigned long long)n);
-}
 
-/* First launch of a frame: every slot fetches a work item and its first camera ray. */
+/* Generate: starts the next sample (camera ray) of every slot whose path has ended, hands out work
+ * items, retires slots when none are left, and lists the slots to trace. One warp per window of
+ * WAVE_WINDOW consecutive slots; a window takes its work items from a block of WAVE_WINDOW consecutive
+ * items at a time (MPICoordinator::getBlock, mpi.hpp:241-254, as a device atomic), so the slots of a
+ * window always work on neighbouring pixels and their camera rays - listed first in the trace queue,
+ * window by window - walk the tree together. */
 template<int F>
-__global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveInitKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+__global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
-    const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
-    unsigned int newSamples = 0;
-    if (slot < P.W.nSlots) {
-        Ctx<F> ctx;
-        ctx.nested = 0;
-        ctx.nodes = ctx.leaves = 0;
-        PathState ps;
-        loadItem<F>(P, slot, make_int4(-1, -1, -1, -1), ps, ctx);
-        newSamples = refillSlot<F>(S, P, ps, ctx);
-        storeSlot<F>(P, slot, ps, ctx);
+    __shared__ uint32_t lists[BLOCK / 32][2][WAVE_WINDOW];
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned below = (1u << lane) - 1u;
+    const unsigned int w = blockIdx.x * (BLOCK / 32u) + warp;
+    const unsigned int windowBase = w * WAVE_WINDOW;
+    if (windowBase >= P.W.nSlots)
+        return;
+    uint32_t* camList = lists[warp][0];
+    uint32_t* otherList = lists[warp][1];
+    uint2 block = P.W.window[w];            /* x = next item, y = end of the block; x = ~0: no items left */
+    unsigned int nCam = 0, nOther = 0, newSamples = 0, retired = 0;
+    for (unsigned int k = 0; k < WAVE_WINDOW / 32u; k++) {
+        const unsigned int slot = windowBase + k * 32u + lane;
+        const bool valid = slot < P.W.nSlots;
+        int4 item = make_int4(0, 0, ST_EXHAUSTED, 0);
+        if (valid)
+            item = P.W.item[slot];
+        int state = slotState(item.z);
+        unsigned int pathComponent = (unsigned int)item.w;
+        const bool generate = valid && (state == ST_NEW || state == ST_IDLE);
+        if (__any_sync(FULL, generate)) {
+            Ctx<F> ctx;
+            ctx.nested = 0;
+            ctx.nodes = ctx.leaves = 0;
+            PathState ps;
+            ps.state = ST_EXHAUSTED;
+            if (generate)
+                loadItem<F>(P, slot, item, ps, ctx);
+            bool working = generate;
+            while (__any_sync(FULL, working)) {
+                if (working && ps.state == ST_NEW) {
+                    if (startSample<F>(S, P, ps, ctx)) {
+                        newSamples++;
+                        working = false;
+                    } else {
+                        finishItem(P, ps);
+                        ps.state = ST_IDLE;
+                    }
+                }
+                const bool wantItem = working && ps.state == ST_IDLE;
+                const unsigned wantMask = __ballot_sync(FULL, wantItem);
+                if (wantMask != 0u) {
+                    if (block.x == block.y && block.x != 0xFFFFFFFFu) {     /* the window's block is used up */
+                        unsigned int base = 0;
+                        if (lane == 0)
+                            base = (unsigned int)atomicAdd(P.counters + CTR_ITEM, (unsigned long long)WAVE_WINDOW);
+                        base = __shfl_sync(FULL, base, 0);
+                        if (base >= P.nItems)
+                            block = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+                        else
+                            block = make_uint2(base, min(base + WAVE_WINDOW, P.nItems));
+                    }
+                    const unsigned int avail = block.y - block.x;
+                    const unsigned int rank = __popc(wantMask & below);
+                    if (wantItem) {
+                        if (block.x == 0xFFFFFFFFu) {
+                            ps.state = ST_EXHAUSTED;
+                            working = false;
+                            retired++;
+                        } else if (rank < avail) {
+                            const WorkItem wi = decodeItem(P, block.x + rank);
+                            if (wi.valid)
+                                beginItem<F>(ps, ctx, wi);      /* -> ST_NEW */
+                        }
+                    }
+                    if (block.x != 0xFFFFFFFFu)
+                        block.x += min((unsigned int)__popc(wantMask), avail);
+                }
+            }
+            if (generate) {
+                storeSlot<F>(P, slot, ps, ctx);
+                state = ps.state;
+                pathComponent = ps.pathComponent;
+            }
+        }
+        /* trace queue: camera rays of the window first */
+        const bool traceable = (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV);
+        const bool camera = traceable && state == ST_MAIN && pathComponent == 0u;
+        const unsigned camMask = __ballot_sync(FULL, camera);
+        const unsigned otherMask = __ballot_sync(FULL, traceable && !camera);
+        if (camera)
+            camList[nCam + __popc(camMask & below)] = slot;
+        if (traceable && !camera)
+            otherList[nOther + __popc(otherMask & below)] = slot;
+        nCam += __popc(camMask);
+        nOther += __popc(otherMask);
     }
+    __syncwarp();
+    unsigned int camBase = 0, otherBase = 0;
+    if (lane == 0) {
+        P.W.window[w] = block;
+        if (nCam)
+            camBase = (unsigned int)atomicAdd(ctrTraceCamera(P), (unsigned long long)nCam);
+        if (nOther)
+            otherBase = (unsigned int)atomicAdd(ctrTraceOther(P), (unsigned long long)nOther);
+    }
+    camBase = __shfl_sync(FULL, camBase, 0);
+    otherBase = __shfl_sync(FULL, otherBase, 0);
+    for (unsigned int e = lane; e < nCam; e += 32u)
+        P.W.traceQueue[camBase + e] = camList[e];
+    for (unsigned int e = lane; e < nOther; e += 32u)
+        P.W.traceQueue[P.W.nSlots - 1u - (otherBase + e)] = otherList[e];
     countSamples(P, newSamples);
+    const unsigned int r = __reduce_add_sync(FULL, retired);
+    if (lane == 0 && r != 0u)
+        atomicAdd(P.counters + CTR_DONE, (unsigned long long)r);
 }
 
 /* Logic: everything after a query except shading a surface hit -- rays that left the scene, shadow-ray
@@ -390,7 +480,6 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveLogicKernel(c
 {
     const unsigned int i = blockIdx.x * BLOCK + threadIdx.x;
     const unsigned int count = (unsigned int)*ctrLogic(P);
-    unsigned int newSamples = 0;
     if (i < count) {
         const unsigned int slot = P.W.queue[P.W.nSlots - 1u - i];
         Ctx<F> ctx;
@@ -401,10 +490,8 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveLogicKernel(c
         animationCacheInit<F>(S, ctx, ps.walkRay.time);
         const RayHelper h = makeRayHelper(ps.walkRay);
         processLogic<F>(S, P, ps, ctx, hit, h);
-        newSamples = refillSlot<F>(S, P, ps, ctx);
         storeSlot<F>(P, slot, ps, ctx);
     }
-    countSamples(P, newSamples);
 }
 
 /* Material: shade the surface hits of camera and bounce rays. One thread per entry of the material queue. */
@@ -413,7 +500,6 @@ __global__ void __launch_bounds__(BLOCK, WPT_MATERIAL_MIN_BLOCKS) waveMaterialKe
 {
     const unsigned int i = blockIdx.x * BLOCK + threadIdx.x;
     const unsigned int count = (unsigned int)*ctrMaterial(P);
-    unsigned int newSamples = 0;
     if (i < count) {
         const unsigned int slot = P.W.queue[i];
         Ctx<F> ctx;
@@ -424,10 +510,8 @@ __global__ void __launch_bounds__(BLOCK, WPT_MATERIAL_MIN_BLOCKS) waveMaterialKe
         animationCacheInit<F>(S, ctx, ps.walkRay.time);
         const RayHelper h = makeRayHelper(ps.walkRay);
         processHit<F>(S, P, ps, ctx, hit, h);
-        newSamples = refillSlot<F>(S, P, ps, ctx);
         storeSlot<F>(P, slot, ps, ctx);
     }
-    countSamples(P, newSamples);
 }
 
 /* Trace: the closest-hit query of every slot that has one pending. */
@@ -436,23 +520,25 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
 {
     extern __shared__ uint2 smStackAll[];
     uint2* smStack = smStackAll + threadIdx.x;
-    const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
-    if (slot == 0) {        /* queue lengths of this round (the sort kernel that follows counts them up) */
+    const unsigned int p = blockIdx.x * BLOCK + threadIdx.x;
+    if (p == 0) {           /* queue lengths of this round (the sort kernel that follows counts them up) */
         *ctrMaterial(P) = 0ull;
         *ctrLogic(P) = 0ull;
     }
+    const unsigned int nCamera = (unsigned int)*ctrTraceCamera(P);
+    const unsigned int nQueued = nCamera + (unsigned int)*ctrTraceOther(P);
     unsigned int traced = 0;
     Ctx<F> ctx;
     ctx.nested = 0;
     ctx.nodes = ctx.leaves = 0;
-    if (slot < P.W.nSlots) {
-        const int state = slotState(P.W.item[slot].z);
-        if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV) {
-            const float4 o = P.W.rayO[slot], d = P.W.rayD[slot];
+    if (p < nQueued) {
+        const unsigned int slot = traceQueueSlot(P, p, nCamera);
+        {
+            const float4 o = P.W.rayO[2 * slot], d = P.W.rayD[2 * slot];
             Ray ray;
             ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
             if (F & F_MEDIA) {
-                const uint4 r = P.W.prng[slot];
+                const uint4 r = P.W.prng[2 * slot];
                 ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
             }
             animationCacheInit<F>(S, ctx, ray.time);
@@ -460,7 +546,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
             const Hit hit = closestHit<F>(S, P, ray, h, ctx, smStack);
             P.W.hit[slot] = make_uint2(__float_as_uint(hit.a), hit.ref);
             if (F & F_MEDIA)
-                P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
+                P.W.prng[2 * slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
             traced = 1;
         }
     }
@@ -495,6 +581,8 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
         *ctrLogic(P) = 0ull;
     }
 
+    const unsigned int nCamera = (unsigned int)*ctrTraceCamera(P);
+    const unsigned int nQueued = nCamera + (unsigned int)*ctrTraceOther(P);
     unsigned int slot = 0;
     bool active = false, exhausted = false;
     Ray ray;
@@ -521,15 +609,17 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     for (;;) {
         const unsigned wantMask = __ballot_sync(FULL, !active && !exhausted);
         const unsigned busyMask = __ballot_sync(FULL, active);
-        if (wantMask != 0u && (__popc(wantMask) >= REFILL_MIN || busyMask == 0u)) {
+        /* camera rays of one window are coherent: they are started 32 at a time so that they stay together */
+        const int refillMin = (warpNext < warpEnd && warpNext < nCamera) ? WPT_CAMERA_REFILL_MIN : REFILL_MIN;
+        if (wantMask != 0u && (__popc(wantMask) >= refillMin || busyMask == 0u)) {
             if (warpNext >= warpEnd && !drained) {
                 unsigned int base = 0;
                 if (lane == 0)
                     base = (unsigned int)atomicAdd(ctrTicket(P), (unsigned long long)CHUNK);
                 base = __shfl_sync(FULL, base, 0);
                 warpNext = base;
-                warpEnd = min(base + CHUNK, P.W.nSlots);
-                if (base >= P.W.nSlots) {
+                warpEnd = min(base + CHUNK, nQueued);
+                if (base >= nQueued) {
                     drained = true;
                     warpNext = warpEnd = 0;
                 }
@@ -538,24 +628,21 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
             const unsigned int rank = __popc(wantMask & laneBelow);
             if (!active && !exhausted) {
                 if (rank < avail) {
-                    const unsigned int s = warpNext + rank;
-                    const int state = slotState(P.W.item[s].z);
-                    if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV) {
-                        const float4 o = P.W.rayO[s], d = P.W.rayD[s];
-                        ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
-                        if (F & F_MEDIA) {
-                            const uint4 r = P.W.prng[s];
-                            ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
-                        }
-                        animationCacheInit<F>(S, ctx, ray.time);
-                        h = makeRayHelper(ray);
-                        slot = s;
-                        active = true;
-                        best.hit.a = MAXVAL;
-                        best.hit.ref = NO_HIT;
-                        st.sp = 0;
-                        cur = S.root4;
+                    const unsigned int s = traceQueueSlot(P, warpNext + rank, nCamera);
+                    const float4 o = P.W.rayO[2 * s], d = P.W.rayD[2 * s];
+                    ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
+                    if (F & F_MEDIA) {
+                        const uint4 r = P.W.prng[2 * s];
+                        ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
                     }
+                    animationCacheInit<F>(S, ctx, ray.time);
+                    h = makeRayHelper(ray);
+                    slot = s;
+                    active = true;
+                    best.hit.a = MAXVAL;
+                    best.hit.ref = NO_HIT;
+                    st.sp = 0;
+                    cur = S.root4;
                 } else if (drained) {
                     exhausted = true;
                 }
@@ -611,7 +698,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
         if (cur == EMPTY_CHILD) {
             P.W.hit[slot] = make_uint2(__float_as_uint(best.hit.a), best.hit.ref);
             if (F & F_MEDIA)
-                P.W.prng[slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
+                P.W.prng[2 * slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
             active = false;
             traced++;
         }
@@ -897,10 +984,12 @@ static RenderParams slotGroup(const RenderParams& P, uint32_t group, uint32_t fi
     RenderParams G = P;
     G.W.group = group;
     G.W.nSlots = count;
-    G.W.item += first; G.W.prng += first; G.W.rayO += first; G.W.rayD += first; G.W.hit += first;
-    G.W.acc += first; G.W.att += first; G.W.nextAtt += first; G.W.nextDirHot += first; G.W.pendRad += first;
+    G.W.item += first; G.W.prng += 2 * first; G.W.rayO += 2 * first; G.W.rayD += 2 * first; G.W.hit += first;
+    G.W.acc += 2 * first; G.W.att += first; G.W.nextAtt += first; G.W.nextDirHot += 2 * first; G.W.pendRad += 2 * first;
     if (G.W.opl) { G.W.opl += first; G.W.rayRi += first; G.W.nextRi += first; G.W.shadowRi += first; }
     G.W.queue += first;
+    G.W.traceQueue += first;
+    G.W.window += first / WAVE_WINDOW;
     return G;
 }
 
@@ -930,7 +1019,7 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
     RenderParams G[2];
     unsigned int grid[2], sgrid[2], pgrid[2];
     cudaStream_t st[2] = { stream, stream2 };
-    const uint32_t half = (nGroups == 2 ? (P.W.nSlots / 2 + BLOCK - 1) / BLOCK * BLOCK : P.W.nSlots);
+    const uint32_t half = (nGroups == 2 ? (P.W.nSlots / 2 + WAVE_WINDOW - 1) / WAVE_WINDOW * WAVE_WINDOW : P.W.nSlots);
     for (int g = 0; g < nGroups; g++) {
         const uint32_t first = (g == 0 ? 0 : half);
         const uint32_t count = (g == 0 ? half : P.W.nSlots - half);
@@ -953,7 +1042,7 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
         if ((e = cudaStreamWaitEvent(stream2, events[2], 0)) != cudaSuccess) return e;
     }
     for (int g = 0; g < nGroups; g++)
-        waveInitKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, G[g]);   /* gives every slot its first camera ray */
+        waveGenerateKernel<F><<<sgrid[g], BLOCK, 0, st[g]>>>(S, G[g]);      /* every slot gets an item and its first camera ray */
     n += nGroups;
     hostDone[0] = hostDone[1] = 0;
     for (int k = 0;; k++) {
@@ -967,9 +1056,10 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
                 waveSortKernel<<<sgrid[g], SORT_BLOCK, 0, st[g]>>>(R);
                 waveLogicKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, R);
                 waveMaterialKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, R);
+                waveGenerateKernel<F><<<sgrid[g], BLOCK, 0, st[g]>>>(S, R);
             }
         }
-        n += 4 * batch * nGroups;
+        n += 5 * batch * nGroups;
         if (nGroups == 2) {     /* join the second stream before reading the counter */
             if ((e = cudaEventRecord(events[3], stream2)) != cudaSuccess) return e;
             if ((e = cudaStreamWaitEvent(stream, events[3], 0)) != cudaSuccess) return e;
