@@ -635,7 +635,7 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
          * items keep the tail, where few lanes still have work, short */
         const uint64_t pixels = uint64_t(sensor->width) * sensor->height;
         const uint64_t wantItems = 8ull * waveSlotLimit();
-        while (sub < 32 && pixels * sub < wantItems && sub * 2 <= P.samples && (P.samples / (sub * 2)) >= 8)
+        while (sub < 32 && pixels * sub < wantItems && sub * 2 <= P.samples && (P.samples / (sub * 2)) >= 4)
             sub *= 2;
     }
     while (sub > P.samples && sub > 1)
