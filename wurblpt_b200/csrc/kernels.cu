@@ -305,6 +305,7 @@ WPT_DEV int queueOf(const RenderParams& P, int4 item, uint32_t hitRef)
  * neighbours in the slot arrays (whole sectors) and every one of its lanes has work. Two atomics per
  * window. */
 constexpr unsigned int SORT_WINDOW = 256;       /* slots per warp */
+constexpr unsigned int TRACE_CLASSES = 9;       /* see waveGenerateKernel */
 constexpr unsigned int SORT_BLOCK = 128;
 
 __global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_constant__ RenderParams P)
@@ -363,7 +364,9 @@ __global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_consta
 template<int F>
 __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
-    __shared__ uint32_t lists[BLOCK / 32][2][WAVE_WINDOW];
+    /* per warp: the trace class of each slot of the window, then the slots listed class by class */
+    __shared__ uint8_t classOf[BLOCK / 32][WAVE_WINDOW];
+    __shared__ uint32_t lists[BLOCK / 32][WAVE_WINDOW];
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned below = (1u << lane) - 1u;
@@ -371,10 +374,8 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
     const unsigned int windowBase = w * WAVE_WINDOW;
     if (windowBase >= P.W.nSlots)
         return;
-    uint32_t* camList = lists[warp][0];
-    uint32_t* otherList = lists[warp][1];
     uint2 block = P.W.window[w];            /* x = next item, y = end of the block; x = ~0: no items left */
-    unsigned int nCam = 0, nOther = 0, newSamples = 0, retired = 0;
+    unsigned int newSamples = 0, retired = 0;
     for (unsigned int k = 0; k < WAVE_WINDOW / 32u; k++) {
         const unsigned int slot = windowBase + k * 32u + lane;
         const bool valid = slot < P.W.nSlots;
@@ -439,19 +440,33 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
                 pathComponent = ps.pathComponent;
             }
         }
-        /* trace queue: camera rays of the window first */
-        const bool traceable = (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV);
-        const bool camera = traceable && state == ST_MAIN && pathComponent == 0u;
-        const unsigned camMask = __ballot_sync(FULL, camera);
-        const unsigned otherMask = __ballot_sync(FULL, traceable && !camera);
-        if (camera)
-            camList[nCam + __popc(camMask & below)] = slot;
-        if (traceable && !camera)
-            otherList[nOther + __popc(otherMask & below)] = slot;
-        nCam += __popc(camMask);
-        nOther += __popc(otherMask);
+        /* Trace class: rays of one class from one window (= a few neighbouring pixels) are similar rays.
+         * 0 = camera rays; 1..4 = shadow rays after path component 0, 1, 2, 3+ (same region of the scene,
+         * and most of them towards the brightest part of the environment); 5..8 = bounce rays likewise. */
+        unsigned int cls = TRACE_CLASSES;       /* nothing to trace */
+        if (state == ST_MAIN)
+            cls = (pathComponent == 0u ? 0u : 4u + min(pathComponent, 4u));
+        else if (state == ST_SHADOW_HOT || state == ST_SHADOW_ENV)
+            cls = 1u + min(pathComponent, 3u);
+        classOf[warp][k * 32u + lane] = uint8_t(cls);
     }
     __syncwarp();
+    /* counting sort of the window's slots by class; slot order is kept inside a class */
+    unsigned int nCam = 0, nListed = 0;
+    for (unsigned int c = 0; c < TRACE_CLASSES; c++) {
+#pragma unroll
+        for (unsigned int k = 0; k < WAVE_WINDOW / 32u; k++) {
+            const bool mine = (classOf[warp][k * 32u + lane] == c);
+            const unsigned mask = __ballot_sync(FULL, mine);
+            if (mine)
+                lists[warp][nListed + __popc(mask & below)] = windowBase + k * 32u + lane;
+            nListed += __popc(mask);
+        }
+        if (c == 0)
+            nCam = nListed;
+    }
+    __syncwarp();
+    const unsigned int nOther = nListed - nCam;
     unsigned int camBase = 0, otherBase = 0;
     if (lane == 0) {
         P.W.window[w] = block;
@@ -463,9 +478,9 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
     camBase = __shfl_sync(FULL, camBase, 0);
     otherBase = __shfl_sync(FULL, otherBase, 0);
     for (unsigned int e = lane; e < nCam; e += 32u)
-        P.W.traceQueue[camBase + e] = camList[e];
+        P.W.traceQueue[camBase + e] = lists[warp][e];
     for (unsigned int e = lane; e < nOther; e += 32u)
-        P.W.traceQueue[P.W.nSlots - 1u - (otherBase + e)] = otherList[e];
+        P.W.traceQueue[P.W.nSlots - 1u - (otherBase + e)] = lists[warp][nCam + e];
     countSamples(P, newSamples);
     const unsigned int r = __reduce_add_sync(FULL, retired);
     if (lane == 0 && r != 0u)
