@@ -14,6 +14,8 @@
  */
 #pragma once
 
+#include <cassert>
+
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -91,7 +93,7 @@ public:
     T values[N];
 
     vector() {}
-    explicit vector(T s) { for (int i = 0; i < N; i++) values[i] = s; }
+    vector(T s) { for (int i = 0; i < N; i++) values[i] = s; }   /* implicit, as in the reference (gvm.hpp:230) */
     vector(T x, T y) requires (N == 2) : values { x, y } {}
     vector(T x, T y, T z) requires (N == 3) : values { x, y, z } {}
     vector(T x, T y, T z, T w) requires (N == 4) : values { x, y, z, w } {}

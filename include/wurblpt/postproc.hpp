@@ -43,6 +43,22 @@ inline float maxLuminance(const TGD::Array<float>& img)
     return maxLum;
 }
 
+/* multiplies the luminance of every pixel, keeping its chromaticity; luminances above 100 * clamp are cut
+ * (reference postproc.hpp:93-108) */
+inline TGD::Array<float> scaleLuminance(const TGD::Array<float>& img, float factor, float clamp = 1.0f)
+{
+    TGD::Array<float> r(img.description());
+    for (size_t i = 0; i < r.elementCount(); i++) {
+        vec3 xyz = rgb_to_xyz(vec3(img.get<float>(i)));
+        float y = factor * xyz.y();
+        if (clamp > 0.0f && y > 100.0f * clamp)
+            y = 100.0f * clamp;
+        const vec3 rgb = xyz_to_rgb(adjust_y(xyz, y));
+        r.set(i, { rgb.r(), rgb.g(), rgb.b() });
+    }
+    return r;
+}
+
 /* Schlick's uniform rational quantisation tone mapping on luminance */
 inline TGD::Array<float> uniformRationalQuantization(const TGD::Array<float>& img, float maxVal, float brightness)
 {
