@@ -36,8 +36,11 @@ WORKLOADS = {
     "synth": ("synth", 1.0, 1920, 1080, 16),
     "cornell": ("cornell", 1.0, 512, 512, 8),
     "rtiow": ("rtiow", 1.0, 1920, 1080, 16),
-    # C4: omnidirectional stereo, 4.3 Gsamples per step (about 12 s on one B200)
+    # C4: omnidirectional stereo, 4.3 Gsamples per step (about 8 s on one B200)
     "ods": ("synth360", 1.0, 4096, 4096, 16),
+    # C5: one ToF phase image of the animated scene at full quality; participating media
+    "tof": ("tof", 1.0, 352, 288, 30),
+    "media": ("media", 1.0, 512, 512, 16),
     # reduced copies for profiler runs (ncu replays every launch ~40 times)
     "synth_profile": ("synth", 1.0, 960, 540, 4),
     "synth_64spp": ("synth", 1.0, 1920, 1080, 8),
