@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--substreams", type=int, default=0)
     ap.add_argument("--repeat", type=int, default=3)
     ap.add_argument("--save", default="")
+    ap.add_argument("--stride", type=int, default=1, help="render only every stride-th tile (the share of one of N ranks)")
     a = ap.parse_args()
     view = refapi.View(a.scene)
     if a.width:
@@ -42,7 +43,7 @@ def main():
     print("hitables %d tris %d binary nodes %d depth %d | wide nodes %d depth %d | build %.2fs upload %.2fs device MB %.1f" % (
         i.hitables, i.triangles, i.binary_nodes, i.binary_depth, i.wide_nodes, i.wide_depth, i.build_seconds,
         i.upload_seconds, i.device_bytes / 1e6))
-    opts = capi.make_opts(traversal=a.mode, substreams=a.substreams)
+    opts = capi.make_opts(traversal=a.mode, substreams=a.substreams, tile_first=0, tile_stride=a.stride)
     frame = None
     for k in range(a.repeat):
         frame, st = s.render(view.camera, view.sensor, view.params, spp, view.t0, view.t1, opts)

@@ -718,6 +718,8 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
         WPT_CUDA(s->wave[16].reserve(windows * sizeof(uint2)), "allocate window state");
         WPT_CUDA(cudaMemsetAsync(s->wave[16].p, 0, windows * sizeof(uint2), stream), "clear window state");
         P.W.window = static_cast<uint2*>(s->wave[16].p);
+        WPT_CUDA(s->wave[3].reserve(n), "allocate slot codes");
+        P.W.code = static_cast<uint8_t*>(s->wave[3].p);
         P.W.group = 0;
         if (features == 0)
             P.W.opl = P.W.rayRi = P.W.nextRi = P.W.shadowRi = nullptr;

@@ -88,6 +88,7 @@ struct WaveState {
     float4* rayO;       /* pending query: origin xyz, time */
     float4* rayD;       /* pending query: direction xyz; .w = geometric path length so far */
     uint2* hit;         /* answer of the trace kernel: distance bits, leaf reference */
+    uint8_t* code;      /* what the window-scanning kernels need of a slot in one byte (slotCode()) */
     float4* acc;        /* sample accumulator of the item */
     float4* att;        /* path attenuation */
     float4* nextAtt;    /* across a shadow query: attenuation of the next segment */

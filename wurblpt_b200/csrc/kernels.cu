@@ -179,6 +179,18 @@ __global__ void resolveKernel(const __grid_constant__ RenderParams P)
 /* slot state word: item.z = state | (sub << 8); -1 (all ones) = idle */
 WPT_DEV int slotState(int word) { return word < 0 ? ST_IDLE : (word & 0xFF); }
 
+/* One byte per slot for the kernels that scan whole windows (sort, generate): state in bits 0-2 (7 = idle),
+ * bit 3 = the pending query is on the last allowed path component, bits 4-6 = min(path component, 4). */
+constexpr unsigned int CODE_IDLE = 0xFFu;
+WPT_DEV unsigned int slotCode(const RenderParams& P, int state, unsigned int pathComponent)
+{
+    if (state == ST_IDLE)
+        return CODE_IDLE;
+    const unsigned int last = (pathComponent + 1u < P.maxPathComponents) ? 0u : 8u;
+    return (unsigned int)state | last | (min(pathComponent, 4u) << 4);
+}
+WPT_DEV int codeState(unsigned int code) { return code == CODE_IDLE ? ST_IDLE : int(code & 7u); }
+
 /* ---- slot state in HBM <-> PathState in registers ---- */
 
 template<int F>
@@ -243,6 +255,7 @@ template<int F>
 WPT_DEV void storeSlot(const RenderParams& P, unsigned int slot, const PathState& ps, const Ctx<F>& ctx)
 {
     P.W.item[slot] = make_int4(int(ps.pixel), int(ps.sampleIndex), ps.state | int(ps.sub << 8), int(ps.pathComponent));
+    P.W.code[slot] = uint8_t(slotCode(P, ps.state, ps.pathComponent));
     if (ps.state == ST_EXHAUSTED)
         return;
     P.W.prng[2 * slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
@@ -291,12 +304,12 @@ WPT_DEV void countSamples(const RenderParams& P, unsigned int newSamples)
  * be shaded goes to waveMaterialKernel (the case in which processLogic() returns true), everything
  * else to waveLogicKernel. */
 enum { QUEUE_NONE = 0, QUEUE_MATERIAL = 1, QUEUE_LOGIC = 2 };
-WPT_DEV int queueOf(const RenderParams& P, int4 item, uint32_t hitRef)
+WPT_DEV int queueOf(unsigned int code, uint32_t hitRef)
 {
-    const int state = slotState(item.z);
+    const int state = codeState(code);
     if (state != ST_MAIN && state != ST_SHADOW_HOT && state != ST_SHADOW_ENV)
         return QUEUE_NONE;      /* idle or retired slot: no query was pending */
-    return (state == ST_MAIN && hitRef != NO_HIT && (unsigned int)item.w + 1u < P.maxPathComponents) ? QUEUE_MATERIAL : QUEUE_LOGIC;
+    return (state == ST_MAIN && hitRef != NO_HIT && !(code & 8u)) ? QUEUE_MATERIAL : QUEUE_LOGIC;
 }
 
 /* Sort: after the trace kernel, every warp looks at a window of consecutive slots and appends the ones
@@ -327,8 +340,11 @@ __global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_consta
     for (unsigned int k = 0; k < SORT_WINDOW / 32u; k++) {
         const unsigned int slot = windowBase + k * 32u + lane;
         int kind = QUEUE_NONE;
-        if (slot < P.W.nSlots)
-            kind = queueOf(P, P.W.item[slot], P.W.hit[slot].y);
+        if (slot < P.W.nSlots) {
+            const unsigned int code = P.W.code[slot];
+            if (code != CODE_IDLE && (code & 7u) != (unsigned int)ST_EXHAUSTED)     /* most retired slots cost one byte */
+                kind = queueOf(code, P.W.hit[slot].y);
+        }
         const unsigned matMask = __ballot_sync(FULL, kind == QUEUE_MATERIAL);
         const unsigned logMask = __ballot_sync(FULL, kind == QUEUE_LOGIC);
         if (kind == QUEUE_MATERIAL)
@@ -379,11 +395,9 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
     for (unsigned int k = 0; k < WAVE_WINDOW / 32u; k++) {
         const unsigned int slot = windowBase + k * 32u + lane;
         const bool valid = slot < P.W.nSlots;
-        int4 item = make_int4(0, 0, ST_EXHAUSTED, 0);
-        if (valid)
-            item = P.W.item[slot];
-        int state = slotState(item.z);
-        unsigned int pathComponent = (unsigned int)item.w;
+        const unsigned int code = valid ? (unsigned int)P.W.code[slot] : (unsigned int)ST_EXHAUSTED;
+        int state = codeState(code);
+        unsigned int pathComponent = (code >> 4) & 7u;      /* min(path component, 4): all the class needs */
         const bool generate = valid && (state == ST_NEW || state == ST_IDLE);
         if (__any_sync(FULL, generate)) {
             Ctx<F> ctx;
@@ -392,7 +406,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
             PathState ps;
             ps.state = ST_EXHAUSTED;
             if (generate)
-                loadItem<F>(P, slot, item, ps, ctx);
+                loadItem<F>(P, slot, state == ST_IDLE ? make_int4(-1, -1, -1, -1) : P.W.item[slot], ps, ctx);
             bool working = generate;
             while (__any_sync(FULL, working)) {
                 if (working && ps.state == ST_NEW) {
@@ -1000,7 +1014,7 @@ static RenderParams slotGroup(const RenderParams& P, uint32_t group, uint32_t fi
     G.W.group = group;
     G.W.nSlots = count;
     G.W.item += first; G.W.prng += 2 * first; G.W.rayO += 2 * first; G.W.rayD += 2 * first; G.W.hit += first;
-    G.W.acc += 2 * first; G.W.att += first; G.W.nextAtt += first; G.W.nextDirHot += 2 * first; G.W.pendRad += 2 * first;
+    G.W.code += first; G.W.acc += 2 * first; G.W.att += first; G.W.nextAtt += first; G.W.nextDirHot += 2 * first; G.W.pendRad += 2 * first;
     if (G.W.opl) { G.W.opl += first; G.W.rayRi += first; G.W.nextRi += first; G.W.shadowRi += first; }
     G.W.queue += first;
     G.W.traceQueue += first;
@@ -1049,7 +1063,7 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
             pgrid[g] = 1;
     }
     int n = 0;
-    e = cudaMemsetAsync(P.W.item, 0xFF, size_t(P.W.nSlots) * sizeof(int4), stream);    /* all slots idle */
+    e = cudaMemsetAsync(P.W.code, 0xFF, size_t(P.W.nSlots), stream);   /* all slots idle */
     if (e != cudaSuccess)
         return e;
     if (nGroups == 2) {     /* fork */
