@@ -1,22 +1,23 @@
 /*
  * kernels.cu -- the sm_100a kernels of the path-tracing core and their launchers.
  *
- * Two pipelines run the same path logic (device_path.cuh):
+ * Two pipelines run the same per-path state machine (device_path.cuh):
  *
- *   megakernel   renderKernel<F>: persistent CTAs, every lane owns one work item (pixel, sub-stream)
- *                and loops  startSample -> closest hit -> processHit  with ONE tree-walk site, so
- *                lanes tracing camera rays, bounce rays and shadow rays walk the tree together. A lane
- *                that finishes its item takes the next from an atomic ticket counter.
- *   wavefront    waveShadeKernel<F> / waveTraceKernel<F>: the loop body split at the tree walk. Path
- *                state lives in HBM (structure of arrays, one slot per in-flight item); the trace kernel
- *                is lean (closest hit only) and runs at high occupancy, the shade kernel carries the fat
- *                material / light / camera code. The host enqueues the two kernels in batches and reads a
- *                "slots exhausted" counter one batch late, so the GPU never waits for the host.
+ *   wavefront    (default) path state lives in HBM, one slot per in-flight work item (WaveState). A round is
+ *                  waveTracePersistentKernel   closest hit for every slot listed in the trace queue
+ *                  waveSortKernel              answered queries -> material queue / logic queue (slot order)
+ *                  waveLogicKernel             misses, shadow-ray results, Russian roulette, path end
+ *                  waveMaterialKernel          hit record, emission, scatter, next-event estimation set-up
+ *                  waveGenerateKernel          finishPixel, next work item, next camera ray; builds the trace queue
+ *                The slots are split into two groups whose rounds run on two streams. The host enqueues rounds in
+ *                batches and reads a "slots retired" counter one batch late, so the GPU never waits for the host.
+ *   megakernel   renderKernel<F>: every lane keeps one work item's state in registers and loops
+ *                startSample -> closest hit -> processHit with ONE tree-walk site; kept for A/B comparisons.
  *
- *   queryKernel<F>   closest hit for explicit rays or pixel-centre camera rays (the loop of
- *                    getGroundTruth(), wurblpt.hpp:659-668); used for bit-exact parity checks.
- *   resolveKernel    fixed-order sum of sub-stream partial sums.
- *   prngKernel       Prng known answers.
+ *   groundTruthKernel<F>  getGroundTruth() (wurblpt.hpp:643-759): one pixel-centre ray per pixel, 20 images.
+ *   queryKernel<F>        closest hit for explicit rays or pixel-centre camera rays; bit-exact parity checks.
+ *   resolveKernel         fixed-order sum of sub-stream partial sums.
+ *   prngKernel            Prng known answers.
  *
  * Compiled with --fmad=false (no contraction) so FP32 results round like the strict oracle.
  */
