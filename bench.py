@@ -314,8 +314,8 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "kernel": "renderKernel (megakernel)" if launches_per_step <= 2 else
-                    "one mcpt() = %d launches of waveTracePersistentKernel (dominant, ~66 %% of the time), waveSortKernel, "
-                    "waveLogicKernel, waveMaterialKernel; timed as a whole" % launches_per_step,
+                    "one mcpt() = %d launches of waveTracePersistentKernel (dominant, ~65 %% of the time), waveSortKernel, "
+                    "waveMaterialKernel, waveGenerateKernel; timed as a whole" % launches_per_step,
                     "kernel_ms": kernel_ms,
                     "queries_per_launch": rays_rank, "bytes_per_query": work["bytes_per_query"],
                     "nodes_per_query": work["nodes_per_query"], "leaves_per_query": work["leaves_per_query"],

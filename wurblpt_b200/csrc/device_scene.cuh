@@ -95,8 +95,7 @@ struct WaveState {
     float4* nextDirHot; /* across a shadow query: next direction xyz, chosen hot spot reference */
     float4* pendRad;    /* across a shadow query: light sample to add if visible */
     float4* opl; float4* rayRi; float4* nextRi; float4* shadowRi;  /* F_OPL only */
-    uint32_t* queue;    /* nSlots entries filled by the sort kernel: slots whose surface hit is to be shaded from
-                           the front (material queue), all other answered queries from the back (logic queue) */
+    uint32_t* queue;    /* filled by the sort kernel: the slots whose surface hit is to be shaded (material queue) */
     uint32_t* traceQueue;   /* nSlots entries filled by the generate kernel: slots with a new camera ray from the
                                front, slots with a bounce or shadow ray from the back */
     uint2* window;      /* per window of WAVE_WINDOW slots: the block of work items it hands out (next, end) */
@@ -115,7 +114,6 @@ enum : int {
     CTR_DONE = 64,          /* wavefront slots that found no item left */
     CTR_TICKET = 80,        /* + 16 * group: slot ticket of the persistent trace kernel */
     CTR_MATERIAL = 112,     /* + 16 * group: material queue length */
-    CTR_LOGIC = 144,        /* + 16 * group: logic queue length */
     CTR_TRACE_CAMERA = 176, /* + 16 * group: trace queue, camera rays */
     CTR_TRACE_OTHER = 208,  /* + 16 * group: trace queue, bounce and shadow rays */
     CTR_WORDS = 240

@@ -5,10 +5,10 @@
  *
  *   wavefront    (default) path state lives in HBM, one slot per in-flight work item (WaveState). A round is
  *                  waveTracePersistentKernel   closest hit for every slot listed in the trace queue
- *                  waveSortKernel              answered queries -> material queue / logic queue (slot order)
- *                  waveLogicKernel             misses, shadow-ray results, Russian roulette, path end
+ *                  waveSortKernel              surface hits that are to be shaded -> material queue (slot order)
  *                  waveMaterialKernel          hit record, emission, scatter, next-event estimation set-up
- *                  waveGenerateKernel          finishPixel, next work item, next camera ray; builds the trace queue
+ *                  waveGenerateKernel          misses, shadow-ray results, Russian roulette, path end; finishPixel,
+ *                                              next work item, next camera ray; builds the trace queue
  *                The slots are split into two groups whose rounds run on two streams. The host enqueues rounds in
  *                batches and reads a "slots retired" counter one batch late, so the GPU never waits for the host.
  *   megakernel   renderKernel<F>: every lane keeps one work item's state in registers and loops
@@ -183,6 +183,7 @@ WPT_DEV int slotState(int word) { return word < 0 ? ST_IDLE : (word & 0xFF); }
 /* One byte per slot for the kernels that scan whole windows (sort, generate): state in bits 0-2 (7 = idle),
  * bit 3 = the pending query is on the last allowed path component, bits 4-6 = min(path component, 4). */
 constexpr unsigned int CODE_IDLE = 0xFFu;
+constexpr uint32_t HIT_PENDING = 0xFFFFFFFEu;   /* W.hit[slot].y of an unanswered query (no leaf reference looks like this) */
 WPT_DEV unsigned int slotCode(const RenderParams& P, int state, unsigned int pathComponent)
 {
     if (state == ST_IDLE)
@@ -263,6 +264,7 @@ WPT_DEV void storeSlot(const RenderParams& P, unsigned int slot, const PathState
     P.W.acc[2 * slot] = f4(ps.acc[0], ps.acc[1], ps.acc[2], 0.0f);
     if (ps.state == ST_NEW)
         return;     /* path ended: the generate kernel starts the next sample */
+    P.W.hit[slot] = make_uint2(0u, HIT_PENDING);    /* a new query: unanswered until the trace kernel writes here */
     P.W.rayO[2 * slot] = f4(ps.walkRay.o, ps.walkRay.time);
     P.W.rayD[2 * slot] = f4(ps.walkRay.d, ps.pathLength);
     P.W.att[slot] = ps.att;
@@ -284,7 +286,6 @@ WPT_DEV void storeSlot(const RenderParams& P, unsigned int slot, const PathState
 /* ---- per-group counters ---- */
 WPT_DEV unsigned long long* ctrTicket(const RenderParams& P) { return P.counters + CTR_TICKET + 16 * P.W.group; }
 WPT_DEV unsigned long long* ctrMaterial(const RenderParams& P) { return P.counters + CTR_MATERIAL + 16 * P.W.group; }
-WPT_DEV unsigned long long* ctrLogic(const RenderParams& P) { return P.counters + CTR_LOGIC + 16 * P.W.group; }
 WPT_DEV unsigned long long* ctrTraceCamera(const RenderParams& P) { return P.counters + CTR_TRACE_CAMERA + 16 * P.W.group; }
 WPT_DEV unsigned long long* ctrTraceOther(const RenderParams& P) { return P.counters + CTR_TRACE_OTHER + 16 * P.W.group; }
 
@@ -303,7 +304,7 @@ WPT_DEV void countSamples(const RenderParams& P, unsigned int newSamples)
 
 /* Which kernel finishes an answered query: a camera or bounce ray that hit a surface which is still to
  * be shaded goes to waveMaterialKernel (the case in which processLogic() returns true), everything
- * else to waveLogicKernel. */
+ * else ("logic": misses, last path component, shadow-ray results) is finished by waveGenerateKernel. */
 enum { QUEUE_NONE = 0, QUEUE_MATERIAL = 1, QUEUE_LOGIC = 2 };
 WPT_DEV int queueOf(unsigned int code, uint32_t hitRef)
 {
@@ -313,18 +314,18 @@ WPT_DEV int queueOf(unsigned int code, uint32_t hitRef)
     return (state == ST_MAIN && hitRef != NO_HIT && !(code & 8u)) ? QUEUE_MATERIAL : QUEUE_LOGIC;
 }
 
-/* Sort: after the trace kernel, every warp looks at a window of consecutive slots and appends the ones
- * with an answered query to the material queue (front of W.queue) or the logic queue (back of
- * W.queue). Entries stay in slot order inside a window, so a warp of a shade kernel reads near
- * neighbours in the slot arrays (whole sectors) and every one of its lanes has work. Two atomics per
- * window. */
+/* Sort: after the trace kernel, every warp looks at a window of consecutive slots and lists the ones
+ * whose camera or bounce ray hit a surface that is to be shaded (the material queue, W.queue). Entries
+ * stay in slot order inside a window, so a warp of the material kernel reads near neighbours in the slot
+ * arrays (whole sectors) and every one of its lanes has work. One atomic per window. Everything else
+ * that was answered is left to waveGenerateKernel, which looks at every slot anyway. */
 constexpr unsigned int SORT_WINDOW = 256;       /* slots per warp */
 constexpr unsigned int TRACE_CLASSES = 9;       /* see waveGenerateKernel */
 constexpr unsigned int SORT_BLOCK = 128;
 
 __global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_constant__ RenderParams P)
 {
-    __shared__ uint32_t lists[SORT_BLOCK / 32][2][SORT_WINDOW];
+    __shared__ uint32_t lists[SORT_BLOCK / 32][SORT_WINDOW];
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned below = (1u << lane) - 1u;
@@ -333,46 +334,34 @@ __global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_consta
         *ctrTraceCamera(P) = 0ull;  /* trace queue lengths: the trace kernel is done with them, the generate kernel */
         *ctrTraceOther(P) = 0ull;   /* of this round counts them up again */
     }
-    uint32_t* matList = lists[warp][0];
-    uint32_t* logList = lists[warp][1];
+    uint32_t* matList = lists[warp];
     const unsigned int windowBase = (blockIdx.x * (SORT_BLOCK / 32u) + warp) * SORT_WINDOW;
-    unsigned int nMat = 0, nLog = 0;
+    unsigned int nMat = 0;
 #pragma unroll
     for (unsigned int k = 0; k < SORT_WINDOW / 32u; k++) {
         const unsigned int slot = windowBase + k * 32u + lane;
         int kind = QUEUE_NONE;
         if (slot < P.W.nSlots) {
             const unsigned int code = P.W.code[slot];
-            if (code != CODE_IDLE && (code & 7u) != (unsigned int)ST_EXHAUSTED)     /* most retired slots cost one byte */
+            if ((code & 0x0Fu) == (unsigned int)ST_MAIN)    /* a camera / bounce ray, not on the last path component */
                 kind = queueOf(code, P.W.hit[slot].y);
         }
         const unsigned matMask = __ballot_sync(FULL, kind == QUEUE_MATERIAL);
-        const unsigned logMask = __ballot_sync(FULL, kind == QUEUE_LOGIC);
         if (kind == QUEUE_MATERIAL)
             matList[nMat + __popc(matMask & below)] = slot;
-        if (kind == QUEUE_LOGIC)
-            logList[nLog + __popc(logMask & below)] = slot;
         nMat += __popc(matMask);
-        nLog += __popc(logMask);
     }
     __syncwarp();
-    unsigned int matBase = 0, logBase = 0;
-    if (lane == 0) {
-        if (nMat)
-            matBase = (unsigned int)atomicAdd(ctrMaterial(P), (unsigned long long)nMat);
-        if (nLog)
-            logBase = (unsigned int)atomicAdd(ctrLogic(P), (unsigned long long)nLog);
-    }
+    unsigned int matBase = 0;
+    if (lane == 0 && nMat)
+        matBase = (unsigned int)atomicAdd(ctrMaterial(P), (unsigned long long)nMat);
     matBase = __shfl_sync(FULL, matBase, 0);
-    logBase = __shfl_sync(FULL, logBase, 0);
     for (unsigned int e = lane; e < nMat; e += 32u)
         P.W.queue[matBase + e] = matList[e];
-    for (unsigned int e = lane; e < nLog; e += 32u)
-        P.W.queue[P.W.nSlots - 1u - (logBase + e)] = logList[e];
 }
 
-
-/* Generate: starts the next sample (camera ray) of every slot whose path has ended, hands out work
+/* Generate: finishes the answered queries the material kernel did not take (processLogic(): rays that left
+ * the scene, shadow-ray results, Russian roulette), starts the next sample (camera ray) of every slot whose path has ended, hands out work
  * items, retires slots when none are left, and lists the slots to trace. One warp per window of
  * WAVE_WINDOW consecutive slots; a window takes its work items from a block of WAVE_WINDOW consecutive
  * items at a time (MPICoordinator::getBlock, mpi.hpp:241-254, as a device atomic), so the slots of a
@@ -400,15 +389,26 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
         int state = codeState(code);
         unsigned int pathComponent = (code >> 4) & 7u;      /* min(path component, 4): all the class needs */
         const bool generate = valid && (state == ST_NEW || state == ST_IDLE);
-        if (__any_sync(FULL, generate)) {
+        /* an answered query the material kernel did not take: a ray that left the scene or reached the last
+         * path component, or a shadow ray (everything processLogic() finishes on its own) */
+        bool logic = false;
+        if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV)
+            logic = (P.W.hit[slot].y != HIT_PENDING);
+        if (__any_sync(FULL, generate || logic)) {
             Ctx<F> ctx;
             ctx.nested = 0;
             ctx.nodes = ctx.leaves = 0;
             PathState ps;
             ps.state = ST_EXHAUSTED;
-            if (generate)
+            if (logic) {
+                const Hit hit = loadAnswered<F, true>(P, slot, ps, ctx);
+                animationCacheInit<F>(S, ctx, ps.walkRay.time);
+                const RayHelper h = makeRayHelper(ps.walkRay);
+                processLogic<F>(S, P, ps, ctx, hit, h);
+            } else if (generate) {
                 loadItem<F>(P, slot, state == ST_IDLE ? make_int4(-1, -1, -1, -1) : P.W.item[slot], ps, ctx);
-            bool working = generate;
+            }
+            bool working = generate || (logic && ps.state == ST_NEW);
             while (__any_sync(FULL, working)) {
                 if (working && ps.state == ST_NEW) {
                     if (startSample<F>(S, P, ps, ctx)) {
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
                         block.x += min((unsigned int)__popc(wantMask), avail);
                 }
             }
-            if (generate) {
+            if (generate || logic) {
                 storeSlot<F>(P, slot, ps, ctx);
                 state = ps.state;
                 pathComponent = ps.pathComponent;
@@ -502,28 +502,6 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
         atomicAdd(P.counters + CTR_DONE, (unsigned long long)r);
 }
 
-/* Logic: everything after a query except shading a surface hit -- rays that left the scene, shadow-ray
- * results, Russian roulette -- then the next sample / item for slots whose path ended. One thread per
- * entry of the logic queue. */
-template<int F>
-__global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveLogicKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
-{
-    const unsigned int i = blockIdx.x * BLOCK + threadIdx.x;
-    const unsigned int count = (unsigned int)*ctrLogic(P);
-    if (i < count) {
-        const unsigned int slot = P.W.queue[P.W.nSlots - 1u - i];
-        Ctx<F> ctx;
-        ctx.nested = 0;
-        ctx.nodes = ctx.leaves = 0;
-        PathState ps;
-        const Hit hit = loadAnswered<F, true>(P, slot, ps, ctx);
-        animationCacheInit<F>(S, ctx, ps.walkRay.time);
-        const RayHelper h = makeRayHelper(ps.walkRay);
-        processLogic<F>(S, P, ps, ctx, hit, h);
-        storeSlot<F>(P, slot, ps, ctx);
-    }
-}
-
 /* Material: shade the surface hits of camera and bounce rays. One thread per entry of the material queue. */
 template<int F>
 __global__ void __launch_bounds__(BLOCK, WPT_MATERIAL_MIN_BLOCKS) waveMaterialKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
@@ -553,7 +531,6 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
     const unsigned int p = blockIdx.x * BLOCK + threadIdx.x;
     if (p == 0) {           /* queue lengths of this round (the sort kernel that follows counts them up) */
         *ctrMaterial(P) = 0ull;
-        *ctrLogic(P) = 0ull;
     }
     const unsigned int nCamera = (unsigned int)*ctrTraceCamera(P);
     const unsigned int nQueued = nCamera + (unsigned int)*ctrTraceOther(P);
@@ -608,7 +585,6 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     unsigned int traced = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {  /* queue lengths of this round (the sort kernel that follows counts them up) */
         *ctrMaterial(P) = 0ull;
-        *ctrLogic(P) = 0ull;
     }
 
     const unsigned int nCamera = (unsigned int)*ctrTraceCamera(P);
@@ -1084,12 +1060,11 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
                 else
                     waveTraceKernel<F><<<grid[g], BLOCK, stackBytes(), st[g]>>>(S, R);
                 waveSortKernel<<<sgrid[g], SORT_BLOCK, 0, st[g]>>>(R);
-                waveLogicKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, R);
                 waveMaterialKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, R);
                 waveGenerateKernel<F><<<sgrid[g], BLOCK, 0, st[g]>>>(S, R);
             }
         }
-        n += 5 * batch * nGroups;
+        n += 4 * batch * nGroups;
         if (nGroups == 2) {     /* join the second stream before reading the counter */
             if ((e = cudaEventRecord(events[3], stream2)) != cudaSuccess) return e;
             if ((e = cudaStreamWaitEvent(stream, events[3], 0)) != cudaSuccess) return e;
