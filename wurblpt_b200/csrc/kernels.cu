@@ -608,7 +608,10 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     /* Tickets are drawn from the global counter a chunk at a time and handed out inside the warp
      * without further atomics; idle lanes are only refilled once enough of them have gathered (or
      * none is busy), because a refill stalls the whole warp on the loads of the new rays. */
-    constexpr unsigned int CHUNK = 256;
+    /* 256 entries per ticket when the queue is long; down to 32 when it is short (the last rounds of a frame, small
+     * frames), so that the few rays are spread over all resident warps instead of queueing up in a few of them */
+    const unsigned int perWarp = nQueued / (gridDim.x * (BLOCK / 32u));
+    const unsigned int CHUNK = perWarp >= 2048u ? 256u : perWarp >= 512u ? 128u : perWarp >= 128u ? 64u : 32u;
     constexpr int REFILL_MIN = 8;
     unsigned int warpNext = 0, warpEnd = 0;
     bool drained = false;           /* the global ticket counter has run past the last slot */
