@@ -53,6 +53,9 @@ namespace wptd {
 #ifndef WPT_CAMERA_REFILL_MIN
 #define WPT_CAMERA_REFILL_MIN 32
 #endif
+#ifndef WPT_REFILL_MIN
+#define WPT_REFILL_MIN 12   /* idle lanes that must have gathered before the persistent trace kernel fetches new rays */
+#endif
 #ifndef WPT_LEAF_MIN
 #define WPT_LEAF_MIN 12     /* lanes that must be at a leaf before the persistent trace kernel runs a leaf round */
 #endif
@@ -612,7 +615,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
      * frames), so that the few rays are spread over all resident warps instead of queueing up in a few of them */
     const unsigned int perWarp = nQueued / (gridDim.x * (BLOCK / 32u));
     const unsigned int CHUNK = perWarp >= 2048u ? 256u : perWarp >= 512u ? 128u : perWarp >= 128u ? 64u : 32u;
-    constexpr int REFILL_MIN = 8;
+    constexpr int REFILL_MIN = WPT_REFILL_MIN;
     unsigned int warpNext = 0, warpEnd = 0;
     bool drained = false;           /* the global ticket counter has run past the last slot */
     for (;;) {
