@@ -323,7 +323,7 @@ enum {
 typedef struct wpt_render_opts {
     int32_t traversal;          /* WPT_TRAVERSAL_* */
     int32_t substreams;         /* PRNG sub-streams per pixel: 1 = the reference's one stream per pixel
-                                   (wurblpt.hpp:342), 2..32 (power of two) split a pixel's samples over
+                                   (wurblpt.hpp:342), 2..128 (power of two) split a pixel's samples over
                                    lanes, 0 = choose from image size */
     uint32_t tile_first;        /* this call renders pixel tiles tile_first, tile_first+tile_stride, ... */
     uint32_t tile_stride;       /* 0 or 1 = all tiles; N = one of N GPUs (the MPICoordinator block split, mpi.hpp:241-254) */

@@ -627,15 +627,16 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
     /* sub-streams per pixel: enough lanes to fill the GPU a few times over */
     uint32_t sub = 1;
     if (o.substreams > 0) {
-        if (o.substreams > 32 || (o.substreams & (o.substreams - 1)) != 0)
-            return fail(WPT_E_INVALID, "substreams must be a power of two <= 32");
+        if (o.substreams > 128 || (o.substreams & (o.substreams - 1)) != 0)
+            return fail(WPT_E_INVALID, "substreams must be a power of two <= 128");
         sub = uint32_t(o.substreams);
     } else {
-        /* enough work items that every lane (megakernel) or slot (wavefront) gets several: short
-         * items keep the tail, where few lanes still have work, short */
+        /* Many short work items: when the items run out, a slot is at most one item away from retiring, so
+         * the last rounds of a frame (few live slots) stay short. 32 items per slot, at least one sample
+         * per item, and at most 16 GB of partial sums (12 bytes per pixel and sub-stream). */
         const uint64_t pixels = uint64_t(sensor->width) * sensor->height;
-        const uint64_t wantItems = 8ull * waveSlotLimit();
-        while (sub < 32 && pixels * sub < wantItems && sub * 2 <= P.samples && (P.samples / (sub * 2)) >= 4)
+        const uint64_t wantItems = 32ull * waveSlotLimit();
+        while (sub < 128 && pixels * sub < wantItems && sub * 2 <= P.samples && pixels * (sub * 2) * 12ull <= (16ull << 30))
             sub *= 2;
     }
     while (sub > P.samples && sub > 1)
@@ -644,8 +645,10 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
     P.subShift = 0;
     while ((1u << P.subShift) < sub)
         P.subShift++;
-    const uint32_t pixelsPerTile = 32u / sub;
-    static const uint32_t tileWs[6] = { 8, 4, 4, 2, 2, 1 };     /* 32, 16, 8, 4, 2, 1 pixels per tile */
+    /* a tile is 32 work items, or one pixel's sub-streams if those are more */
+    P.tileShift = (P.subShift > 5u ? P.subShift : 5u);
+    const uint32_t pixelsPerTile = (1u << P.tileShift) >> P.subShift;
+    static const uint32_t tileWs[8] = { 8, 4, 4, 2, 2, 1, 1, 1 };   /* 32, 16, 8, 4, 2, 1, 1, 1 pixels per tile */
     P.tileW = tileWs[P.subShift];
     P.tileH = pixelsPerTile / P.tileW;
     P.tilesX = (sensor->width + P.tileW - 1) / P.tileW;
@@ -656,9 +659,9 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
     if (P.tileFirst >= P.tileStride)
         return fail(WPT_E_INVALID, "tile_first must be smaller than tile_stride");
     P.nLocalTiles = (P.tileFirst < P.tilesTotal ? (P.tilesTotal - P.tileFirst + P.tileStride - 1) / P.tileStride : 0);
-    if (uint64_t(P.nLocalTiles) * 32ull >= 0xFFFFFFFFull)
+    if ((uint64_t(P.nLocalTiles) << P.tileShift) >= 0xFFFFFFFFull)
         return fail(WPT_E_UNSUPPORTED, "image too large for 32-bit work item indices");
-    P.nItems = P.nLocalTiles * 32u;
+    P.nItems = P.nLocalTiles << P.tileShift;
 
     const size_t frameBytes = size_t(sensor->width) * sensor->height * 3 * sizeof(float);
     if (o.frame_on_device) {

@@ -220,7 +220,7 @@ WPT_DEV void processHit(const DScene& S, const RenderParams& P, PathState& ps, C
 }
 
 /* A work item is one (pixel, sub-stream): all samples of that sub-stream, run back to back with one
- * Prng (wurblpt.hpp:342-368). Items are numbered tile by tile (32 per tile) so that neighbouring
+ * Prng (wurblpt.hpp:342-368). Items are numbered tile by tile (1 << tileShift per tile) so that neighbouring
  * items are neighbouring pixels. */
 struct WorkItem {
     unsigned int pixel, sub;
@@ -230,7 +230,7 @@ struct WorkItem {
 WPT_DEV WorkItem decodeItem(const RenderParams& P, unsigned int item)
 {
     WorkItem w;
-    const unsigned int localTile = item >> 5, inTile = item & 31u;
+    const unsigned int localTile = item >> P.tileShift, inTile = item & ((1u << P.tileShift) - 1u);
     const unsigned int tile = P.tileFirst + localTile * P.tileStride;
     const unsigned int tileX = tile % P.tilesX, tileY = tile / P.tilesX;
     w.sub = inTile & (P.substreams - 1u);

@@ -146,10 +146,10 @@ struct RenderParams {
     float invSamples, invSamplesSqrt, invWidth, invHeight;
     float t0, t1;
     /* tiling */
-    uint32_t substreams, subShift;
+    uint32_t substreams, subShift, tileShift;   /* work items per tile = 1 << tileShift */
     uint32_t tileW, tileH, tilesX, tilesTotal;
     uint32_t tileFirst, tileStride, nLocalTiles;
-    uint32_t nItems;                /* nLocalTiles * 32 work items (pixel, sub-stream) */
+    uint32_t nItems;                /* nLocalTiles << tileShift work items (pixel, sub-stream) */
     /* output */
     float* frame;
     float* partials;                /* [pixel][sub-stream][3] partial sums when substreams > 1 */

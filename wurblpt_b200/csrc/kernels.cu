@@ -158,11 +158,11 @@ __global__ void __launch_bounds__(BLOCK, WPT_MIN_BLOCKS) renderKernel(const __gr
 __global__ void resolveKernel(const __grid_constant__ RenderParams P)
 {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;       /* (local tile, pixel in tile) */
-    const unsigned int pixelsPerTile = 32u >> P.subShift;
+    const unsigned int pixelsPerTile = (1u << P.tileShift) >> P.subShift;
     if (i >= P.nLocalTiles * pixelsPerTile)
         return;
     const unsigned int localTile = i / pixelsPerTile, pit = i % pixelsPerTile;
-    const WorkItem w = decodeItem(P, (localTile << 5) | (pit << P.subShift));
+    const WorkItem w = decodeItem(P, (localTile << P.tileShift) | (pit << P.subShift));
     if (!w.valid)
         return;
     const float* part = P.partials + size_t(w.pixel) * P.substreams * 3;
@@ -934,7 +934,7 @@ static cudaError_t launchResolve(const RenderParams& P, cudaStream_t stream)
 {
     if (P.substreams == 1)
         return cudaSuccess;
-    const unsigned int pixels = P.nLocalTiles * (32u >> P.subShift);
+    const unsigned int pixels = P.nLocalTiles * ((1u << P.tileShift) >> P.subShift);
     resolveKernel<<<(pixels + 255) / 256, 256, 0, stream>>>(P);
     return cudaGetLastError();
 }

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import capi
 
-_TILE_W = {1: 8, 2: 4, 4: 4, 8: 2, 16: 2, 32: 1}      # capi.cu: tileWs by log2(substreams)
+_TILE_W = {1: 8, 2: 4, 4: 4, 8: 2, 16: 2, 32: 1, 64: 1, 128: 1}      # capi.cu: tileWs by log2(substreams)
 
 
 def env_rank():
@@ -43,9 +43,9 @@ def rank_opts(rank, world, substreams=0, stream=None, traversal=0, frame_on_devi
 
 
 def tile_shape(substreams):
-    """(tile width, tile height) in pixels: a warp covers 32 / substreams pixels."""
+    """(tile width, tile height) in pixels: a tile is 32 work items (32 / substreams pixels), or one pixel."""
     w = _TILE_W[substreams]
-    return w, (32 // substreams) // w
+    return w, max(1, 32 // substreams) // w
 
 
 def owner_map(width, height, substreams, world):
