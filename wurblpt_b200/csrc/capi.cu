@@ -340,6 +340,10 @@ int defaultPipeline()
     return WPT_PIPELINE_WAVEFRONT;
 }
 
+#ifndef WPT_ITEMS_PER_SLOT
+#define WPT_ITEMS_PER_SLOT 4u
+#endif
+
 uint32_t waveSlotLimit()
 {
     const char* e = std::getenv("WPT_WAVE_SLOTS");
@@ -687,7 +691,12 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
         pipeline = defaultPipeline();
     const int features = sceneFeatures(s, needOpl);
     if (pipeline == WPT_PIPELINE_WAVEFRONT && P.nItems > 0) {
+        /* slots: as many as the limit allows for big frames (long launches amortise their ramp and tail), but
+         * every slot should see several work items, or the whole frame is one ramp and one tail */
         uint32_t slots = waveSlotLimit();
+        const uint32_t share = (std::getenv("WPT_WAVE_SLOTS") ? P.nItems : std::max(P.nItems / WPT_ITEMS_PER_SLOT, 65536u));
+        if (slots > share)
+            slots = share;
         if (slots > P.nItems)
             slots = P.nItems;
         P.W.nSlots = slots;
