@@ -1016,7 +1016,7 @@ template<int F>
 static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int numSMs, cudaStream_t stream,
         cudaStream_t stream2, unsigned long long* hostDone, cudaEvent_t* events, int* launches)
 {
-    const int batch = 16;
+    const int batch = 8;
     int perSM = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, waveTracePersistentKernel<F>, BLOCK, stackBytes());
     if (e != cudaSuccess)
