@@ -348,7 +348,7 @@ uint32_t waveSlotLimit()
 {
     const char* e = std::getenv("WPT_WAVE_SLOTS");
     long v = e ? std::atol(e) : 0;
-    return v > 0 ? uint32_t(v) : (1u << 23);
+    return v > 0 ? uint32_t(v) : 12582912u;    /* 12 M slots: 2.3 GB of path state */
 }
 
 int sceneFeatures(const wpt_scene* s, bool needOpl)
