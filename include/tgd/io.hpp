@@ -6,7 +6,7 @@
  *
  * No image codec libraries exist in this environment, so files are written as
  *   *.pfm            portable float map (1 or 3 float32 components)
- *   *.ppm / *.pgm    binary netpbm (3 or 1 uint8 components)
+ *   *.ppm / *.pgm / *.pnm   binary netpbm (3 or 1 uint8 components)
  *   anything else    "WPTARRAY" container: one text header line
  *                    "WPTARRAY <type> <components> <ndims> <dim0> <dim1> ...\n"
  *                    followed by the raw little-endian data (readable with numpy).
@@ -91,7 +91,7 @@ inline Error save(const ArrayContainer& array, const std::string& fileName, bool
         std::fprintf(f, "%s\n%zu %zu\n-1.0\n", array.componentCount() == 3 ? "PF" : "Pf",
                 array.dimension(0), array.dimension(1));
         ok = std::fwrite(array.data(), 1, array.dataSize(), f) == array.dataSize();
-    } else if ((detail::endsWith(fileName, ".ppm") || detail::endsWith(fileName, ".pgm")) && twoD
+    } else if ((detail::endsWith(fileName, ".ppm") || detail::endsWith(fileName, ".pgm") || detail::endsWith(fileName, ".pnm")) && twoD
             && array.componentType() == uint8
             && (array.componentCount() == 1 || array.componentCount() == 3)) {
         // netpbm stores the top row first: flip.

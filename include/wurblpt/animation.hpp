@@ -18,6 +18,26 @@ public:
     virtual Transformation at(float t) const = 0;
 };
 
+namespace detail {
+
+/* Times at which an Animation that is not an AnimationKeyframes is sampled ("baked") into key frames for the
+ * device: exact for t0 == t1 (one key frame); 17 samples across an exposure interval, between which the device
+ * interpolates like AnimationKeyframes does (translation and scaling linearly, rotation by slerp). */
+inline std::vector<float> bakeTimesFor(float t0, float t1)
+{
+    std::vector<float> times;
+    if (!(t1 > t0)) {
+        times.push_back(t0);
+    } else {
+        const int n = 16;
+        for (int i = 0; i <= n; i++)
+            times.push_back(i == n ? t1 : t0 + (t1 - t0) * (float(i) / float(n)));
+    }
+    return times;
+}
+
+}
+
 class AnimationCache
 {
 private:

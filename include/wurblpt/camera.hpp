@@ -106,7 +106,9 @@ public:
     }
 
     /* ---- B200 build only: the C-ABI description; `keyframeStorage` must outlive its use ---- */
-    bool flatten(wpt_camera_desc& c, std::vector<wpt_keyframe>& keyframeStorage) const
+    /* `bakeTimes`: where to sample a camera animation that is not an AnimationKeyframes (detail::bakeTimesFor) */
+    bool flatten(wpt_camera_desc& c, std::vector<wpt_keyframe>& keyframeStorage,
+            const std::vector<float>& bakeTimes = std::vector<float>()) const
     {
         std::memset(&c, 0, sizeof(c));
         c.surround_mode = (surroundMode == Surround_Off ? WPT_SURROUND_OFF : surroundMode == Surround_180 ? WPT_SURROUND_180 : WPT_SURROUND_360);
@@ -125,9 +127,14 @@ public:
         keyframeStorage.clear();
         if (animation.get()) {
             const AnimationKeyframes* kf = dynamic_cast<const AnimationKeyframes*>(animation.get());
-            if (!kf)
+            if (!kf && bakeTimes.empty())
                 return false;
-            for (const auto& k : kf->keyframes()) {
+            std::vector<AnimationKeyframes::Keyframe> baked;
+            if (!kf) {
+                for (float t : bakeTimes)
+                    baked.push_back(AnimationKeyframes::Keyframe(t, animation->at(t)));
+            }
+            for (const auto& k : (kf ? kf->keyframes() : baked)) {
                 wpt_keyframe wk;
                 wk.t = k.t;
                 detail::store(wk.translation, k.transformation.translation, 3);

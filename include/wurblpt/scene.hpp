@@ -87,6 +87,8 @@ private:
     std::unique_ptr<Flattener> _flat;
     wpt_scene* _device;
     bool _descriptionStale;
+    bool _hasBakedAnimations;           /* some Animation is not an AnimationKeyframes: sampled into key frames */
+    std::vector<float> _bakeTimes;      /* the times the current description samples those animations at */
 
     void flattenRange(Flattener& F, const std::vector<Taken>& taken, const std::vector<std::unique_ptr<Hitable>>& list,
             bool hitable, int& nextId, std::vector<std::pair<const Medium*, int>>& mediaToResolve)
@@ -144,20 +146,27 @@ private:
 
     /* Build the C-ABI description. Global hitable ids number the hitables of take() first, then
      * those of takeUnhitable() (the same convention as the oracle's flattening of a reference Scene). */
-    void flatten()
+    void flatten(const std::vector<float>& bakeTimes = std::vector<float>(1, 0.0f))
     {
         _flat.reset(new Flattener);
         Flattener& F = *_flat;
+        _hasBakedAnimations = false;
+        _bakeTimes = bakeTimes;
         for (const auto& a : _animations) {
             const AnimationKeyframes* kf = dynamic_cast<const AnimationKeyframes*>(a.get());
+            std::vector<AnimationKeyframes::Keyframe> baked;
             if (!kf) {
-                F.fail("only AnimationKeyframes (and classes derived from it) can be evaluated on the device");
-                break;
+                /* a user-defined Animation: the device only knows key frames, so at() is sampled at the times
+                 * this description is made for (exact when t0 == t1; see detail::bakeTimesFor) */
+                _hasBakedAnimations = true;
+                for (float t : bakeTimes)
+                    baked.push_back(AnimationKeyframes::Keyframe(t, a->at(t)));
             }
+            const std::vector<AnimationKeyframes::Keyframe>& keys = (kf ? kf->keyframes() : baked);
             wpt_animation wa;
             wa.first_keyframe = F.keyframes.size();
-            wa.keyframe_count = kf->keyframes().size();
-            for (const auto& k : kf->keyframes()) {
+            wa.keyframe_count = keys.size();
+            for (const auto& k : keys) {
                 wpt_keyframe wk;
                 wk.t = k.t;
                 detail::store(wk.translation, k.transformation.translation, 3);
@@ -206,7 +215,8 @@ private:
     }
 
 public:
-    Scene() : _bvhNeedsRebuild(true), _bvhT0(0.0f), _bvhT1(0.0f), _device(nullptr), _descriptionStale(true) {}
+    Scene() : _bvhNeedsRebuild(true), _bvhT0(0.0f), _bvhT1(0.0f), _device(nullptr), _descriptionStale(true),
+        _hasBakedAnimations(false) {}
     Scene(const Scene&) = delete;
     Scene& operator=(const Scene&) = delete;
     ~Scene() { releaseDevice(); }
@@ -274,6 +284,22 @@ public:
         return envmap;
     }
 
+    /* (Re)builds the description and uploads it when needed: first use, objects taken since, or sampled
+     * ("baked") animations that were sampled for other times. */
+    void prepareDevice(const std::vector<float>& bakeTimes)
+    {
+        if (_device && !_descriptionStale && !(_hasBakedAnimations && _bakeTimes != bakeTimes))
+            return;
+        /* Note: a material's public members (e.g. normalTex) may have been changed after take();
+         * the description is rebuilt whenever the set of taken objects changed. */
+        releaseDevice();
+        flatten(bakeTimes);
+        wpt_scene_desc d = _flat->desc();
+        if (wpt_scene_create(&d, detail::deviceFromEnvironment(), &_device) != WPT_OK)
+            detail::die("WurblPT scene upload", wpt_last_error());
+        _descriptionStale = false;
+    }
+
     bool bvhNeedsUpdate(float t0 = 0.0f, float t1 = 0.0f) const
     {
         return _bvhNeedsRebuild || (_animations.size() > 0 && (_bvhT0 > t0 || _bvhT1 < t1));
@@ -285,16 +311,7 @@ public:
             fprintf(stderr, "Bounding volume hierarchy does not need updating.\n");
             return;
         }
-        if (!_device || _descriptionStale) {
-            /* Note: a material's public members (e.g. normalTex) may have been changed after take();
-             * the description is rebuilt whenever the set of taken objects changed. */
-            releaseDevice();
-            flatten();
-            wpt_scene_desc d = _flat->desc();
-            if (wpt_scene_create(&d, detail::deviceFromEnvironment(), &_device) != WPT_OK)
-                detail::die("WurblPT scene upload", wpt_last_error());
-            _descriptionStale = false;
-        }
+        prepareDevice(detail::bakeTimesFor(t0, t1));
         fprintf(stderr, "Building bounding volume hierarchy for %zu hitables for %.3fs-%.3fs\n", _hitables.size(), t0, t1);
         if (wpt_scene_update_bvh(_device, t0, t1) != WPT_OK)
             detail::die("WurblPT updateBVH", wpt_last_error());
@@ -341,11 +358,31 @@ public:
     /* the flattened description of the last updateBVH() (for inspection and tests) */
     const Flattener* flattened() const { return _flat.get(); }
 
-    /* flatten without touching a device */
-    wpt_scene_desc describe()
+    /* flatten without touching a device; (t0, t1) only matters for animations that are sampled into key frames */
+    wpt_scene_desc describe(float t0 = 0.0f, float t1 = 0.0f)
     {
-        flatten();
+        flatten(detail::bakeTimesFor(t0, t1));
         return _flat->desc();
+    }
+
+    bool hasBakedAnimations() const { return _hasBakedAnimations; }
+
+    /* getGroundTruth() evaluates animations at tPrev and tNext as well: sampled animations get key frames at
+     * exactly these times and the tree for t0 is rebuilt. Logically const (the scene is unchanged). */
+    void prepareGroundTruth(float t0, float tPrev, float tNext) const
+    {
+        if (!_hasBakedAnimations || (tPrev == t0 && tNext == t0))
+            return;
+        std::vector<float> times;
+        times.push_back(tPrev);
+        if (t0 > tPrev)
+            times.push_back(t0);
+        if (tNext > t0)
+            times.push_back(tNext);
+        Scene* self = const_cast<Scene*>(this);
+        self->prepareDevice(times);
+        if (wpt_scene_update_bvh(self->_device, t0, t0) != WPT_OK)
+            detail::die("WurblPT updateBVH", wpt_last_error());
     }
 };
 

@@ -87,8 +87,8 @@ inline void mcpt(
         detail::die("mcpt", "a user-defined Sensor cannot accumulate radiance on the device");
     wpt_camera_desc cameraDesc;
     std::vector<wpt_keyframe> cameraKeyframes;
-    if (!camera.flatten(cameraDesc, cameraKeyframes))
-        detail::die("mcpt", "only AnimationKeyframes camera animations can be evaluated on the device");
+    if (!camera.flatten(cameraDesc, cameraKeyframes, detail::bakeTimesFor(t0, t1)))
+        detail::die("mcpt", "the camera animation cannot be evaluated on the device");
     wpt_params p;
     p.max_path_components = params.maxPathComponents;
     p.rr_threshold = params.rrThreshold;
@@ -254,10 +254,16 @@ inline GroundTruth getGroundTruth(const Sensor& sensor, const Camera& camera, co
     /* the reference asserts tPrev <= t0 <= tNext and !scene.bvhNeedsUpdate(t0, t0) (wurblpt.hpp:648-651) */
     if (scene.bvhNeedsUpdate(t0, t0) || !scene.deviceScene())
         detail::die("getGroundTruth", "Scene::updateBVH(t0, t0) must be called first");
+    scene.prepareGroundTruth(t0, tPrev, tNext);
     wpt_camera_desc cameraDesc;
     std::vector<wpt_keyframe> cameraKeyframes;
-    if (!camera.flatten(cameraDesc, cameraKeyframes))
-        detail::die("getGroundTruth", "only AnimationKeyframes camera animations can be evaluated on the device");
+    std::vector<float> cameraTimes(1, tPrev);
+    if (t0 > tPrev)
+        cameraTimes.push_back(t0);
+    if (tNext > t0)
+        cameraTimes.push_back(tNext);
+    if (!camera.flatten(cameraDesc, cameraKeyframes, cameraTimes))
+        detail::die("getGroundTruth", "the camera animation cannot be evaluated on the device");
     const unsigned int width = sensor.width();
     const unsigned int height = sensor.height();
     GroundTruth gt(width, height, groundTruthBits);

@@ -121,3 +121,32 @@ def test_reference_tof_example_app_runs_unchanged(gpu, tmp_path):
     rel = np.abs(measured[ok] - dist[..., 0][ok]) / dist[..., 0][ok]
     assert np.median(rel) < 0.05
     assert np.abs(flow).max() > 0.01
+
+
+def test_reference_material_playground_app_runs_unchanged(gpu, tmp_path):
+    """wurblpt-material-playground.cpp, unchanged: the camera and two mesh instances follow user-defined Animation
+    subclasses (not key frames), which the API mirror samples for every frame's updateBVH(t0, t0). The app
+    renders 125 frames of 800x600 at 225 spp; the first few are enough here."""
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "apps", "_bin",
+                       "wurblpt-material-playground")
+    if not os.path.exists(exe):
+        pytest.skip("apps/_bin/wurblpt-material-playground not built")
+    log = ""
+    try:
+        log = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=25).stderr
+    except subprocess.TimeoutExpired as e:
+        log = (e.stderr or b"").decode(errors="replace") if isinstance(e.stderr, bytes) else (e.stderr or "")
+    frames = sorted(p.name for p in tmp_path.glob("frame-*.pnm"))
+    assert len(frames) >= 3, log[-3000:]
+
+    def read_ppm(path):
+        with open(path, "rb") as f:
+            assert f.readline().strip() == b"P6"
+            w, h = [int(v) for v in f.readline().split()]
+            assert f.readline().strip() == b"255"
+            return np.frombuffer(f.read(), dtype=np.uint8).reshape(h, w, 3)
+
+    a, b = read_ppm(tmp_path / frames[0]), read_ppm(tmp_path / frames[2])
+    assert a.shape == (600, 800, 3)
+    assert 5 < a.mean() < 250 and a.std() > 5          # an image, not a constant
+    assert np.abs(a.astype(np.int32) - b.astype(np.int32)).mean() > 0.5     # the camera and the objects moved
