@@ -25,6 +25,10 @@ class Mesh;
 class Flattener
 {
 public:
+    /* user-defined Texture subclasses are sampled ("baked") into float RGBA images of this size at this time */
+    float bakeTime = 0.0f;
+    unsigned int bakeTextureSize = 512;
+    bool bakedTextures = false;
     std::vector<wpt_animation> animations;
     std::vector<wpt_keyframe> keyframes;
     std::vector<wpt_texture> textures;

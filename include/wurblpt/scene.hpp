@@ -87,7 +87,8 @@ private:
     std::unique_ptr<Flattener> _flat;
     wpt_scene* _device;
     bool _descriptionStale;
-    bool _hasBakedAnimations;           /* some Animation is not an AnimationKeyframes: sampled into key frames */
+    bool _hasBakedAnimations;           /* some Animation is not an AnimationKeyframes (sampled into key frames) or some
+                                           Texture is user-defined (sampled into an image): the description depends on time */
     std::vector<float> _bakeTimes;      /* the times the current description samples those animations at */
 
     void flattenRange(Flattener& F, const std::vector<Taken>& taken, const std::vector<std::unique_ptr<Hitable>>& list,
@@ -152,6 +153,7 @@ private:
         Flattener& F = *_flat;
         _hasBakedAnimations = false;
         _bakeTimes = bakeTimes;
+        F.bakeTime = bakeTimes.empty() ? 0.0f : bakeTimes.front();
         for (const auto& a : _animations) {
             const AnimationKeyframes* kf = dynamic_cast<const AnimationKeyframes*>(a.get());
             std::vector<AnimationKeyframes::Keyframe> baked;
@@ -197,6 +199,8 @@ private:
         }
         if (_envmap && !_envmap->flatten(F))
             F.fail("a user-defined EnvironmentMap cannot be evaluated on the device");
+        if (F.bakedTextures)
+            _hasBakedAnimations = true;     /* the description depends on the time it was made for */
         if (!F.error.empty())
             detail::die("WurblPT scene", F.error.c_str());
     }

@@ -2,7 +2,7 @@
  * libwurblpt/texture.hpp:40-246). value() is evaluated on the host for environment-map importance
  * tables and application use; the device evaluates the same four texture kinds from their flattened
  * description (csrc/device_shade.cuh). A user-defined Texture subclass cannot run on the device:
- * flattening it is reported as an error when the scene is prepared. */
+ * it is sampled into an image texture when the scene is prepared (Flattener::texture). */
 #pragma once
 
 #include <tgd/array.hpp>
@@ -143,8 +143,31 @@ inline int Flattener::texture(const Texture* tex)
     std::memset(&t, 0, sizeof(t));
     t.src_texture = -1;
     if (!tex->flatten(*this, t)) {
-        fail("a user-defined Texture subclass cannot be evaluated on the device");
-        return -1;
+        /* A user-defined Texture: the device cannot call its value(). It is sampled at the texel centres of a
+         * bakeTextureSize^2 float RGBA image (bilinear lookup with fract() wrap, like TextureImage) at the time
+         * the description is made for; the scene re-bakes when updateBVH() is called for other times. */
+        bakedTextures = true;
+        const unsigned int n = bakeTextureSize;
+        t.type = WPT_TEX_IMAGE;
+        t.width = t.height = int(n);
+        t.components = 4;
+        t.texel_type = WPT_TEXEL_F32;
+        t.linearize_srgb = 0;
+        t.coord_factor[0] = t.coord_factor[1] = 1.0f;
+        for (int c = 0; c < 4; c++)
+            t.val_factor[c] = 1.0f;
+        while (texels.size() % 16 != 0)
+            texels.push_back(0);
+        t.texel_offset = texels.size();
+        texels.resize(texels.size() + size_t(n) * n * 4 * sizeof(float));
+        float* dst = reinterpret_cast<float*>(texels.data() + t.texel_offset);
+        for (unsigned int y = 0; y < n; y++) {
+            for (unsigned int x = 0; x < n; x++) {
+                const vec4 v = tex->value(vec2((x + 0.5f) / n, (y + 0.5f) / n), bakeTime);
+                for (int c = 0; c < 4; c++)
+                    dst[(size_t(y) * n + x) * 4 + c] = v[c];
+            }
+        }
     }
     int index = textures.size();
     textures.push_back(t);

@@ -125,7 +125,7 @@ struct wpt_scene {
     /* per updateBVH */
     DeviceBuf node4, bnode, tri, triShade, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs;
     /* per call scratch */
-    DeviceBuf counters, camKeys, frame, partials, wave[17], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds;
+    DeviceBuf counters, camKeys, frame, partials, wave[17], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds, animTable;
     cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaStream_t stream2 = nullptr;
     unsigned long long* hostDone = nullptr;     /* pinned, 2 counters */
@@ -356,6 +356,39 @@ int sceneFeatures(const wpt_scene* s, bool needOpl)
     return (s->sceneHasMedia || s->sceneHasAnimation || needOpl) ? 7 : 0;
 }
 
+/* The device scene for one launch. When all rays of the launch have the same time (t0 == t1: no motion blur, or a
+ * query at one time) the animations are evaluated once, here, with the host arithmetic the bounds were computed
+ * with, and the kernels read them from a table; otherwise every thread evaluates the key frames at its ray's time
+ * into a per-thread cache, which holds MAX_CACHED_ANIMATIONS animations. */
+int launchScene(wpt_scene* s, float t0, float t1, cudaStream_t stream, wptd::DScene& d)
+{
+    d = s->d;
+    d.animTable = nullptr;
+    const size_t n = s->host.animations.size();
+    if (!s->sceneHasAnimation || n == 0)
+        return WPT_OK;
+    if (t0 == t1) {
+        std::vector<float> table(n * 32, 0.0f);
+        for (size_t i = 0; i < n; i++) {
+            const wpt::Trs T = s->host.animationAt(int(i), t0);
+            float* e = table.data() + i * 32;
+            e[0] = T.t.x; e[1] = T.t.y; e[2] = T.t.z;
+            e[3] = T.r.x; e[4] = T.r.y; e[5] = T.r.z; e[6] = T.r.w;
+            e[7] = T.s.x; e[8] = T.s.y; e[9] = T.s.z;
+            const wpt::Mat34 M = wpt::toMat34(T);
+            std::memcpy(e + 10, M.m, sizeof(M.m));
+            wpt::toMat3(T.r, e + 22);
+        }
+        WPT_CUDA(s->animTable.upload(table.data(), table.size() * sizeof(float), stream), "upload animation table");
+        d.animTable = s->animTable.as<float>();
+        return WPT_OK;
+    }
+    if (n > size_t(wptd::MAX_CACHED_ANIMATIONS))
+        return fail(WPT_E_UNSUPPORTED, "more than " + std::to_string(wptd::MAX_CACHED_ANIMATIONS)
+                + " scene animations are only supported for t0 == t1 (no motion blur)");
+    return WPT_OK;
+}
+
 int checkReady(wpt_scene* s)
 {
     if (!s)
@@ -453,9 +486,6 @@ int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** out)
         s->sceneHasAnimation = s->sceneHasAnimation || in.animation >= 0;
     for (const wpt_sphere& sp : s->host.spheres)
         s->sceneHasAnimation = s->sceneHasAnimation || sp.animation >= 0;
-    if (s->sceneHasAnimation && s->host.animations.size() > size_t(wptd::MAX_CACHED_ANIMATIONS))
-        return fail(WPT_E_UNSUPPORTED, "more than " + std::to_string(wptd::MAX_CACHED_ANIMATIONS)
-                + " scene animations are not supported yet");
     auto start = std::chrono::steady_clock::now();
     rc = uploadStatic(s.get());
     if (rc != WPT_OK)
@@ -741,11 +771,15 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
     int launches = 0;
     if (timed)
         WPT_CUDA(cudaEventRecord(s->evStart, stream), "cudaEventRecord");
+    wptd::DScene dscene;
+    rc = launchScene(s, t0, t1, stream, dscene);
+    if (rc != WPT_OK)
+        return rc;
     if (P.nLocalTiles > 0) {
         if (pipeline == WPT_PIPELINE_WAVEFRONT)
-            WPT_CUDA(wptd::launchWavefront(features, s->d, P, s->numSMs, stream, s->stream2, s->hostDone, s->evWave, &launches), "wavefront launch");
+            WPT_CUDA(wptd::launchWavefront(features, dscene, P, s->numSMs, stream, s->stream2, s->hostDone, s->evWave, &launches), "wavefront launch");
         else
-            WPT_CUDA(wptd::launchRender(features, s->d, P, s->numSMs, stream, &launches), "render kernel launch");
+            WPT_CUDA(wptd::launchRender(features, dscene, P, s->numSMs, stream, &launches), "render kernel launch");
     }
     if (timed)
         WPT_CUDA(cudaEventRecord(s->evStop, stream), "cudaEventRecord");
@@ -816,7 +850,11 @@ static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width,
         WPT_CUDA(cudaMemsetAsync(s->qStats.p, 0, sizeof(wptd::TraceStats), stream), "clear stats");
         dStats = static_cast<wptd::TraceStats*>(s->qStats.p);
     }
-    WPT_CUDA(wptd::launchQuery(sceneFeatures(s, false), counters != nullptr, s->d, P, dO, dD, nRays, time,
+    wptd::DScene dscene;
+    rc = launchScene(s, time, time, stream, dscene);
+    if (rc != WPT_OK)
+        return rc;
+    WPT_CUDA(wptd::launchQuery(sceneFeatures(s, false), counters != nullptr, dscene, P, dO, dD, nRays, time,
                 static_cast<int32_t*>(s->qIds.p), static_cast<float*>(s->qDist.p), dStats, stream), "query kernel launch");
     WPT_CUDA(cudaMemcpyAsync(ids, s->qIds.p, nRays * sizeof(int32_t), cudaMemcpyDeviceToHost, stream), "copy ids");
     WPT_CUDA(cudaMemcpyAsync(a, s->qDist.p, nRays * sizeof(float), cudaMemcpyDeviceToHost, stream), "copy distances");
@@ -919,7 +957,11 @@ int wpt_get_ground_truth(wpt_scene* s, const wpt_camera_desc* camera, uint32_t w
         G.materialIds = s->gtMaterialIds.as<int32_t>();
         G.nMaterialIds = nMaterialIds;
     }
-    WPT_CUDA(wptd::launchGroundTruth(sceneFeatures(s, false), s->d, P, G, stream), "ground truth kernel launch");
+    wptd::DScene dscene;
+    rc = launchScene(s, t0, t0, stream, dscene);
+    if (rc != WPT_OK)
+        return rc;
+    WPT_CUDA(wptd::launchGroundTruth(sceneFeatures(s, false), dscene, P, G, stream), "ground truth kernel launch");
     for (int i = 0; i < WPT_GT_FLOAT_IMAGES; i++)
         if (bits & (1u << i))
             WPT_CUDA(cudaMemcpyAsync(out->aov[i], G.aov[i], pixels * WPT_GT_COMPONENTS[i] * sizeof(float),

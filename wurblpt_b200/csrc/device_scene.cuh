@@ -63,6 +63,9 @@ struct DScene {
     const float4* texels;
     const wpt_animation* animations;
     const wpt_keyframe* keyframes;
+    const float* animTable;     /* all rays of the launch share one time: per animation 32 floats, evaluated on the host
+                                   for that time (translation 3, rotation 4, scaling 3, mat4 as 3x4 12, normal matrix 9,
+                                   pad); nullptr = every thread evaluates the key frames at its ray's time */
     const float* envM;
     const int32_t* envMs;
     const float* envMcs;

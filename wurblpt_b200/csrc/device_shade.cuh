@@ -75,7 +75,7 @@ WPT_DEV HitRec triangleHitRecord(const DScene& S, uint32_t slot, const Ray& ray,
     if (transform)
         n = mul33(inst->N, n);
     if ((F & F_ANIM) && anim != 0)
-        n = mul33(ctx.animN[anim - 1].m, n);
+        n = mul33(animNormalMatrix<F>(S, ctx, anim), n);
     n = normalize(n);
     if (backfacing)
         n = -n;
@@ -93,7 +93,7 @@ WPT_DEV HitRec triangleHitRecord(const DScene& S, uint32_t slot, const Ray& ray,
             if (transform)
                 t = mul33(inst->N, t);
             if ((F & F_ANIM) && anim != 0)
-                t = mul33(ctx.animN[anim - 1].m, t);
+                t = mul33(animNormalMatrix<F>(S, ctx, anim), t);
             t = normalize(t - dot(n, t) * n);
         }
         hr.t = t;
@@ -825,7 +825,7 @@ WPT_DEV float hotSpotPdf(const DScene& S, uint32_t ref, float3 origin, float3 di
         if (F & F_ANIM) {
             const uint32_t anim = __float_as_uint(s2.y);
             if (anim != 0) {
-                const Trs& T = ctx.animT[anim - 1];
+                const Trs T = animTrs<F>(S, ctx, anim);
                 const float scale = rmax(rmax(T.s.x, T.s.y), T.s.z);
                 hitCenter = center + T.t;
                 hitRadius = radius * scale;
@@ -880,7 +880,7 @@ WPT_DEV float3 hotSpotDirection(const DScene& S, uint32_t ref, float3 origin, Ct
         if (inst->has_transform)
             p = transformPoint(inst->M, 4, p);
         if ((F & F_ANIM) && anim != 0)
-            p = transformPoint(ctx.animM[anim - 1].m, 3, p);
+            p = transformPoint(animMatrix<F>(S, ctx, anim), 3, p);
         return normalize(p - origin);
     }
     if (type == PRIM_SPHERE) {          /* HitableSphere::direction (hitable_sphere.hpp:192-219) */

@@ -154,6 +154,8 @@ template<int F>
 WPT_DEV void animationCacheInit(const DScene& S, Ctx<F>& ctx, float t)
 {
     if (F & F_ANIM) {
+        if (S.animTable)
+            return;     /* one time for the whole launch: the transformations are in S.animTable */
         for (uint32_t i = 0; i < S.nAnimations && i < uint32_t(MAX_CACHED_ANIMATIONS); i++) {
             const wpt_animation an = S.animations[i];
             Trs T = keyframesAt(S.keyframes + an.first_keyframe, an.keyframe_count, t);
@@ -163,6 +165,31 @@ WPT_DEV void animationCacheInit(const DScene& S, Ctx<F>& ctx, float t)
             ctx.animM[i] = toMat34(T, N);
         }
     }
+}
+
+/* Transformation of animation `anim` (1-based, as stored with the primitives) at the thread's current time. */
+template<int F>
+WPT_DEV Trs animTrs(const DScene& S, const Ctx<F>& ctx, uint32_t anim)
+{
+    if (S.animTable) {
+        const float* e = S.animTable + size_t(anim - 1u) * 32u;
+        Trs T;
+        T.t = f3(e[0], e[1], e[2]);
+        T.r = f4(e[3], e[4], e[5], e[6]);
+        T.s = f3(e[7], e[8], e[9]);
+        return T;
+    }
+    return ctx.animT[anim - 1u];
+}
+template<int F>
+WPT_DEV const float* animMatrix(const DScene& S, const Ctx<F>& ctx, uint32_t anim)
+{
+    return S.animTable ? S.animTable + size_t(anim - 1u) * 32u + 10u : ctx.animM[anim - 1u].m;
+}
+template<int F>
+WPT_DEV const float* animNormalMatrix(const DScene& S, const Ctx<F>& ctx, uint32_t anim)
+{
+    return S.animTable ? S.animTable + size_t(anim - 1u) * 32u + 22u : ctx.animN[anim - 1u].m;
 }
 
 /* ------------------------------------------------------------ ray / triangle */
@@ -180,7 +207,7 @@ WPT_DEV void triangleCorners(const DScene& S, uint32_t slot, const Ctx<F>& ctx,
     anim = __float_as_uint(c.w);
     if (F & F_ANIM) {
         if (anim != 0) {
-            const float* M = ctx.animM[anim - 1].m;
+            const float* M = animMatrix<F>(S, ctx, anim);
             v0 = transformPoint(M, 3, v0);
             v1 = transformPoint(M, 3, v1);
             v2 = transformPoint(M, 3, v2);
@@ -265,7 +292,7 @@ WPT_DEV SphereGeom sphereGeom(const DScene& S, uint32_t slot, const Ctx<F>& ctx)
     if (F & F_ANIM) {
         uint32_t anim = __float_as_uint(c.y);
         if (anim != 0) {
-            const Trs& T = ctx.animT[anim - 1];
+            const Trs T = animTrs<F>(S, ctx, anim);
             g.center = g.center + T.t;
             g.radius = g.radius * rmax(rmax(T.s.x, T.s.y), T.s.z);
             g.rotation = qmul(g.rotation, T.r);
