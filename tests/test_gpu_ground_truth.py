@@ -150,3 +150,18 @@ def test_reference_material_playground_app_runs_unchanged(gpu, tmp_path):
     assert a.shape == (600, 800, 3)
     assert 5 < a.mean() < 250 and a.std() > 5          # an image, not a constant
     assert np.abs(a.astype(np.int32) - b.astype(np.int32)).mean() > 0.5     # the camera and the objects moved
+
+
+def test_reference_toomuch_app_runs_unchanged(gpu, tmp_path):
+    """wurblpt-toomuch.cpp, unchanged, frame 0: eleven user-defined Animation subclasses (lights, objects, camera)
+    with motion blur, a user-defined time-dependent Texture on the lights (sampled into images), mirror sphere,
+    glass pillars, ModPhong objects, 21 hot spots."""
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "apps", "_bin", "wurblpt-toomuch")
+    if not os.path.exists(exe):
+        pytest.skip("apps/_bin/wurblpt-toomuch not built")
+    r = subprocess.run([exe, "0"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "Rendering 400x300 pixels with 100 samples" in r.stderr
+    hdr = read_wptarray(str(tmp_path / "toomuch-0000.tgd"))
+    assert hdr.shape == (300, 400, 3) and np.isfinite(hdr).all()
+    assert hdr.mean() > 0.01 and (hdr > 0).mean() > 0.9      # a lit room, not a black frame

@@ -58,10 +58,10 @@ def test_mirror_views_equal_reference_views(scenes, ref):
 @pytest.mark.skipif(not os.path.exists(REFERENCE + "/wurblpt-cornellbox/wurblpt-cornellbox.cpp"),
                     reason="reference sources not present")
 @pytest.mark.parametrize("app", ["wurblpt-animations", "wurblpt-envmap", "wurblpt-material-comparison",
-                                 "wurblpt-normalmap", "wurblpt-toomuch"])
+                                 "wurblpt-normalmap"])
 def test_reference_app_source_is_accepted_by_the_mirror(app):
-    """Apps that need image files or bake user-defined Animation / Texture subclasses cannot
-    run yet, but their unchanged sources must at least compile against the API mirror."""
+    """Apps that need image files that are not available offline cannot run here, but their unchanged sources
+    must at least compile against the API mirror."""
     src = "%s/%s/%s.cpp" % (REFERENCE, app, app)
     r = subprocess.run(["/usr/bin/g++", "-std=c++20", "-O0", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), src],
                        capture_output=True, text=True)
@@ -71,7 +71,8 @@ def test_reference_app_source_is_accepted_by_the_mirror(app):
 @pytest.mark.skipif(not os.path.exists(REFERENCE + "/wurblpt-cornellbox/wurblpt-cornellbox.cpp"),
                     reason="reference sources not present")
 @pytest.mark.parametrize("app", ["wurblpt-cornellbox", "wurblpt-rtiow", "wurblpt-furnace-test", "wurblpt-mis-test",
-                                 "wurblpt-participating-media", "wurblpt-tof-example", "wurblpt-material-playground"])
+                                 "wurblpt-participating-media", "wurblpt-tof-example", "wurblpt-material-playground",
+                                 "wurblpt-toomuch"])
 def test_reference_app_compiles_unchanged_against_the_mirror(app, tmp_path):
     """'existing example apps link unchanged': compile the reference's own app source against
     include/wurblpt + include/tgd and link it against libwurblpt_b200.so."""

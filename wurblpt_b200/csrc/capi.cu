@@ -353,7 +353,9 @@ uint32_t waveSlotLimit()
 
 int sceneFeatures(const wpt_scene* s, bool needOpl)
 {
-    return (s->sceneHasMedia || s->sceneHasAnimation || needOpl) ? 7 : 0;
+    if (!(s->sceneHasMedia || s->sceneHasAnimation || needOpl))
+        return 0;
+    return s->sceneHasAnimation ? 7 : 5;    /* F_MEDIA | F_OPL, plus F_ANIM (kernels.cu picks the compiled variant) */
 }
 
 /* The device scene for one launch. When all rays of the launch have the same time (t0 == t1: no motion blur, or a

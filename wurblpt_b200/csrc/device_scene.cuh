@@ -79,7 +79,7 @@ struct DScene {
     int32_t envTex[6];
 };
 
-constexpr int MAX_CACHED_ANIMATIONS = 4;    /* per-thread animation cache entries (AnimationCache) */
+constexpr int MAX_CACHED_ANIMATIONS = 16;   /* per-thread animation cache entries (AnimationCache), filled lazily */
 
 /* Wavefront slot arrays (structure of arrays). The kernels reach the slots through queues, i.e. in
  * scattered order, so fields that are always used together are interleaved in pairs that fill one

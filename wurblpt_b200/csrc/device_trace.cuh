@@ -96,9 +96,12 @@ struct Ctx {
     Prng prng;
     unsigned int nested;
     unsigned int nodes, leaves;
-    Trs animT[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
-    Mat34 animM[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
-    Mat33 animN[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
+    /* AnimationCache (animation.hpp:52-125): filled lazily, entry by entry, for the time `animTime` */
+    mutable float animTime;
+    mutable uint32_t animValid;     /* bit i: entry i holds animation i at animTime */
+    mutable Trs animT[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
+    mutable Mat34 animM[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
+    mutable Mat33 animN[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
 };
 
 /* AnimationKeyframes::at (animation_keyframes.hpp:191-215) */
@@ -148,26 +151,33 @@ __device__ __noinline__ Trs keyframesAt(const wpt_keyframe* kf, uint32_t count, 
     return trsMix(keyframeTrs(kf[lower]), keyframeTrs(kf[higher]), alpha);
 }
 
-/* AnimationCache::init(t) followed by the lazy per-index evaluation (animation.hpp:62-70,96-101);
- * evaluated eagerly here for the (few) animations of the scene. */
+/* AnimationCache::init(t) (animation.hpp:62-70): a new time invalidates the entries; they are evaluated on
+ * first use (animation.hpp:96-101). */
 template<int F>
 WPT_DEV void animationCacheInit(const DScene& S, Ctx<F>& ctx, float t)
 {
     if (F & F_ANIM) {
-        if (S.animTable)
-            return;     /* one time for the whole launch: the transformations are in S.animTable */
-        for (uint32_t i = 0; i < S.nAnimations && i < uint32_t(MAX_CACHED_ANIMATIONS); i++) {
-            const wpt_animation an = S.animations[i];
-            Trs T = keyframesAt(S.keyframes + an.first_keyframe, an.keyframe_count, t);
-            Mat33 N = toMat33(T.r);
-            ctx.animT[i] = T;
-            ctx.animN[i] = N;
-            ctx.animM[i] = toMat34(T, N);
-        }
+        ctx.animTime = t;
+        ctx.animValid = 0u;
     }
 }
 
-/* Transformation of animation `anim` (1-based, as stored with the primitives) at the thread's current time. */
+template<int F>
+WPT_DEV void animationCacheEnsure(const DScene& S, const Ctx<F>& ctx, uint32_t i)
+{
+    if (!(ctx.animValid & (1u << i))) {
+        const wpt_animation an = S.animations[i];
+        const Trs T = keyframesAt(S.keyframes + an.first_keyframe, an.keyframe_count, ctx.animTime);
+        const Mat33 N = toMat33(T.r);
+        ctx.animT[i] = T;
+        ctx.animN[i] = N;
+        ctx.animM[i] = toMat34(T, N);
+        ctx.animValid |= (1u << i);
+    }
+}
+
+/* Transformation of animation `anim` (1-based, as stored with the primitives) at the thread's current time:
+ * from the launch's table when all rays share one time, else from the thread's cache. */
 template<int F>
 WPT_DEV Trs animTrs(const DScene& S, const Ctx<F>& ctx, uint32_t anim)
 {
@@ -179,17 +189,24 @@ WPT_DEV Trs animTrs(const DScene& S, const Ctx<F>& ctx, uint32_t anim)
         T.s = f3(e[7], e[8], e[9]);
         return T;
     }
+    animationCacheEnsure<F>(S, ctx, anim - 1u);
     return ctx.animT[anim - 1u];
 }
 template<int F>
 WPT_DEV const float* animMatrix(const DScene& S, const Ctx<F>& ctx, uint32_t anim)
 {
-    return S.animTable ? S.animTable + size_t(anim - 1u) * 32u + 10u : ctx.animM[anim - 1u].m;
+    if (S.animTable)
+        return S.animTable + size_t(anim - 1u) * 32u + 10u;
+    animationCacheEnsure<F>(S, ctx, anim - 1u);
+    return ctx.animM[anim - 1u].m;
 }
 template<int F>
 WPT_DEV const float* animNormalMatrix(const DScene& S, const Ctx<F>& ctx, uint32_t anim)
 {
-    return S.animTable ? S.animTable + size_t(anim - 1u) * 32u + 22u : ctx.animN[anim - 1u].m;
+    if (S.animTable)
+        return S.animTable + size_t(anim - 1u) * 32u + 22u;
+    animationCacheEnsure<F>(S, ctx, anim - 1u);
+    return ctx.animN[anim - 1u].m;
 }
 
 /* ------------------------------------------------------------ ray / triangle */

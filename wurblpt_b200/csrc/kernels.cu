@@ -1108,6 +1108,8 @@ cudaError_t launchWavefront(int features, const DScene& S, const RenderParams& P
 {
     if (features == 0)
         return launchWavefrontT<0>(S, P, numSMs, stream, stream2, hostDone, events, launches);
+    if (!(features & F_ANIM))   /* media / ToF / gated sensor without animated hitables: no per-thread animation cache */
+        return launchWavefrontT<F_MEDIA | F_OPL>(S, P, numSMs, stream, stream2, hostDone, events, launches);
     return launchWavefrontT<F_MEDIA | F_ANIM | F_OPL>(S, P, numSMs, stream, stream2, hostDone, events, launches);
 }
 
