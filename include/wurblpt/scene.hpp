@@ -371,6 +371,19 @@ public:
 
     bool hasBakedAnimations() const { return _hasBakedAnimations; }
 
+    /* mcpt(t0, t1) on a description that was sampled for other times (user-defined textures are functions of
+     * time, and nothing obliges the caller to call updateBVH() again when the scene has no animations):
+     * sample again for (t0, t1) and rebuild the tree. Logically const. */
+    void prepareRender(float t0, float t1) const
+    {
+        if (!_hasBakedAnimations || _bakeTimes == detail::bakeTimesFor(t0, t1))
+            return;
+        Scene* self = const_cast<Scene*>(this);
+        self->prepareDevice(detail::bakeTimesFor(t0, t1));
+        if (wpt_scene_update_bvh(self->_device, t0, t1) != WPT_OK)
+            detail::die("WurblPT updateBVH", wpt_last_error());
+    }
+
     /* getGroundTruth() evaluates animations at tPrev and tNext as well: sampled animations get key frames at
      * exactly these times and the tree for t0 is rebuilt. Logically const (the scene is unchanged). */
     void prepareGroundTruth(float t0, float tPrev, float tNext) const

@@ -21,6 +21,7 @@
 // for convenience, like the reference:
 #include "animation_keyframes.hpp"
 #include "texture_image.hpp"
+#include "texture_noise.hpp"
 #include "envmap.hpp"
 #include "fresnel.hpp"
 #include "material_lambertian.hpp"
@@ -82,6 +83,7 @@ inline void mcpt(
     if (scene.bvhNeedsUpdate(t0, t1) || !scene.deviceScene())
         detail::die("mcpt", "Scene::updateBVH(t0, t1) must be called before rendering");
 
+    scene.prepareRender(t0, t1);
     wpt_sensor_desc sensorDesc;
     if (!sensor.describe(sensorDesc))
         detail::die("mcpt", "a user-defined Sensor cannot accumulate radiance on the device");

@@ -165,3 +165,19 @@ def test_reference_toomuch_app_runs_unchanged(gpu, tmp_path):
     hdr = read_wptarray(str(tmp_path / "toomuch-0000.tgd"))
     assert hdr.shape == (300, 400, 3) and np.isfinite(hdr).all()
     assert hdr.mean() > 0.01 and (hdr > 0).mean() > 0.9      # a lit room, not a black frame
+
+
+def test_reference_noise_textures_app_runs_unchanged(gpu, tmp_path):
+    """wurblpt-noise-textures.cpp, unchanged: value / gradient / Worley / Perlin noise textures combined by
+    user-defined Texture classes that switch with the render time; ten renders at t = 0..9 after one updateBVH()."""
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "apps", "_bin", "wurblpt-noise-textures")
+    if not os.path.exists(exe):
+        pytest.skip("apps/_bin/wurblpt-noise-textures not built")
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=200)
+    assert r.returncode == 0, r.stderr[-3000:]
+    images = [read_wptarray(str(tmp_path / ("noise-example-%d.png" % t))) for t in range(10)]
+    assert all(im.shape == (600, 800, 3) and im.dtype == np.uint8 for im in images)
+    assert all(im.std() > 3 for im in images)
+    # the textures are functions of time: consecutive renders differ by more than Monte-Carlo noise
+    d01 = np.abs(images[0].astype(np.int32) - images[1].astype(np.int32)).mean()
+    assert d01 > 1.0, d01
