@@ -15,128 +15,155 @@
 
 namespace WurblPT {
 
+namespace detail {
+
+/* The area-preserving map between the unit square and the unit sphere that the importance tables live on
+ * (Lambers 2022; reference envmap.hpp:55-118): Shirley and Chiu's concentric square-to-disk map followed by
+ * Lambert's azimuthal equal-area projection, with +y as the pole direction. The statements keep the
+ * reference's arithmetic, because bin boundaries decide which table entry a direction reads. */
+struct SquareSphereMap
+{
+    /* disk radius and angle of a point of [-1,1]^2 */
+    static void squareToPolar(float u, float v, float& radius, float& angle)
+    {
+        const bool uDominates = u * u > v * v;
+        radius = uDominates ? u : v;
+        if (uDominates)
+            angle = pi_4 * v / u;
+        else
+            angle = (abs(v) > 0.0f ? pi_2 - pi_4 * u / v : 0.0f);
+    }
+
+    static vec3 toSphere(const vec2& uv)
+    {
+        float radius, angle;
+        squareToPolar(2.0f * uv.x() - 1.0f, 2.0f * uv.y() - 1.0f, radius, angle);
+        const float latitude = pi_2 - 2.0f * asin(radius);
+        const float longitude = angle + pi_2;
+        return normalize(vec3(-cos(latitude) * sin(longitude), sin(latitude), cos(latitude) * cos(longitude)));
+    }
+
+    static vec2 toSquare(const vec3& direction)
+    {
+        const float latitude = asin(clamp(direction.y(), -1.0f, +1.0f));
+        const float longitude = atan2(-direction.x(), direction.z());
+        const float radius = sin(0.5f * (pi_2 - latitude));
+        float angle = longitude - pi_2;
+        if (angle < -pi_4)
+            angle += 2.0f * pi;
+        /* the four triangles of the square, counter-clockwise from the one around +u */
+        const int triangle = (angle < pi_4 ? 0 : angle < pi_2 + pi_4 ? 1 : angle < pi + pi_4 ? 2 : 3);
+        float u = 0.0f, v = 0.0f;
+        switch (triangle) {
+        case 0:
+            u = radius;
+            v = angle * u / pi_4;
+            break;
+        case 1:
+            v = radius;
+            u = -(angle - pi_2) * v / pi_4;
+            break;
+        case 2:
+            u = -radius;
+            v = (angle - pi) * u / pi_4;
+            break;
+        default:
+            v = -radius;
+            u = -(angle - (pi + pi_2)) * v / pi_4;
+            break;
+        }
+        return vec2(0.5f * (u + 1.0f), 0.5f * (v + 1.0f));
+    }
+};
+
+}
+
 class EnvironmentMap
 {
 private:
-    int N;
-    std::vector<float> M;       // importance per bin, normalised
-    std::vector<int> Ms;        // bins by descending importance
-    std::vector<float> Mcs;     // cumulative importance along Ms
+    int N;                      /* bins per side of the square; 0 = no importance sampling */
+    std::vector<float> M;       /* normalised importance of bin y * N + x */
+    std::vector<int> Ms;        /* bin numbers, most important first */
+    std::vector<float> Mcs;     /* running sum of M along Ms */
 
-    /* square [0,1]^2 -> unit sphere, equal area (Shirley's square-to-disk, then Lambert) */
-    static vec3 invm(const vec2& uv)
+    int binOf(const vec3& direction) const
     {
-        float u = 2.0f * uv.x() - 1.0f;
-        float v = 2.0f * uv.y() - 1.0f;
-        float r, alpha;
-        if (u * u > v * v) {
-            r = u;
-            alpha = pi_4 * v / u;
-        } else {
-            r = v;
-            if (abs(v) > 0.0f)
-                alpha = pi_2 - pi_4 * u / v;
-            else
-                alpha = 0.0f;
-        }
-        float lat = pi_2 - 2.0f * asin(r);
-        float lon = alpha + pi_2;
-        vec3 d = vec3(-cos(lat) * sin(lon), sin(lat), cos(lat) * cos(lon));
-        return normalize(d);
+        const vec2 uv = detail::SquareSphereMap::toSquare(direction);
+        int column = uv.x() * N;
+        int row = uv.y() * N;
+        column = (column >= N ? N - 1 : column);
+        row = (row >= N ? N - 1 : row);
+        return row * N + column;
     }
 
-    /* unit sphere -> square, inverse of invm() */
-    static vec2 m(const vec3& d)
+    /* index into Ms of the first bin whose running sum reaches r (bisection as in the reference) */
+    int rankFor(float r) const
     {
-        float lat = asin(clamp(d.y(), -1.0f, +1.0f));
-        float lon = atan2(-d.x(), d.z());
-        float r = sin(0.5f * (pi_2 - lat));
-        float alpha = lon - pi_2;
-        float u, v;
-        if (alpha < -pi_4)
-            alpha += 2.0f * pi;
-        if (alpha < pi_4) {
-            u = r;
-            v = alpha * u / pi_4;
-        } else if (alpha < pi_2 + pi_4) {
-            v = r;
-            u = -(alpha - pi_2) * v / pi_4;
-        } else if (alpha < pi + pi_4) {
-            u = -r;
-            v = (alpha - pi) * u / pi_4;
-        } else {
-            v = -r;
-            u = -(alpha - (pi + pi_2)) * v / pi_4;
+        int below = 0;
+        int above = N * N - 1;
+        while (above > below + 1) {
+            const int middle = (below + above) / 2;
+            if (Mcs[middle] < r)
+                below = middle;
+            else
+                above = middle;
         }
-        return vec2(0.5f * (u + 1.0f), 0.5f * (v + 1.0f));
+        return Mcs[below] >= r ? below : above;
     }
 
 public:
     EnvironmentMap() : N(0) {}
     virtual ~EnvironmentMap() {}
 
+    virtual vec4 L(const vec3& direction, float t = 0.0f) const = 0;
+
+    /* Tabulates the radiance (sum of the four channels) at the bin centres, normalises, ranks the bins and
+     * accumulates; single precision sums in this order, like the reference (envmap.hpp:121-158). */
     void initializeImportanceSampling(int n)
     {
         N = n;
-        M.resize(N * N);
-        Ms.resize(N * N);
-        Mcs.resize(N * N);
-        float totalImportance = 0.0f;
-        for (int y = 0; y < N; y++) {
-            float v = (y + 0.5f) / N;
-            for (int x = 0; x < N; x++) {
-                float u = (x + 0.5f) / N;
-                vec4 radiance = L(invm(vec2(u, v)));
-                float importance = radiance.x() + radiance.y() + radiance.z() + radiance.w();
-                totalImportance += importance;
-                M[y * N + x] = importance;
-            }
+        const int bins = N * N;
+        M.assign(bins, 0.0f);
+        float total = 0.0f;
+        for (int bin = 0; bin < bins; bin++) {
+            const float v = ((bin / N) + 0.5f) / N;
+            const float u = ((bin % N) + 0.5f) / N;
+            const vec4 radiance = L(detail::SquareSphereMap::toSphere(vec2(u, v)));
+            const float importance = radiance.x() + radiance.y() + radiance.z() + radiance.w();
+            total += importance;
+            M[bin] = importance;
         }
-        for (int i = 0; i < N * N; i++)
-            M[i] /= totalImportance;
-        for (int i = 0; i < N * N; i++)
-            Ms[i] = i;
+        for (float& importance : M)
+            importance /= total;
+        Ms.resize(bins);
+        for (int bin = 0; bin < bins; bin++)
+            Ms[bin] = bin;
         std::sort(Ms.begin(), Ms.end(), [this](unsigned int i, unsigned int j) { return this->M[i] > this->M[j]; });
-        float sum = 0.0f;
-        for (int i = 0; i < N * N; i++) {
-            sum += M[Ms[i]];
-            Mcs[i] = sum;
+        Mcs.resize(bins);
+        float running = 0.0f;
+        for (int rank = 0; rank < bins; rank++) {
+            running += M[Ms[rank]];
+            Mcs[rank] = running;
         }
     }
 
     bool supportsImportanceSampling() const { return N > 0; }
 
-    virtual vec4 L(const vec3& direction, float t = 0.0f) const = 0;
-
+    /* solid-angle density of d() in `direction` */
     float p(const vec3& direction) const
     {
-        vec2 uv = m(direction);
-        int x = uv.x() * N;
-        int y = uv.y() * N;
-        if (x >= N)
-            x = N - 1;
-        if (y >= N)
-            y = N - 1;
-        float invBinSizeOnSphere = (N * N) * 0.25f * inv_pi;
-        return M[y * N + x] * invBinSizeOnSphere;
+        const float binsPerSteradian = (N * N) * 0.25f * inv_pi;
+        return M[binOf(direction)] * binsPerSteradian;
     }
 
+    /* a direction drawn proportionally to the tabulated radiance: one draw picks the bin, two place the
+     * direction inside it */
     vec3 d(Prng& prng) const
     {
-        float r = prng.in01();
-        int a = 0;
-        int b = N * N - 1;
-        while (b > a + 1) {
-            int c = (a + b) / 2;
-            if (Mcs[c] < r)
-                a = c;
-            else
-                b = c;
-        }
-        int bin = Ms[Mcs[a] >= r ? a : b];
-        float u = ((bin % N) + prng.in01()) / N;
-        float v = ((bin / N) + prng.in01()) / N;
-        return invm(vec2(u, v));
+        const int bin = Ms[rankFor(prng.in01())];
+        const float u = ((bin % N) + prng.in01()) / N;
+        const float v = ((bin / N) + prng.in01()) / N;
+        return detail::SquareSphereMap::toSphere(vec2(u, v));
     }
 
     /* type-specific part of the description; returns false for user-defined subclasses */

@@ -88,76 +88,97 @@ public:
 
     Helper getHelper(const Projection& projection, unsigned int width, unsigned int height) const
     {
-        Helper h;
-        h.center = projection.center();
-        h.focalLength = projection.focalLength();
-        h.inverseFocalLength = projection.inverseFocalLength();
-        h.width = width;
-        h.height = height;
-        return h;
+        return Helper { projection.center(), projection.focalLength(), projection.inverseFocalLength(), width, height };
     }
 
+private:
+    /* normalized image coordinates [0,1]^2 <-> lens coordinates (centred, in focal lengths) */
+    static void toLens(float p, float q, const Helper& h, float& s, float& t)
+    {
+        s = (p - h.center.x()) * h.inverseFocalLength.x();
+        t = (q - h.center.y()) * h.inverseFocalLength.y();
+    }
+    static void toImage(float s, float t, const Helper& h, float& p, float& q)
+    {
+        p = s * h.focalLength.x() + h.center.x();
+        q = t * h.focalLength.y() + h.center.y();
+    }
+
+    /* the forward model shared by all three types (unused coefficients are zero): radial polynomial in r^2
+     * plus the two tangential terms (reference optics.hpp:226-246) */
+    void applyModel(float s, float t, float& sOut, float& tOut) const
+    {
+        const float r2 = s * s + t * t;
+        const float r4 = r2 * r2;
+        const float r6 = r4 * r2;
+        const float radial = 1.0f + k1 * r2 + k2 * r4 + k3 * r6;
+        const float mixed = 2.0f * s * t;
+        const float alongS = r2 + 2.0f * s * s;
+        const float alongT = r2 + 2.0f * t * t;
+        sOut = s * radial + p1 * mixed + p2 * alongS;
+        tOut = t * radial + p1 * alongT + p2 * mixed;
+    }
+
+public:
+    /* p and q are normalized image coordinates in [0,1]^2 */
     void distort(float& p, float& q, const Helper& helper) const
     {
         if (type == None)
             return;
-        float s = (p - helper.center.x()) * helper.inverseFocalLength.x();
-        float t = (q - helper.center.y()) * helper.inverseFocalLength.y();
-        float r2 = s * s + t * t;
-        float r4 = r2 * r2;
-        float r6 = r4 * r2;
-        float rd = 1.0f + k1 * r2 + k2 * r4 + k3 * r6;
-        float term1 = 2.0f * s * t;
-        float term2 = r2 + 2.0f * s * s;
-        float term3 = r2 + 2.0f * t * t;
-        float ns = s * rd + p1 * term1 + p2 * term2;
-        float nt = t * rd + p1 * term3 + p2 * term1;
-        p = ns * helper.focalLength.x() + helper.center.x();
-        q = nt * helper.focalLength.y() + helper.center.y();
+        float s, t, sd, td;
+        toLens(p, q, helper, s, t);
+        applyModel(s, t, sd, td);
+        toImage(sd, td, helper, p, q);
     }
 
+    /* the inverse: closed-form approximations for the two analytic models (optics.hpp:251-278), fixed-point
+     * iteration with a tolerance of `epsilon` pixels for the OpenCV model (optics.hpp:279-308) */
     void undistort(float& p, float& q, const Helper& helper) const
     {
         if (type == None)
             return;
-        float s = (p - helper.center.x()) * helper.inverseFocalLength.x();
-        float t = (q - helper.center.y()) * helper.inverseFocalLength.y();
-        if (type == RadialAndPlanar) {
-            float r2 = s * s + t * t;
-            float r4 = r2 * r2;
-            float d1 = k1 * r2 + k2 * r4;
-            float d2 = 1.0f / (4.0f * k1 * r2 + 6.0f * k2 * r4 + 8.0f * p1 * t + 8.0f * p2 * s + 1.0f);
+        float s, t;
+        toLens(p, q, helper, s, t);
+        const float r2 = s * s + t * t;
+        const float r4 = r2 * r2;
+        switch (type) {
+        case RadialAndPlanar: {
+            const float d1 = k1 * r2 + k2 * r4;
+            const float d2 = 1.0f / (4.0f * k1 * r2 + 6.0f * k2 * r4 + 8.0f * p1 * t + 8.0f * p2 * s + 1.0f);
             p = (s - d2 * (d1 * s + 2.0f * p1 * s * t + p2 * (r2 + 2.0f * s * s))) * helper.focalLength.x() + helper.center.x();
             q = (t - d2 * (d1 * t + p1 * (r2 + 2.0f * t * t) + 2.0f * p2 * s * t)) * helper.focalLength.y() + helper.center.y();
-        } else if (type == RadialOnly) {
-            float r2 = s * s + t * t;
-            float r4 = r2 * r2;
-            float r6 = r4 * r2;
-            float r8 = r4 * r4;
-            float d = 1.0f + b1 * r2 + b2 * r4 + b3 * r6 + b4 * r8;
+            break;
+        }
+        case RadialOnly: {
+            const float r6 = r4 * r2;
+            const float r8 = r4 * r4;
+            const float d = 1.0f + b1 * r2 + b2 * r4 + b3 * r6 + b4 * r8;
             p = s * d * helper.focalLength.x() + helper.center.x();
             q = t * d * helper.focalLength.y() + helper.center.y();
-        } else {
-            const float s0 = s, t0 = t;
+            break;
+        }
+        default: {
+            const float sTarget = s, tTarget = t;
             float squaredError = std::numeric_limits<float>::max();
             for (int i = 0; i < maxIterations && squaredError >= epsilon * epsilon; i++) {
-                float r2 = s * s + t * t;
-                float r4 = r2 * r2;
-                float r6 = r4 * r2;
-                float rd = 1.0f + k1 * r2 + k2 * r4 + k3 * r6;
-                float invrd = 1.0f / rd;
-                float ds = 2.0f * p1 * s * t + p2 * (r2 + 2.0f * s * s);
-                float dt = 2.0f * p2 * s * t + p1 * (r2 + 2.0f * t * t);
-                s = (s0 - ds) * invrd;
-                t = (t0 - dt) * invrd;
-                float ep = s * helper.focalLength.x() + helper.center.x();
-                float eq = t * helper.focalLength.y() + helper.center.y();
-                distort(ep, eq, helper);
-                vec2 offsetInPixels = (vec2(ep, eq) - vec2(p, q)) * vec2(helper.width, helper.height);
+                const float rr2 = s * s + t * t;
+                const float rr4 = rr2 * rr2;
+                const float rr6 = rr4 * rr2;
+                const float radial = 1.0f + k1 * rr2 + k2 * rr4 + k3 * rr6;
+                const float inverseRadial = 1.0f / radial;
+                const float shiftS = 2.0f * p1 * s * t + p2 * (rr2 + 2.0f * s * s);
+                const float shiftT = 2.0f * p2 * s * t + p1 * (rr2 + 2.0f * t * t);
+                s = (sTarget - shiftS) * inverseRadial;
+                t = (tTarget - shiftT) * inverseRadial;
+                float checkP, checkQ;
+                toImage(s, t, helper, checkP, checkQ);
+                distort(checkP, checkQ, helper);
+                const vec2 offsetInPixels = (vec2(checkP, checkQ) - vec2(p, q)) * vec2(helper.width, helper.height);
                 squaredError = dot(offsetInPixels, offsetInPixels);
             }
-            p = s * helper.focalLength.x() + helper.center.x();
-            q = t * helper.focalLength.y() + helper.center.y();
+            toImage(s, t, helper, p, q);
+            break;
+        }
         }
     }
 };
