@@ -54,6 +54,9 @@ def test_no_cpu_fallback(capi):
     with pytest.raises(capi.WptError) as e:
         s.primary_hits(g.camera, 8, 8)
     assert e.value.code == abi.WPT_E_NO_DEVICE
+    with pytest.raises(capi.WptError) as e:
+        s.ground_truth(g.camera, 8, 8)
+    assert e.value.code == abi.WPT_E_NO_DEVICE
     with pytest.raises(capi.WptError):
         capi.prng_kat([1, 2], 4)
 

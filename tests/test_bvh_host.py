@@ -51,3 +51,28 @@ def test_empty_scene_builds(capi):
     from wurblpt_b200 import scene_desc as sd
     s = capi.Scene(sd.HostScene(arrays).desc, device=-1).update_bvh()
     assert s.info().hitables == 0
+
+
+def test_coincident_triangles_build_a_valid_tree(capi):
+    """Exact ties in the SAH sweep (every triangle of a mesh instanced twice at the same place): the builder must
+    terminate, keep one hitable per leaf and list every hitable once; this is also the input on which the device
+    has to settle exact-distance ties the reference's way."""
+    g = Golden("cornell")
+    arrays = dict(g.host.arrays)
+    from wurblpt_b200 import scene_desc as sd
+    comps = arrays["components"].copy()
+    arrays["components"] = np.concatenate([comps, comps])      # every component a second time
+    s = capi.Scene(sd.HostScene(arrays).desc, device=-1).update_bvh()
+    n = s.info().hitables
+    assert n == 2 * capi.Scene(g.desc, device=-1).update_bvh().info().hitables
+    boxes, link, leaf = s.binary_nodes()
+    assert len(leaf) == 2 * n - 1
+    assert np.array_equal(np.sort(leaf[leaf >= 0]), np.arange(n))
+    assert np.isfinite(boxes).all() and (boxes[:, :3] <= boxes[:, 3:]).all()
+
+
+def test_single_hitable_tree(capi):
+    g = Golden("furnace")       # one sphere
+    s = capi.Scene(g.desc, device=-1).update_bvh()
+    boxes, link, leaf = s.binary_nodes()
+    assert s.info().hitables == 1 and len(leaf) == 1 and leaf[0] == 0
