@@ -1,12 +1,12 @@
-"""Regenerates profiles/r1_algorithmic_work.json: the reference's own node visits / leaf tests per BVH::hit()
+"""TEST INFRASTRUCTURE (uses oracle/). Regenerates profiles/r1_algorithmic_work.json: the reference's own node visits / leaf tests per BVH::hit()
 (SURVEY.md section 8d), counted by the instrumented build of the unmodified reference (oracle/_ref/libwpt_ref_instr.so)
 on a reduced image of each benchmark config. bytes/query = 32 n + 68 l, flops/query = 25 n + 50 l.
-Run in the build container: make -C oracle ref && python scripts/algorithmic_work.py [config ...]"""
+Run in the build container: make -C oracle ref && python tests/tools/algorithmic_work.py [config ...]"""
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import refapi  # noqa: E402
 

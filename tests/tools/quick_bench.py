@@ -1,4 +1,4 @@
-"""Ad-hoc timing on the GPU box (development aid, not the bench contract): renders a config with
+"""TEST INFRASTRUCTURE (uses oracle/): ad-hoc timing on the GPU box (development aid, not the bench contract): renders a config with
 the scene taken from the oracle harness and prints Msamples/s, Mrays/s and the reference's CPU time."""
 import argparse
 import os
@@ -7,7 +7,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
