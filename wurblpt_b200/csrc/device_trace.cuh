@@ -476,17 +476,43 @@ __device__ Hit traverseReference(const DScene& S, uint32_t root, const Ray& ray,
 
 /* ------------------------------------------------------------ 4-wide walk */
 
+#ifndef WPT_SHARED_STACK_PTX
+#define WPT_SHARED_STACK_PTX 0      /* experiment (not yet measured): ld.shared / st.shared instead of generic accesses */
+#endif
+
 struct WideStack {
     uint2* sm;              /* this thread's column of the shared-memory stack, stride = blockDim.x */
     int stride;
     uint2 spill[LOCAL_STACK];
     int sp;
 
+#if WPT_SHARED_STACK_PTX
+    /* The pointer above reaches shared memory through the generic address space (LD.E / ST.E in SASS,
+     * profiles/r1_sass_trace_kernel.txt); these two address it as shared memory. */
+    WPT_DEV uint32_t sharedAddress(int entry) const
+    {
+        return uint32_t(__cvta_generic_to_shared(sm)) + uint32_t(entry * stride) * uint32_t(sizeof(uint2));
+    }
+    WPT_DEV void storeShared(int entry, uint2 e) const
+    {
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(sharedAddress(entry)), "r"(e.x), "r"(e.y) : "memory");
+    }
+    WPT_DEV uint2 loadShared(int entry) const
+    {
+        uint2 e;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(sharedAddress(entry)) : "memory");
+        return e;
+    }
+#else
+    WPT_DEV void storeShared(int entry, uint2 e) const { sm[entry * stride] = e; }
+    WPT_DEV uint2 loadShared(int entry) const { return sm[entry * stride]; }
+#endif
+
     WPT_DEV void push(uint32_t code, float tmin)
     {
         uint2 e = make_uint2(code, __float_as_uint(tmin));
         if (sp < SM_STACK)
-            sm[sp * stride] = e;
+            storeShared(sp, e);
         else
             spill[sp - SM_STACK] = e;
         sp++;
@@ -494,7 +520,7 @@ struct WideStack {
     WPT_DEV uint2 pop()
     {
         --sp;
-        return sp < SM_STACK ? sm[sp * stride] : spill[sp - SM_STACK];
+        return sp < SM_STACK ? loadShared(sp) : spill[sp - SM_STACK];
     }
 };
 
