@@ -477,7 +477,7 @@ __device__ Hit traverseReference(const DScene& S, uint32_t root, const Ray& ray,
 /* ------------------------------------------------------------ 4-wide walk */
 
 #ifndef WPT_SHARED_STACK_PTX
-#define WPT_SHARED_STACK_PTX 0      /* experiment (not yet measured): ld.shared / st.shared instead of generic accesses */
+#define WPT_SHARED_STACK_PTX 0      /* experiment: ld.shared / st.shared instead of generic accesses (same frame, +0.5 % on C3) */
 #endif
 
 struct WideStack {
