@@ -4,7 +4,10 @@
 
 #include <tgd/array.hpp>
 
+#include <cassert>
+#include <cstring>
 #include <memory>
+#include <vector>
 
 #include "gvm.hpp"
 #include "color.hpp"
@@ -120,6 +123,31 @@ inline TGD::Array<float> cameraSpaceToPMDSpace(const TGD::Array<float>& coords /
         pmd[e][2] = -coords[e][2];
     }
     return pmd;
+}
+
+/* A new array holding the listed components of `a`, in the listed order, with their tags
+ * (reference postproc.hpp:313-337) */
+inline TGD::ArrayContainer extractComponents(const TGD::ArrayContainer& a, const std::vector<size_t>& componentList)
+{
+    TGD::ArrayContainer picked(a.dimensions(), componentList.size(), a.componentType());
+    picked.globalTagList() = a.globalTagList();
+    for (size_t d = 0; d < a.dimensionCount(); d++)
+        picked.dimensionTagList(d) = a.dimensionTagList(d);
+    const size_t bytes = a.componentSize();
+    const unsigned char* from = static_cast<const unsigned char*>(a.data());
+    unsigned char* to = static_cast<unsigned char*>(picked.data());
+    for (size_t c = 0; c < componentList.size(); c++) {
+        assert(componentList[c] < a.componentCount());
+        picked.componentTagList(c) = a.componentTagList(componentList[c]);
+        for (size_t e = 0; e < a.elementCount(); e++)
+            std::memcpy(to + e * picked.elementSize() + c * bytes, from + e * a.elementSize() + componentList[c] * bytes, bytes);
+    }
+    return picked;
+}
+
+inline TGD::ArrayContainer extractComponent(const TGD::ArrayContainer& a, size_t component)
+{
+    return extractComponents(a, std::vector<size_t>(1, component));
 }
 
 }

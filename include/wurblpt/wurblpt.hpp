@@ -42,6 +42,7 @@
 #include "sensor.hpp"
 #include "sensor_rgb.hpp"
 #include "sensor_tof_amcw.hpp"
+#include "import.hpp"
 
 namespace WurblPT {
 

@@ -22,8 +22,15 @@
 #pragma once
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
+
+#include <unistd.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace wptcfg {
 
@@ -467,6 +474,70 @@ inline void buildMixed(Scene& scene)
     scene.take(new EnvironmentMapCube(faces[0], faces[1], faces[2], faces[3], faces[4], faces[5]));
 }
 
+/* ---- an OBJ/MTL file written on the fly and imported: exercises importIntoScene() (import.hpp) ---- */
+
+inline void buildImported(Scene& scene)
+{
+    /* every number below is exactly representable, so that two OBJ readers agree on every bit */
+    char dirTemplate[] = "/tmp/wpt_import_XXXXXX";
+    const char* dir = mkdtemp(dirTemplate);
+    if (!dir)
+        return;
+    const std::string base(dir);
+    {
+        /* a 4x4 rgb texture in the PPM format the libtgd stand-in reads */
+        FILE* f = std::fopen((base + "/checks.ppm").c_str(), "wb");
+        std::fprintf(f, "P6\n4 4\n255\n");
+        for (int i = 0; i < 16; i++) {
+            unsigned char px[3] = { (unsigned char)((i % 2) ? 224 : 64), (unsigned char)((i / 4) % 2 ? 192 : 96), 128 };
+            std::fwrite(px, 1, 3, f);
+        }
+        std::fclose(f);
+    }
+    {
+        FILE* f = std::fopen((base + "/room.mtl").c_str(), "w");
+        std::fputs(
+            "newmtl floor\nKd 0.5 0.5 0.5\n\n"
+            "newmtl painted\nKd 0.75 0.25 0.25\nKs 0.125 0.125 0.125\nNs 32\nmap_Kd -s 2 2 1 checks.ppm\n\n"
+            "newmtl lamp\nKd 0 0 0\nKe 8 8 6\n\n"
+            "newmtl pane\nKd 0.5 0.75 0.5\nd 0.25\nNi 1.5\n", f);
+        std::fclose(f);
+    }
+    {
+        FILE* f = std::fopen((base + "/room.obj").c_str(), "w");
+        std::fputs(
+            "mtllib room.mtl\n"
+            "v -2 0 -2\nv 2 0 -2\nv 2 0 2\nv -2 0 2\n"                 /* 1-4 floor */
+            "v -1 0 -1\nv 0 0 -1\nv 0 1 -1\nv -1 1 -1\n"                /* 5-8 box front (quad) */
+            "v -1 0 -1.5\nv 0 0 -1.5\nv 0 1 -1.5\nv -1 1 -1.5\n"        /* 9-12 box back */
+            "v -0.5 2.5 -0.5\nv 0.5 2.5 -0.5\nv 0.5 2.5 0.5\nv -0.5 2.5 0.5\n"  /* 13-16 lamp */
+            "v 0.5 0 0.5\nv 1.5 0 0.5\nv 1 1.5 0.5\n"                    /* 17-19 pane */
+            "v 1.25 0 -0.75\nv 1.75 0 -0.75\nv 1.5 0.5 -0.75\n"          /* 20-22 loose triangle, no material */
+            "vn 0 1 0\nvn 0 0 1\nvn 0 -2 0\n"
+            "vt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\n"
+            "o floor\nusemtl floor\nf 1//1 4//1 3//1 2//1\n"
+            "o box\nusemtl painted\nf 5/1/2 6/2/2 7/3/2 8/4/2\nf 6/1 10/2 11/3 7/4\nf -12/1 -14/2 -13/3\n"
+            "g lamp\nusemtl lamp\nf 13//3 14//3 15//3 16//3\n"
+            "g pane\nusemtl pane\nf 17 18 19\n"
+            "usemtl nosuchmaterial\nf 20 21 22\n", f);
+        std::fclose(f);
+    }
+    /* the reference imports materials in an OpenMP loop and takes the meshes in completion order: one thread
+     * makes that order the file's order (this header is compiled against the reference as well) */
+#ifdef _OPENMP
+    const int threadsBefore = omp_get_max_threads();
+    omp_set_num_threads(1);
+#endif
+    importIntoScene(scene, base + "/room.obj", Transformation(vec3(0.0f, 0.0f, -0.5f)));
+#ifdef _OPENMP
+    omp_set_num_threads(threadsBefore);
+#endif
+    std::remove((base + "/room.obj").c_str());
+    std::remove((base + "/room.mtl").c_str());
+    std::remove((base + "/checks.ppm").c_str());
+    rmdir(dir);
+}
+
 /* ---- registry ---- */
 
 struct View {
@@ -493,6 +564,7 @@ inline bool buildScene(const std::string& name, Scene& scene, float scale = 1.0f
     else if (name == "mis") buildMis(scene, true);
     else if (name == "mis_nohot") buildMis(scene, false);
     else if (name == "mixed") buildMixed(scene);
+    else if (name == "imported") buildImported(scene);
     else return false;
     return true;
 }
@@ -536,6 +608,10 @@ inline View defaultView(const std::string& name)
         v.width = 960; v.height = 540; v.samplesSqrt = 10;
         v.vfovDegrees = 50.0f;
         v.pose = Transformation(vec3(0.0f, -4.5f, -1.2f));
+    } else if (name == "imported") {
+        v.width = 320; v.height = 240; v.samplesSqrt = 8;
+        v.vfovDegrees = 50.0f;
+        v.pose = Transformation::fromLookAt(vec3(0.0f, 1.5f, 4.5f), vec3(0.0f, 0.8f, -1.0f));
     } else if (name == "mixed") {
         v.width = 480; v.height = 320; v.samplesSqrt = 8;
         v.vfovDegrees = 55.0f;
