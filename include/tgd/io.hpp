@@ -7,10 +7,11 @@
  * No image codec libraries exist in this environment, so files are written as
  *   *.pfm            portable float map (1 or 3 float32 components)
  *   *.ppm / *.pgm / *.pnm   binary netpbm (3 or 1 uint8 components)
+ *   *.png            PNG, 8 bit, 1 to 4 components (png.hpp: valid but uncompressed)
  *   anything else    "WPTARRAY" container: one text header line
  *                    "WPTARRAY <type> <components> <ndims> <dim0> <dim1> ...\n"
  *                    followed by the raw little-endian data (readable with numpy).
- * load() understands exactly these three.
+ * load() understands these four; PNG files may come from anywhere (non-interlaced, 8 or 16 bit).
  */
 #pragma once
 
@@ -18,6 +19,7 @@
 #include <string>
 
 #include "array.hpp"
+#include "png.hpp"
 
 namespace TGD {
 
@@ -101,6 +103,9 @@ inline Error save(const ArrayContainer& array, const std::string& fileName, bool
         const unsigned char* base = static_cast<const unsigned char*>(array.data());
         for (size_t y = array.dimension(1); y > 0 && ok; y--)
             ok = std::fwrite(base + (y - 1) * rowSize, 1, rowSize, f) == rowSize;
+    } else if (detail::endsWith(fileName, ".png") && twoD && array.componentType() == uint8
+            && array.componentCount() >= 1 && array.componentCount() <= 4) {
+        ok = png::write(f, array);
     } else {
         std::fprintf(f, "WPTARRAY %s %zu %zu", detail::typeName(array.componentType()),
                 array.componentCount(), array.dimensionCount());
@@ -122,7 +127,18 @@ inline ArrayContainer load(const std::string& fileName, const TagList& /* hints 
         e = ErrorSysErrno;
     } else {
         char magic[16] = { 0 };
-        if (std::fscanf(f, "%15s", magic) != 1) {
+        unsigned char first = 0;
+        if (std::fread(&first, 1, 1, f) == 1 && first == 0x89) {
+            /* PNG: read the whole file */
+            std::vector<unsigned char> bytes(1, first);
+            unsigned char buffer[65536];
+            size_t n;
+            while ((n = std::fread(buffer, 1, sizeof(buffer), f)) > 0)
+                bytes.insert(bytes.end(), buffer, buffer + n);
+            result = png::read(bytes);
+            if (result.elementCount() == 0)
+                e = ErrorFeaturesUnsupported;
+        } else if (std::fseek(f, 0, SEEK_SET) != 0 || std::fscanf(f, "%15s", magic) != 1) {
             e = ErrorInvalidData;
         } else if (std::string(magic) == "WPTARRAY") {
             char tname[16] = { 0 };

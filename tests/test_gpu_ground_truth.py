@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from wurblpt_b200 import abi
-from util import GOLDEN, Golden, read_wptarray
+from util import GOLDEN, Golden, read_png, read_wptarray
 
 pytestmark = pytest.mark.gpu
 
@@ -175,7 +175,7 @@ def test_reference_noise_textures_app_runs_unchanged(gpu, tmp_path):
         pytest.skip("apps/_bin/wurblpt-noise-textures not built")
     r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=200)
     assert r.returncode == 0, r.stderr[-3000:]
-    images = [read_wptarray(str(tmp_path / ("noise-example-%d.png" % t))) for t in range(10)]
+    images = [read_png(str(tmp_path / ("noise-example-%d.png" % t))) for t in range(10)]
     assert all(im.shape == (600, 800, 3) and im.dtype == np.uint8 for im in images)
     assert all(im.std() > 3 for im in images)
     # the textures are functions of time: consecutive renders differ by more than Monte-Carlo noise

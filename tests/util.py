@@ -77,12 +77,38 @@ def compare_hits(ids, dist, ref_ids, ref_dist):
     return dict(total=int(ids.size), same=same, ties=ties, near=near, wrong=wrong, dist_bit_equal=bit_equal_dist)
 
 
+def read_png(path):
+    """Reader for 8-bit non-interlaced PNG files with filter type 0 rows, which is what the libtgd stand-in writes
+    (include/tgd/png.hpp). Returns (height, width, components) uint8 with row 0 = BOTTOM row, like every other
+    array the stand-in stores."""
+    import struct
+    import zlib
+    with open(path, "rb") as f:
+        data = f.read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n", "not a PNG file"
+    pos, idat, header = 8, b"", None
+    while pos < len(data):
+        n = struct.unpack(">I", data[pos:pos + 4])[0]
+        kind = data[pos + 4:pos + 8]
+        if kind == b"IHDR":
+            header = struct.unpack(">IIBBBBB", data[pos + 8:pos + 8 + 13])
+        elif kind == b"IDAT":
+            idat += data[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    w, h, depth, colour, _, _, interlace = header
+    comps = {0: 1, 2: 3, 4: 2, 6: 4}[colour]
+    assert depth == 8 and interlace == 0
+    rows = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + w * comps)
+    assert (rows[:, 0] == 0).all(), "only filter type 0 is handled here"
+    return rows[::-1, 1:].reshape(h, w, comps).copy()
+
+
 def read_wptarray(path):
     """Reader for the container the libtgd stand-in writes (include/tgd/io.hpp)."""
     with open(path, "rb") as f:
         header = f.readline().decode().split()
         assert header[0] == "WPTARRAY"
-        dtype = {"float32": np.float32, "uint8": np.uint8}[header[1]]
+        dtype = {"float32": np.float32, "uint8": np.uint8, "uint16": np.uint16, "int32": np.int32}[header[1]]
         comps, ndims = int(header[2]), int(header[3])
         dims = [int(x) for x in header[4:4 + ndims]]
         data = np.frombuffer(f.read(), dtype=dtype)
