@@ -311,7 +311,9 @@ typedef struct wpt_params {
 
 enum {
     WPT_TRAVERSAL_WIDE      = 0,    /* 4-wide BVH, near-to-far ordered (default) */
-    WPT_TRAVERSAL_REFERENCE = 1     /* binary BVH walked in the reference's storage order (bvh.hpp:277-311) */
+    WPT_TRAVERSAL_REFERENCE = 1,    /* binary BVH walked in the reference's storage order (bvh.hpp:277-311) */
+    WPT_TRAVERSAL_POOL      = 2     /* queries only: the 4-wide walk as the wavefront pipeline's pooled trace kernel runs it
+                                       (scenes without media and animated hitables); renders treat it like WIDE */
 };
 
 enum {

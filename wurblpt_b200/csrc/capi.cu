@@ -123,9 +123,9 @@ struct wpt_scene {
     DeviceBuf animations, keyframes, envM, envMs, envMcs, envGuide;
     int envGuideBits = 0;
     /* per updateBVH */
-    DeviceBuf node4, bnode, tri, triShade, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs;
+    DeviceBuf node4, bnode, tri, triShade, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs, triClass, sphClass, medClass;
     /* per call scratch */
-    DeviceBuf counters, camKeys, frame, partials, wave[17], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds, animTable;
+    DeviceBuf counters, camKeys, frame, partials, wave[17], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds, animTable, poolSpill;
     cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaStream_t stream2 = nullptr;
     unsigned long long* hostDone = nullptr;     /* pinned, 2 counters */
@@ -146,7 +146,7 @@ struct wpt_scene {
     {
         const DeviceBuf* all[] = { &materials, &instances, &meshes, &vertices, &indices, &textures, &texels,
             &animations, &keyframes, &envM, &envMs, &envMcs, &envGuide, &node4, &bnode, &tri, &triShade, &sph, &med,
-            &triGlobal, &sphGlobal, &medGlobal, &hotRefs };
+            &triGlobal, &sphGlobal, &medGlobal, &hotRefs, &triClass, &sphClass, &medClass };
         uint64_t n = 0;
         for (const DeviceBuf* b : all)
             n += b->capacity;
@@ -263,6 +263,11 @@ void refreshDeviceScene(wpt_scene* s)
     d.sphGlobal = s->sphGlobal.as<uint32_t>();
     d.medGlobal = s->medGlobal.as<uint32_t>();
     d.hotRefs = s->hotRefs.as<uint32_t>();
+    d.triClass = s->triClass.as<uint8_t>();
+    d.sphClass = s->sphClass.as<uint8_t>();
+    d.medClass = s->medClass.as<uint8_t>();
+    d.classMask = h.classMask;
+    d.simpleWalk = (s->sceneHasMedia || s->sceneHasAnimation) ? 0 : 1;
     d.materials = s->materials.as<wpt_material>();
     d.instances = s->instances.as<wpt_instance>();
     d.meshes = s->meshes.as<wpt_mesh>();
@@ -388,6 +393,19 @@ int launchScene(wpt_scene* s, float t0, float t1, cudaStream_t stream, wptd::DSc
     if (n > size_t(wptd::MAX_CACHED_ANIMATIONS))
         return fail(WPT_E_UNSUPPORTED, "more than " + std::to_string(wptd::MAX_CACHED_ANIMATIONS)
                 + " scene animations are only supported for t0 == t1 (no motion blur)");
+    return WPT_OK;
+}
+
+/* Spill area of the pooled trace kernel: stack entries beyond those held in shared memory, for every pool entry
+ * of every resident block of two concurrent launches. The walk's stack never holds more than 3 * depth + 1 entries. */
+int reservePoolSpill(wpt_scene* s, wptd::RenderParams& P)
+{
+    const uint32_t need = 3 * s->host.wideDepth + 1;
+    const uint32_t held = wptd::poolStackEntries();
+    P.poolSpillPerRay = (need > held ? need - held : 0) + 1;
+    const size_t entries = size_t(2) * wptd::poolGridBlocks(s->numSMs) * wptd::poolRaysPerBlock() * P.poolSpillPerRay;
+    WPT_CUDA(s->poolSpill.reserve(entries * sizeof(uint2)), "allocate trace spill area");
+    P.poolSpill = static_cast<uint2*>(s->poolSpill.p);
     return WPT_OK;
 }
 
@@ -527,6 +545,9 @@ int wpt_scene_update_bvh(wpt_scene* s, float t0, float t1)
     WPT_CUDA(s->sphGlobal.upload(h.sphGlobal.data(), h.sphGlobal.size() * sizeof(uint32_t)), "upload sphere ids");
     WPT_CUDA(s->medGlobal.upload(h.medGlobal.data(), h.medGlobal.size() * sizeof(uint32_t)), "upload medium ids");
     WPT_CUDA(s->hotRefs.upload(h.hotSpotRefs.data(), h.hotSpotRefs.size() * sizeof(uint32_t)), "upload hot spots");
+    WPT_CUDA(s->triClass.upload(h.triClass.data(), h.triClass.size()), "upload triangle material classes");
+    WPT_CUDA(s->sphClass.upload(h.sphClass.data(), h.sphClass.size()), "upload sphere material classes");
+    WPT_CUDA(s->medClass.upload(h.medClass.data(), h.medClass.size()), "upload medium material classes");
     WPT_CUDA(cudaDeviceSynchronize(), "upload acceleration structure");
     refreshDeviceScene(s);
     s->uploadSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
@@ -654,10 +675,12 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
     P.invHeight = 1.0f / float(sensor->height);
     P.t0 = t0;
     P.t1 = t1;
-    P.traversal = o.traversal;
-    if (o.traversal == WPT_TRAVERSAL_WIDE && !(P.minHit > 0.0f))
+    if (o.traversal < WPT_TRAVERSAL_WIDE || o.traversal > WPT_TRAVERSAL_POOL)
+        return fail(WPT_E_INVALID, "unknown traversal");
+    P.traversal = (o.traversal == WPT_TRAVERSAL_POOL ? WPT_TRAVERSAL_WIDE : o.traversal);
+    if (P.traversal == WPT_TRAVERSAL_WIDE && !(P.minHit > 0.0f))
         P.traversal = WPT_TRAVERSAL_REFERENCE;  /* the ordered walk needs a positive lower bound */
-    if (o.traversal == WPT_TRAVERSAL_WIDE && 3 * s->host.wideDepth + 1 > uint32_t(12 + 84))
+    if (P.traversal == WPT_TRAVERSAL_WIDE && 3 * s->host.wideDepth + 1 > wptd::wideStackEntries())
         P.traversal = WPT_TRAVERSAL_REFERENCE;  /* deeper than the wide walk's stack */
 
     /* sub-streams per pixel: enough lanes to fill the GPU a few times over */
@@ -733,40 +756,48 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
             slots = P.nItems;
         P.W.nSlots = slots;
         const size_t n = slots;
-        /* wave[1], [2], [8] hold interleaved pairs (see WaveState); [3], [5], [9] are unused */
-        const size_t sizes[14] = { sizeof(int4), 2 * sizeof(uint4), 2 * sizeof(float4), 0, sizeof(uint2), 0,
-            sizeof(float4), sizeof(float4), 2 * sizeof(float4), 0, sizeof(float4), sizeof(float4), sizeof(float4), sizeof(float4) };
-        const int used = (features != 0 ? 14 : 10);
+        /* wave[1], [2], [3] hold interleaved pairs (see WaveState) */
+        enum { W_ITEM, W_PRNG_ACC, W_RAY, W_SHADOW, W_ATT, W_HIT, W_CTL, W_CODE, W_OPL, W_RAYRI, W_SHADOWRI, W_SHPRNG,
+               W_QUEUE, W_TRACEQ, W_WINDOW };
+        const size_t sizes[12] = { sizeof(int4), 2 * sizeof(uint4), 2 * sizeof(float4), 2 * sizeof(float4), sizeof(float4),
+            sizeof(uint4), sizeof(uint32_t), sizeof(uint8_t), sizeof(float4), sizeof(float4), sizeof(float4), sizeof(uint4) };
+        const int used = (features != 0 ? 12 : 8);
         for (int k = 0; k < used; k++)
-            if (sizes[k])
-                WPT_CUDA(s->wave[k].reserve(n * sizes[k]), "allocate wavefront state");
-        P.W.item = static_cast<int4*>(s->wave[0].p);
-        P.W.prng = static_cast<uint4*>(s->wave[1].p);
-        P.W.acc = static_cast<float4*>(s->wave[1].p) + 1;
-        P.W.rayO = static_cast<float4*>(s->wave[2].p);
-        P.W.rayD = static_cast<float4*>(s->wave[2].p) + 1;
-        P.W.hit = static_cast<uint2*>(s->wave[4].p);
-        P.W.att = static_cast<float4*>(s->wave[6].p);
-        P.W.nextAtt = static_cast<float4*>(s->wave[7].p);
-        P.W.nextDirHot = static_cast<float4*>(s->wave[8].p);
-        P.W.pendRad = static_cast<float4*>(s->wave[8].p) + 1;
-        P.W.opl = static_cast<float4*>(s->wave[10].p);
-        P.W.rayRi = static_cast<float4*>(s->wave[11].p);
-        P.W.nextRi = static_cast<float4*>(s->wave[12].p);
-        P.W.shadowRi = static_cast<float4*>(s->wave[13].p);
-        WPT_CUDA(s->wave[14].reserve(n * sizeof(uint32_t)), "allocate shade queues");
-        P.W.queue = static_cast<uint32_t*>(s->wave[14].p);
-        WPT_CUDA(s->wave[15].reserve(n * sizeof(uint32_t)), "allocate trace queue");
-        P.W.traceQueue = static_cast<uint32_t*>(s->wave[15].p);
+            WPT_CUDA(s->wave[k].reserve(n * sizes[k]), "allocate wavefront state");
+        P.W.item = static_cast<int4*>(s->wave[W_ITEM].p);
+        P.W.prng = static_cast<uint4*>(s->wave[W_PRNG_ACC].p);
+        P.W.acc = static_cast<float4*>(s->wave[W_PRNG_ACC].p) + 1;
+        P.W.rayO = static_cast<float4*>(s->wave[W_RAY].p);
+        P.W.rayD = static_cast<float4*>(s->wave[W_RAY].p) + 1;
+        P.W.shD = static_cast<float4*>(s->wave[W_SHADOW].p);
+        P.W.pendRad = static_cast<float4*>(s->wave[W_SHADOW].p) + 1;
+        P.W.att = static_cast<float4*>(s->wave[W_ATT].p);
+        P.W.hit = static_cast<uint4*>(s->wave[W_HIT].p);
+        P.W.ctl = static_cast<uint32_t*>(s->wave[W_CTL].p);
+        P.W.code = static_cast<uint8_t*>(s->wave[W_CODE].p);
+        P.W.opl = P.W.rayRi = P.W.shadowRi = nullptr;
+        P.W.shPrng = nullptr;
+        if (features != 0) {
+            P.W.opl = static_cast<float4*>(s->wave[W_OPL].p);
+            P.W.rayRi = static_cast<float4*>(s->wave[W_RAYRI].p);
+            P.W.shadowRi = static_cast<float4*>(s->wave[W_SHADOWRI].p);
+            P.W.shPrng = static_cast<uint4*>(s->wave[W_SHPRNG].p);
+        }
+        WPT_CUDA(s->wave[W_QUEUE].reserve(n * wptd::MAT_CLASSES * sizeof(uint32_t)), "allocate shade queues");
+        P.W.queue = static_cast<uint32_t*>(s->wave[W_QUEUE].p);
+        P.W.queueStride = slots;
+        WPT_CUDA(s->wave[W_TRACEQ].reserve(2 * n * sizeof(uint32_t)), "allocate trace queue");
+        P.W.traceQueue = static_cast<uint32_t*>(s->wave[W_TRACEQ].p);
         const size_t windows = (n + wptd::WAVE_WINDOW - 1) / wptd::WAVE_WINDOW + 2;
-        WPT_CUDA(s->wave[16].reserve(windows * sizeof(uint2)), "allocate window state");
-        WPT_CUDA(cudaMemsetAsync(s->wave[16].p, 0, windows * sizeof(uint2), stream), "clear window state");
-        P.W.window = static_cast<uint2*>(s->wave[16].p);
-        WPT_CUDA(s->wave[3].reserve(n), "allocate slot codes");
-        P.W.code = static_cast<uint8_t*>(s->wave[3].p);
+        WPT_CUDA(s->wave[W_WINDOW].reserve(windows * sizeof(uint2)), "allocate window state");
+        WPT_CUDA(cudaMemsetAsync(s->wave[W_WINDOW].p, 0, windows * sizeof(uint2), stream), "clear window state");
+        P.W.window = static_cast<uint2*>(s->wave[W_WINDOW].p);
         P.W.group = 0;
-        if (features == 0)
-            P.W.opl = P.W.rayRi = P.W.nextRi = P.W.shadowRi = nullptr;
+        if (s->d.simpleWalk) {
+            rc = reservePoolSpill(s, P);
+            if (rc != WPT_OK)
+                return rc;
+        }
     }
 
     const bool timed = (stats != nullptr) || !o.frame_on_device;
@@ -829,11 +860,18 @@ static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width,
     }
     P.t0 = P.t1 = time;
     P.minHit = minHit;
+    if (o.traversal < WPT_TRAVERSAL_WIDE || o.traversal > WPT_TRAVERSAL_POOL)
+        return fail(WPT_E_INVALID, "unknown traversal");
     P.traversal = o.traversal;
-    if (o.traversal == WPT_TRAVERSAL_WIDE && (!(minHit > 0.0f) || 3 * s->host.wideDepth + 1 > uint32_t(12 + 84)))
+    if (o.traversal != WPT_TRAVERSAL_REFERENCE && (!(minHit > 0.0f) || 3 * s->host.wideDepth + 1 > wptd::wideStackEntries()))
         P.traversal = WPT_TRAVERSAL_REFERENCE;
+    if (P.traversal == WPT_TRAVERSAL_POOL && (!s->d.simpleWalk || counters))
+        return fail(WPT_E_UNSUPPORTED, "WPT_TRAVERSAL_POOL: the pooled trace kernel serves scenes without media and animated "
+                "hitables, and does not count node visits");
     if (nRays == 0)
         return WPT_OK;
+    if (nRays >= (1ull << 31))
+        return fail(WPT_E_INVALID, "too many rays for one query call");
     const float* dO = nullptr;
     const float* dD = nullptr;
     if (!camera) {
@@ -856,8 +894,37 @@ static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width,
     rc = launchScene(s, time, time, stream, dscene);
     if (rc != WPT_OK)
         return rc;
+    const bool queryTiming = std::getenv("WPT_QUERY_TIMING") != nullptr;   /* experiment knob: kernel time to stderr */
+    if (queryTiming)
+        WPT_CUDA(cudaEventRecord(s->evStart, stream), "cudaEventRecord");
+    if (P.traversal == WPT_TRAVERSAL_POOL) {
+        /* the rays as wavefront slots: rays (wave[2]), answers (wave[5]), trace queue (wave[13]) */
+        WPT_CUDA(s->wave[2].reserve(nRays * 2 * sizeof(float4)), "allocate query slots");
+        WPT_CUDA(s->wave[5].reserve(nRays * sizeof(uint4)), "allocate query answers");
+        WPT_CUDA(s->wave[13].reserve(nRays * sizeof(uint32_t)), "allocate query queue");
+        P.W.rayO = static_cast<float4*>(s->wave[2].p);
+        P.W.rayD = static_cast<float4*>(s->wave[2].p) + 1;
+        P.W.shD = P.W.rayD;
+        P.W.hit = static_cast<uint4*>(s->wave[5].p);
+        P.W.traceQueue = static_cast<uint32_t*>(s->wave[13].p);
+        P.W.nSlots = uint32_t(nRays);
+        P.W.group = 0;
+        P.counters = static_cast<unsigned long long*>(s->counters.p);
+        rc = reservePoolSpill(s, P);
+        if (rc != WPT_OK)
+            return rc;
+        WPT_CUDA(wptd::launchPoolQuery(dscene, P, s->numSMs, dO, dD, nRays, time, static_cast<int32_t*>(s->qIds.p),
+                    static_cast<float*>(s->qDist.p), stream), "pooled query launch");
+    } else
     WPT_CUDA(wptd::launchQuery(sceneFeatures(s, false), counters != nullptr, dscene, P, dO, dD, nRays, time,
                 static_cast<int32_t*>(s->qIds.p), static_cast<float*>(s->qDist.p), dStats, stream), "query kernel launch");
+    if (queryTiming) {
+        WPT_CUDA(cudaEventRecord(s->evStop, stream), "cudaEventRecord");
+        WPT_CUDA(cudaEventSynchronize(s->evStop), "query kernel");
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, s->evStart, s->evStop);
+        std::fprintf(stderr, "wpt query: %llu rays in %.3f ms (%.1f Mrays/s)\n", (unsigned long long)nRays, ms, double(nRays) / ms / 1e3);
+    }
     WPT_CUDA(cudaMemcpyAsync(ids, s->qIds.p, nRays * sizeof(int32_t), cudaMemcpyDeviceToHost, stream), "copy ids");
     WPT_CUDA(cudaMemcpyAsync(a, s->qDist.p, nRays * sizeof(float), cudaMemcpyDeviceToHost, stream), "copy distances");
     wptd::TraceStats hs = { 0, 0, 0 };
@@ -912,8 +979,8 @@ int wpt_get_ground_truth(wpt_scene* s, const wpt_camera_desc* camera, uint32_t w
         return rc;
     P.t0 = P.t1 = t0;
     P.minHit = minHitDistance;
-    P.traversal = o.traversal;
-    if (o.traversal == WPT_TRAVERSAL_WIDE && (!(minHitDistance > 0.0f) || 3 * s->host.wideDepth + 1 > uint32_t(12 + 84)))
+    P.traversal = (o.traversal == WPT_TRAVERSAL_REFERENCE ? WPT_TRAVERSAL_REFERENCE : WPT_TRAVERSAL_WIDE);
+    if (P.traversal == WPT_TRAVERSAL_WIDE && (!(minHitDistance > 0.0f) || 3 * s->host.wideDepth + 1 > wptd::wideStackEntries()))
         P.traversal = WPT_TRAVERSAL_REFERENCE;
 
     wptd::GroundTruthParams G;

@@ -54,6 +54,9 @@ struct DScene {
     const uint32_t* sphGlobal;
     const uint32_t* medGlobal;
     const uint32_t* hotRefs;
+    const uint8_t* triClass;    /* material class (MC_*) of the hitable in each triangle / sphere / medium slot */
+    const uint8_t* sphClass;
+    const uint8_t* medClass;
     const wpt_material* materials;
     const wpt_instance* instances;
     const wpt_mesh* meshes;
@@ -73,6 +76,8 @@ struct DScene {
     int32_t envGuideBits;       /* 0: no guide table */
     int32_t root4;              /* encoded child of the 4-wide tree */
     int32_t prefetchLeaves;     /* triangle data is larger than an SM's L1: ask for a leaf's triangles on arrival */
+    uint32_t classMask;         /* bit c: some hitable of the scene has material class c */
+    int32_t simpleWalk;         /* no media, no animated hitables: a walk needs no Prng and no animation cache */
     uint32_t nHot;
     uint32_t nAnimations;
     int32_t envType, envCompat, envN;
@@ -83,29 +88,42 @@ constexpr int MAX_CACHED_ANIMATIONS = 16;   /* per-thread animation cache entrie
 
 /* Wavefront slot arrays (structure of arrays). The kernels reach the slots through queues, i.e. in
  * scattered order, so fields that are always used together are interleaved in pairs that fill one
- * 32-byte sector: (rayO, rayD), (prng, acc), (nextDirHot, pendRad) are indexed [2 * slot]; the second
- * pointer of a pair is the first plus one element. The other arrays are indexed [slot]. */
+ * 32-byte sector: (prng, acc), (rayO, rayD), (shD, pendRad) are indexed [2 * slot]; the second
+ * pointer of a pair is the first plus one element. The other arrays are indexed [slot].
+ *
+ * A slot has up to TWO closest-hit queries pending per round, both leaving the same point rayO:
+ *   B  the camera ray / the next path segment (direction rayD), state ST_MAIN
+ *   S  the shadow ray of the next-event estimation set up at the same path vertex (direction shD)
+ * so a path vertex costs one round (trace both, shade) instead of two. */
 struct WaveState {
-    int4* item;         /* pixel, sampleIndex, state | sub << 8 (all ones = idle), pathComponent */
-    uint4* prng;        /* xoshiro128+ state of the item's stream */
-    float4* rayO;       /* pending query: origin xyz, time */
-    float4* rayD;       /* pending query: direction xyz; .w = geometric path length so far */
-    uint2* hit;         /* answer of the trace kernel: distance bits, leaf reference */
+    int4* item;         /* pixel, sampleIndex, sub-stream, - : only the generate kernel touches it */
+    uint32_t* ctl;      /* state (bits 0-2) | kind of the pending shadow query (bits 3-4) | path component << 8 */
     uint8_t* code;      /* what the window-scanning kernels need of a slot in one byte (slotCode()) */
+    uint4* prng;        /* xoshiro128+ state of the item's stream */
     float4* acc;        /* sample accumulator of the item */
-    float4* att;        /* path attenuation */
-    float4* nextAtt;    /* across a shadow query: attenuation of the next segment */
-    float4* nextDirHot; /* across a shadow query: next direction xyz, chosen hot spot reference */
-    float4* pendRad;    /* across a shadow query: light sample to add if visible */
-    float4* opl; float4* rayRi; float4* nextRi; float4* shadowRi;  /* F_OPL only */
-    uint32_t* queue;    /* filled by the sort kernel: the slots whose surface hit is to be shaded (material queue) */
-    uint32_t* traceQueue;   /* nSlots entries filled by the generate kernel: slots with a new camera ray from the
-                               front, slots with a bounce or shadow ray from the back */
+    float4* rayO;       /* origin xyz of the pending queries, time */
+    float4* rayD;       /* query B: direction xyz; .w = geometric path length so far */
+    float4* shD;        /* query S: direction xyz; .w = the chosen hot spot's leaf reference */
+    float4* pendRad;    /* query S: light sample to add if visible */
+    float4* att;        /* path attenuation of the segment B */
+    uint4* hit;         /* answers of the trace kernel: (distance bits, leaf reference) of B, then of S */
+    float4* opl; float4* rayRi; float4* shadowRi;  /* F_OPL only: optical path length, refractive index of B and of S */
+    uint4* shPrng;      /* F_MEDIA only: the stream the walk of query S draws its free-flight samples from */
+    uint32_t* queue;    /* filled by the sort kernel: per material class, the slots whose surface hit is to be shaded;
+                           class c starts at c * queueStride */
+    uint32_t* traceQueue;   /* 2 * nSlots entries (slot << 1 | query) filled by the generate kernel: camera rays
+                               from the front, bounce and shadow rays from the back */
     uint2* window;      /* per window of WAVE_WINDOW slots: the block of work items it hands out (next, end) */
     uint32_t nSlots;
     uint32_t group;     /* slot group (0 or 1): selects the group's trace ticket / queue length counters */
+    uint32_t queueStride;
 };
 constexpr uint32_t WAVE_WINDOW = 256;       /* slots per window = work items per block */
+
+/* Material classes of the shading queues: a class has a kernel of its own in which the material type is a
+ * compile-time constant. Everything else (lights, mirrors, phase functions, two-sided materials whose sides differ)
+ * is shaded by the generic kernel. */
+enum : int { MC_GENERIC = 0, MC_LAMBERTIAN = 1, MC_GGX = 2, MC_GLASS = 3, MC_MODPHONG = 4, MAT_CLASSES = 5 };
 
 /* Counter words (64 bit). Every hot counter has a 128-byte line of its own so that atomics on different
  * counters do not meet in one L2 sector. */
@@ -115,11 +133,11 @@ enum : int {
     CTR_RAYS = 32,          /* closest-hit queries */
     CTR_NESTED = 48,        /* nested medium boundary queries */
     CTR_DONE = 64,          /* wavefront slots that found no item left */
-    CTR_TICKET = 80,        /* + 16 * group: slot ticket of the persistent trace kernel */
-    CTR_MATERIAL = 112,     /* + 16 * group: material queue length */
-    CTR_TRACE_CAMERA = 176, /* + 16 * group: trace queue, camera rays */
-    CTR_TRACE_OTHER = 208,  /* + 16 * group: trace queue, bounce and shadow rays */
-    CTR_WORDS = 240
+    CTR_TICKET = 80,        /* + 16 * group: queue ticket of the persistent trace kernel */
+    CTR_TRACE_CAMERA = 112, /* + 16 * group: trace queue, camera rays */
+    CTR_TRACE_OTHER = 144,  /* + 16 * group: trace queue, bounce and shadow rays */
+    CTR_MATERIAL = 176,     /* + 16 * (group * MAT_CLASSES + class): material queue lengths */
+    CTR_WORDS = 176 + 16 * 2 * MAT_CLASSES
 };
 
 struct RenderParams {
@@ -158,6 +176,8 @@ struct RenderParams {
     float* partials;                /* [pixel][sub-stream][3] partial sums when substreams > 1 */
     unsigned long long* counters;   /* CTR_WORDS words, see CTR_* */
     WaveState W;
+    uint2* poolSpill;               /* pooled trace kernel: stack entries beyond POOL_STACK, per pool entry (2 groups) */
+    uint32_t poolSpillPerRay;
     int32_t traversal;
 };
 

@@ -159,7 +159,7 @@ WPT_DEV float4 imageTexel(const DScene& S, const DTexture& t, uint32_t x, uint32
     return __ldg(S.texels + t.texelBase + size_t(y) * t.width + x);
 }
 
-__device__ __noinline__ float4 textureValue(const DScene& S, int32_t index, float2 uv)
+static __device__ __noinline__ float4 textureValue(const DScene& S, int32_t index, float2 uv)
 {
     /* unwind TextureTransformer chains (texture.hpp:207-246) iteratively */
     float4 factors[4], offsets[4];
@@ -360,14 +360,16 @@ WPT_DEV float phongPdf(float3 n, float3 v, float3 l, float s, float cosTheta, fl
     return rmix(diffusePdf, specularPdf, specProb);
 }
 
-/* Material::scatter of the resolved material */
-__device__ __noinline__ ScatterRec materialScatter(const DScene& S, const wpt_material* m, const Ray& ray, float4 rayRi,
+/* Material::scatter of the resolved material. MT >= 0: the material's type is known at compile time (the
+ * shading queues are sorted by material class, device_scene.cuh MC_*), the switch collapses to one case. */
+template<int MT>
+WPT_DEV ScatterRec materialScatterT(const DScene& S, const wpt_material* m, const Ray& ray, float4 rayRi,
         const HitRec& hr, Prng& prng)
 {
     if (!m)
         return scatterNone();
     ScatterRec sr;
-    switch (m->type) {
+    switch (MT >= 0 ? MT : m->type) {
     case WPT_MAT_LAMBERTIAN: {      /* material_lambertian.hpp:61-84 */
         if (hr.backside)
             return scatterNone();
@@ -541,9 +543,16 @@ __device__ __noinline__ ScatterRec materialScatter(const DScene& S, const wpt_ma
     }
 }
 
+static __device__ __noinline__ ScatterRec materialScatter(const DScene& S, const wpt_material* m, const Ray& ray, float4 rayRi,
+        const HitRec& hr, Prng& prng)
+{
+    return materialScatterT<-1>(S, m, ray, rayRi, hr, prng);
+}
+
 /* Material::scatterToDirection of the resolved material. Only materials that return
  * ScatterRandom from scatter() are ever asked. */
-__device__ __noinline__ ScatterRec materialScatterToDirection(const DScene& S, const wpt_material* m, const Ray& ray,
+template<int MT>
+WPT_DEV ScatterRec materialScatterToDirectionT(const DScene& S, const wpt_material* m, const Ray& ray,
         float4 rayRi, const HitRec& hr, float3 direction)
 {
     ScatterRec sr;
@@ -554,7 +563,7 @@ __device__ __noinline__ ScatterRec materialScatterToDirection(const DScene& S, c
     sr.ri = rayRi;
     if (!m)
         return scatterNone();
-    switch (m->type) {
+    switch (MT >= 0 ? MT : m->type) {
     case WPT_MAT_LAMBERTIAN: {      /* material_lambertian.hpp:86-102 */
         const float cosTheta = dot(normalAt(S, m, hr), direction);
         if (cosTheta > 0.0f) {
@@ -601,6 +610,12 @@ __device__ __noinline__ ScatterRec materialScatterToDirection(const DScene& S, c
     default:                        /* Material::scatterToDirection (material.hpp:177-183) */
         return scatterNone();
     }
+}
+
+static __device__ __noinline__ ScatterRec materialScatterToDirection(const DScene& S, const wpt_material* m, const Ray& ray,
+        float4 rayRi, const HitRec& hr, float3 direction)
+{
+    return materialScatterToDirectionT<-1>(S, m, ray, rayRi, hr, direction);
 }
 
 /* Material::emitted of the resolved material */
@@ -695,7 +710,7 @@ WPT_DEV float3 envDirectionFromSquare(float2 uv)
 }
 
 /* EnvironmentMapEquiRect::L (envmap.hpp:231-247) / EnvironmentMapCube::L (:264-285) */
-__device__ __noinline__ float4 envRadiance(const DScene& S, float3 direction)
+static __device__ __noinline__ float4 envRadiance(const DScene& S, float3 direction)
 {
     if (S.envType == WPT_ENV_EQUIRECT) {
         float y = asinf(rclamp(direction.y, -1.0f, 1.0f));
@@ -920,7 +935,7 @@ WPT_DEV void lensDistort(const RenderParams& P, float& p, float& q)
 }
 
 /* LensDistortion::undistort (optics.hpp:249-309) */
-__device__ __noinline__ void lensUndistort(const RenderParams& P, float& p, float& q)
+static __device__ __noinline__ void lensUndistort(const RenderParams& P, float& p, float& q)
 {
     if (P.distortionType == WPT_DISTORTION_RADIAL_AND_PLANAR) {
         const float s = (p - P.distCenter.x) * P.distInvFocal.x;

@@ -114,7 +114,7 @@ WPT_DEV Trs keyframeTrs(const wpt_keyframe& k)
     return T;
 }
 
-__device__ __noinline__ Trs keyframesAt(const wpt_keyframe* kf, uint32_t count, float t)
+static __device__ __noinline__ Trs keyframesAt(const wpt_keyframe* kf, uint32_t count, float t)
 {
     if (count == 0) {
         Trs T;
@@ -477,7 +477,7 @@ __device__ Hit traverseReference(const DScene& S, uint32_t root, const Ray& ray,
 /* ------------------------------------------------------------ 4-wide walk */
 
 #ifndef WPT_SHARED_STACK_PTX
-#define WPT_SHARED_STACK_PTX 0      /* experiment: ld.shared / st.shared instead of generic accesses (same frame, +0.5 % on C3) */
+#define WPT_SHARED_STACK_PTX 1      /* ld.shared / st.shared instead of generic accesses (same frame, +1 % on C3) */
 #endif
 
 struct WideStack {
@@ -555,6 +555,66 @@ WPT_DEV uint32_t childKey(float lox, float hix, float loy, float hiy, float loz,
     return tmin <= tmax ? ((__float_as_uint(tmin) & ~3u) | k) : 0xFFFFFFFFu;
 }
 
+#ifndef WPT_OCTANT_ROWS
+#define WPT_OCTANT_ROWS 1   /* (+3.5 % on C3) pick each slab's near / far plane row by the sign of the ray direction (no min/max per plane) */
+#endif
+
+/* Slab test of one child when the near and the far plane of every axis are already known (picked by the sign of
+ * the ray direction): the products are the very (plane - o) * inv of AABB::mayHit (aabb.hpp:70-86), min(t0, t1) is
+ * the near plane's and max(t0, t1) the far plane's because rounding is monotonic. NaNs drop out of fmaxf / fminf. */
+WPT_DEV uint32_t childKeyNearFar(float nx, float fx, float ny, float fy, float nz, float fz,
+        float3 o, float3 inv, float amin, float amax, uint32_t k)
+{
+    const float tnx = (nx - o.x) * inv.x, tfx = (fx - o.x) * inv.x;
+    const float tny = (ny - o.y) * inv.y, tfy = (fy - o.y) * inv.y;
+    const float tnz = (nz - o.z) * inv.z, tfz = (fz - o.z) * inv.z;
+    const float tmin = fmaxf(fmaxf(amin, tnx), fmaxf(tny, tnz));
+    const float tmax = fminf(fminf(amax, tfx), fminf(tfy, tfz));
+    return tmin <= tmax ? ((__float_as_uint(tmin) & ~3u) | k) : 0xFFFFFFFFu;
+}
+
+/* The four child keys of a wide node, sorted ascending (nearest entry distance first; 0xFFFFFFFF = missed). */
+struct NodeKeys {
+    uint32_t k0, k1, k2, k3;
+    int4 ch;
+};
+
+WPT_DEV NodeKeys nodeKeys(const DScene& S, int32_t cur, float3 o, float3 inv, float amin, float amax, uint32_t rows)
+{
+    NodeKeys r;
+    const float4* n = S.node4 + size_t(cur) * 8;
+#if WPT_OCTANT_ROWS
+    /* rows: bit 0/1/2 set = direction x/y/z negative: the near plane is the hi row */
+    const uint32_t sx = rows & 1u, sy = (rows >> 1) & 1u, sz = (rows >> 2) & 1u;
+    const float4 nx = __ldg(n + sx), fx = __ldg(n + (1u - sx));
+    const float4 ny = __ldg(n + 2u + sy), fy = __ldg(n + (3u - sy));
+    const float4 nz = __ldg(n + 4u + sz), fz = __ldg(n + (5u - sz));
+    r.ch = __ldg(reinterpret_cast<const int4*>(n + 6));
+    r.k0 = childKeyNearFar(nx.x, fx.x, ny.x, fy.x, nz.x, fz.x, o, inv, amin, amax, 0);
+    r.k1 = childKeyNearFar(nx.y, fx.y, ny.y, fy.y, nz.y, fz.y, o, inv, amin, amax, 1);
+    r.k2 = childKeyNearFar(nx.z, fx.z, ny.z, fy.z, nz.z, fz.z, o, inv, amin, amax, 2);
+    r.k3 = childKeyNearFar(nx.w, fx.w, ny.w, fy.w, nz.w, fz.w, o, inv, amin, amax, 3);
+#else
+    const float4 lox = __ldg(n + 0), hix = __ldg(n + 1);
+    const float4 loy = __ldg(n + 2), hiy = __ldg(n + 3);
+    const float4 loz = __ldg(n + 4), hiz = __ldg(n + 5);
+    r.ch = __ldg(reinterpret_cast<const int4*>(n + 6));
+    r.k0 = childKey(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, o, inv, amin, amax, 0);
+    r.k1 = childKey(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, o, inv, amin, amax, 1);
+    r.k2 = childKey(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, o, inv, amin, amax, 2);
+    r.k3 = childKey(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, o, inv, amin, amax, 3);
+#endif
+    /* 5-comparator sorting network, ascending */
+    sort2(r.k0, r.k1); sort2(r.k2, r.k3); sort2(r.k0, r.k2); sort2(r.k1, r.k3); sort2(r.k1, r.k2);
+    return r;
+}
+
+/* bit 0/1/2: the ray direction's x/y/z is negative (sign bit; -0 counts, its inverse is -inf) */
+WPT_DEV uint32_t octantRows(float3 d)
+{
+    return (__float_as_uint(d.x) >> 31) | ((__float_as_uint(d.y) >> 31) << 1) | ((__float_as_uint(d.z) >> 31) << 2);
+}
+
 /* State of the best hit so far in the wide walk, with what the near-tie rule needs. */
 struct WideBest {
     Hit hit;
@@ -599,6 +659,27 @@ WPT_DEV void wideLeaf(const DScene& S, uint32_t ref, const Ray& ray, const RayHe
     }
 }
 
+/* One step of a leaf: tests ONE primitive of the leaf `ref` and returns what is left of the leaf (a shorter run
+ * of triangles), or NO_HIT when the leaf is done. The persistent trace kernel runs its leaf rounds with this, so
+ * that every lane of a leaf round does exactly one primitive test whatever the length of its run. */
+template<int F>
+WPT_DEV uint32_t wideLeafStep(const DScene& S, uint32_t ref, const Ray& ray, const RayHelper& h,
+        float amin, float minHit, Ctx<F>& ctx, WideBest& best)
+{
+    float a, Ts, da;
+    uint32_t tref = ref, rest = NO_HIT;
+    if ((ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE_RUN) {
+        const uint32_t first = ref & RUN_SLOT_MASK;
+        const uint32_t more = (ref >> RUN_COUNT_SHIFT) & 3u;       /* triangles after this one */
+        tref = (PRIM_TRIANGLE << REF_TYPE_SHIFT) | first;
+        if (more != 0u)
+            rest = (PRIM_TRIANGLE_RUN << REF_TYPE_SHIFT) | ((more - 1u) << RUN_COUNT_SHIFT) | (first + 1u);
+    }
+    if (leafTest<F, true>(S, tref, ray, h, amin, best.hit.a, minHit, ctx, a, Ts, da))
+        considerHit(best, tref, a, Ts, da);
+    return rest;
+}
+
 /* Asks for the triangle data of a leaf the walk has just arrived at; the lanes of the persistent trace
  * kernel then wait a few iterations for their leaf round (see there), which covers the fetch. */
 WPT_DEV void prefetchLeaf(const DScene& S, uint32_t ref)
@@ -632,30 +713,21 @@ __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
     st.stride = smStride;
     st.sp = 0;
     int32_t cur = S.root4;                  /* EMPTY_CHILD doubles as "walk finished" */
+    const uint32_t rows = octantRows(ray.d);
     for (;;) {
         while (cur >= 0 && cur != EMPTY_CHILD) {
-            const float4* n = S.node4 + size_t(cur) * 8;
-            const float4 lox = __ldg(n + 0), hix = __ldg(n + 1);
-            const float4 loy = __ldg(n + 2), hiy = __ldg(n + 3);
-            const float4 loz = __ldg(n + 4), hiz = __ldg(n + 5);
-            const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
             if (F & F_COUNT)
                 ctx.nodes++;
-            uint32_t k0 = childKey(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ray.o, h.inv, amin, best.hit.a, 0);
-            uint32_t k1 = childKey(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ray.o, h.inv, amin, best.hit.a, 1);
-            uint32_t k2 = childKey(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ray.o, h.inv, amin, best.hit.a, 2);
-            uint32_t k3 = childKey(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ray.o, h.inv, amin, best.hit.a, 3);
-            /* 5-comparator sorting network, ascending: nearest entry distance first */
-            sort2(k0, k1); sort2(k2, k3); sort2(k0, k2); sort2(k1, k3); sort2(k1, k2);
-            if (k0 != 0xFFFFFFFFu) {
+            const NodeKeys nk = nodeKeys(S, cur, ray.o, h.inv, amin, best.hit.a, rows);
+            if (nk.k0 != 0xFFFFFFFFu) {
                 /* far children go on the stack farthest first, the nearest is visited next */
-                if (k3 != 0xFFFFFFFFu)
-                    st.push(uint32_t(sel4i(ch, k3 & 3u)), __uint_as_float(k3 & ~3u));
-                if (k2 != 0xFFFFFFFFu)
-                    st.push(uint32_t(sel4i(ch, k2 & 3u)), __uint_as_float(k2 & ~3u));
-                if (k1 != 0xFFFFFFFFu)
-                    st.push(uint32_t(sel4i(ch, k1 & 3u)), __uint_as_float(k1 & ~3u));
-                cur = sel4i(ch, k0 & 3u);
+                if (nk.k3 != 0xFFFFFFFFu)
+                    st.push(uint32_t(sel4i(nk.ch, nk.k3 & 3u)), __uint_as_float(nk.k3 & ~3u));
+                if (nk.k2 != 0xFFFFFFFFu)
+                    st.push(uint32_t(sel4i(nk.ch, nk.k2 & 3u)), __uint_as_float(nk.k2 & ~3u));
+                if (nk.k1 != 0xFFFFFFFFu)
+                    st.push(uint32_t(sel4i(nk.ch, nk.k1 & 3u)), __uint_as_float(nk.k1 & ~3u));
+                cur = sel4i(nk.ch, nk.k0 & 3u);
             } else {
                 cur = popNext(st, best.hit.a);
             }

@@ -56,6 +56,9 @@ namespace wptd {
 #ifndef WPT_REFILL_MIN
 #define WPT_REFILL_MIN 12   /* idle lanes that must have gathered before the persistent trace kernel fetches new rays */
 #endif
+#ifndef WPT_LEAF_UNIT
+#define WPT_LEAF_UNIT 0     /* 1: a lane tests one primitive per leaf round instead of all primitives of its leaf (up to four); leaf lanes 7 -> 12 of 32 but node lanes 21 -> 18: -3 % on C3 */
+#endif
 #ifndef WPT_LEAF_MIN
 #define WPT_LEAF_MIN 12     /* lanes that must be at a leaf before the persistent trace kernel runs a leaf round */
 #endif
@@ -180,122 +183,144 @@ __global__ void resolveKernel(const __grid_constant__ RenderParams P)
 
 /* ------------------------------------------------------------------- wavefront */
 
-/* slot state word: item.z = state | (sub << 8); -1 (all ones) = idle */
-WPT_DEV int slotState(int word) { return word < 0 ? ST_IDLE : (word & 0xFF); }
+/* Slot control word: state in bits 0-2 (7 = idle), kind of the pending shadow query in bits 3-4, path component from bit 8. */
+WPT_DEV unsigned int makeCtl(int state, int shadow, unsigned int pathComponent)
+{
+    return (unsigned int)(state & 7) | ((unsigned int)shadow << 3) | (pathComponent << 8);
+}
+WPT_DEV int ctlState(unsigned int ctl) { return (ctl & 7u) == 7u ? ST_IDLE : int(ctl & 7u); }
+WPT_DEV int ctlShadow(unsigned int ctl) { return int((ctl >> 3) & 3u); }
+WPT_DEV unsigned int ctlPathComponent(unsigned int ctl) { return ctl >> 8; }
 
 /* One byte per slot for the kernels that scan whole windows (sort, generate): state in bits 0-2 (7 = idle),
- * bit 3 = the pending query is on the last allowed path component, bits 4-6 = min(path component, 4). */
-constexpr unsigned int CODE_IDLE = 0xFFu;
-constexpr uint32_t HIT_PENDING = 0xFFFFFFFEu;   /* W.hit[slot].y of an unanswered query (no leaf reference looks like this) */
-WPT_DEV unsigned int slotCode(const RenderParams& P, int state, unsigned int pathComponent)
+ * bit 3 = the pending query B is on the last allowed path component, bit 4 = a shadow query S is pending,
+ * bit 5 = "fresh": the queries were issued by the material kernel of this round and are not answered yet,
+ * bits 6-7 = min(path component, 3). */
+constexpr unsigned int CODE_IDLE = 0xFFu, CODE_LAST = 8u, CODE_SHADOW = 16u, CODE_FRESH = 32u;
+WPT_DEV unsigned int slotCode(const RenderParams& P, int state, int shadow, unsigned int pathComponent, bool fresh)
 {
     if (state == ST_IDLE)
         return CODE_IDLE;
-    const unsigned int last = (pathComponent + 1u < P.maxPathComponents) ? 0u : 8u;
-    return (unsigned int)state | last | (min(pathComponent, 4u) << 4);
+    const unsigned int last = (pathComponent + 1u < P.maxPathComponents) ? 0u : CODE_LAST;
+    return (unsigned int)state | last | (shadow != SHADOW_NONE ? CODE_SHADOW : 0u) | (fresh ? CODE_FRESH : 0u)
+        | (min(pathComponent, 3u) << 6);
 }
 WPT_DEV int codeState(unsigned int code) { return code == CODE_IDLE ? ST_IDLE : int(code & 7u); }
 
 /* ---- slot state in HBM <-> PathState in registers ---- */
 
+/* The work item of a slot whose path has ended (or that is idle): what the generate kernel needs to start the next
+ * sample or to finish the item. */
 template<int F>
-WPT_DEV void loadItem(const RenderParams& P, unsigned int slot, const int4 item, PathState& ps, Ctx<F>& ctx)
+WPT_DEV void loadItem(const RenderParams& P, unsigned int slot, bool idle, PathState& ps, Ctx<F>& ctx)
 {
-    ps.state = slotState(item.z);
+    ps.state = idle ? ST_IDLE : ST_NEW;
+    ps.shadow = SHADOW_NONE;
+    ps.pathComponent = 0;
+    if (idle) {
+        ps.pixel = ps.sampleIndex = ps.sub = 0;
+        return;
+    }
+    const int4 item = P.W.item[slot];
     ps.pixel = (unsigned int)item.x;
     ps.sampleIndex = (unsigned int)item.y;
-    ps.sub = (item.z < 0 ? 0u : (unsigned int)(item.z >> 8));
-    ps.pathComponent = (unsigned int)item.w;
-    if (ps.state != ST_IDLE) {
-        const uint4 r = P.W.prng[2 * slot];
-        ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
-        const float4 acc = P.W.acc[2 * slot];
-        ps.acc[0] = acc.x; ps.acc[1] = acc.y; ps.acc[2] = acc.z;
-    }
+    ps.sub = (unsigned int)item.z;
+    const uint4 r = P.W.prng[2 * slot];
+    ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
+    const float4 acc = P.W.acc[2 * slot];
+    ps.acc[0] = acc.x; ps.acc[1] = acc.y; ps.acc[2] = acc.z;
 }
 
-/* Everything a shade kernel needs of a slot with an answered query, as independent loads (none of them
- * waits for the slot's state word): SHADOW = the slot may be in a shadow-ray state. */
-template<int F, bool SHADOW>
-WPT_DEV Hit loadAnswered(const RenderParams& P, unsigned int slot, PathState& ps, Ctx<F>& ctx)
+/* Everything a shade kernel needs of a slot whose queries have been answered, as independent loads (none of them
+ * waits for the slot's control word). ITEM: the work item too (the path may end here). */
+template<int F, bool ITEM>
+WPT_DEV void loadAnswered(const RenderParams& P, unsigned int slot, PathState& ps, Ctx<F>& ctx, Hit& hitB, Hit& hitS)
 {
-    const int4 item = P.W.item[slot];
+    const unsigned int ctl = P.W.ctl[slot];
     const uint4 r = P.W.prng[2 * slot];
     const float4 acc = P.W.acc[2 * slot];
     const float4 o = P.W.rayO[2 * slot], d = P.W.rayD[2 * slot];
+    const float4 sd = P.W.shD[2 * slot], pr = P.W.pendRad[2 * slot];
     const float4 att = P.W.att[slot];
-    const uint2 hw = P.W.hit[slot];
+    const uint4 hw = P.W.hit[slot];
     if (F & F_OPL) {
         ps.opl = P.W.opl[slot];
         ps.rayRi = P.W.rayRi[slot];
+        ps.shadowRi = P.W.shadowRi[slot];
     }
-    if (SHADOW) {
-        ps.nextAtt = P.W.nextAtt[slot];
-        const float4 nd = P.W.nextDirHot[2 * slot];
-        ps.nextDir = xyz(nd);
-        ps.pendHot = __float_as_uint(nd.w);
-        ps.pendRad = P.W.pendRad[2 * slot];
-        if (F & F_OPL) {
-            ps.nextRi = P.W.nextRi[slot];
-            ps.shadowRi = P.W.shadowRi[slot];
-        }
+    if (ITEM) {
+        const int4 item = P.W.item[slot];
+        ps.pixel = (unsigned int)item.x;
+        ps.sampleIndex = (unsigned int)item.y;
+        ps.sub = (unsigned int)item.z;
     }
-    ps.state = slotState(item.z);
-    ps.pixel = (unsigned int)item.x;
-    ps.sampleIndex = (unsigned int)item.y;
-    ps.sub = (unsigned int)(item.z >> 8);
-    ps.pathComponent = (unsigned int)item.w;
+    ps.state = ctlState(ctl);
+    ps.shadow = ctlShadow(ctl);
+    ps.pathComponent = ctlPathComponent(ctl);
     ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
     ps.acc[0] = acc.x; ps.acc[1] = acc.y; ps.acc[2] = acc.z;
     ps.walkRay.o = xyz(o); ps.walkRay.time = o.w;
     ps.walkRay.d = xyz(d); ps.pathLength = d.w;
+    ps.shDir = xyz(sd); ps.pendHot = __float_as_uint(sd.w);
+    ps.pendRad = pr;
     ps.att = att;
-    Hit hit;
-    hit.a = __uint_as_float(hw.x);
-    hit.ref = hw.y;
-    return hit;
+    hitB.a = __uint_as_float(hw.x); hitB.ref = hw.y;
+    hitS.a = __uint_as_float(hw.z); hitS.ref = hw.w;
 }
 
-template<int F>
-WPT_DEV void storeSlot(const RenderParams& P, unsigned int slot, const PathState& ps, const Ctx<F>& ctx)
+/* A PathState's own stream for the walk of its shadow query (media draw free-flight samples inside the walk,
+ * hitable_medium.hpp:89, and the two walks of a slot run concurrently): two draws of the item's stream seed it. */
+WPT_DEV uint4 forkPrng(Prng& prng)
 {
-    P.W.item[slot] = make_int4(int(ps.pixel), int(ps.sampleIndex), ps.state | int(ps.sub << 8), int(ps.pathComponent));
-    P.W.code[slot] = uint8_t(slotCode(P, ps.state, ps.pathComponent));
+    const uint64_t seed = (uint64_t(prngNext(prng)) << 32) | uint64_t(prngNext(prng));
+    const uint64_t s01 = splitmix64(seed);
+    const uint64_t s23 = splitmix64(s01);
+    return make_uint4(uint32_t(s01 >> 32), uint32_t(s01), uint32_t(s23 >> 32), uint32_t(s23));
+}
+
+/* ITEM: the work item's fields may have changed (generate kernel). `fresh`: see slotCode(). */
+template<int F, bool ITEM>
+WPT_DEV void storeSlot(const RenderParams& P, unsigned int slot, PathState& ps, Ctx<F>& ctx, bool fresh)
+{
+    if (ITEM)
+        P.W.item[slot] = make_int4(int(ps.pixel), int(ps.sampleIndex), int(ps.sub), 0);
+    P.W.ctl[slot] = makeCtl(ps.state, ps.shadow, ps.pathComponent);
+    P.W.code[slot] = uint8_t(slotCode(P, ps.state, ps.shadow, ps.pathComponent, fresh));
     if (ps.state == ST_EXHAUSTED)
         return;
+    if ((F & F_MEDIA) && ps.shadow != SHADOW_NONE)
+        P.W.shPrng[slot] = forkPrng(ctx.prng);
     P.W.prng[2 * slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
     P.W.acc[2 * slot] = f4(ps.acc[0], ps.acc[1], ps.acc[2], 0.0f);
     if (ps.state == ST_NEW)
         return;     /* path ended: the generate kernel starts the next sample */
-    P.W.hit[slot] = make_uint2(0u, HIT_PENDING);    /* a new query: unanswered until the trace kernel writes here */
     P.W.rayO[2 * slot] = f4(ps.walkRay.o, ps.walkRay.time);
-    P.W.rayD[2 * slot] = f4(ps.walkRay.d, ps.pathLength);
-    P.W.att[slot] = ps.att;
-    if (F & F_OPL) {
-        P.W.opl[slot] = ps.opl;
-        P.W.rayRi[slot] = ps.rayRi;
+    if (ps.state == ST_MAIN) {
+        P.W.rayD[2 * slot] = f4(ps.walkRay.d, ps.pathLength);
+        P.W.att[slot] = ps.att;
+        if (F & F_OPL)
+            P.W.rayRi[slot] = ps.rayRi;
     }
-    if (ps.state != ST_MAIN) {
-        P.W.nextAtt[slot] = ps.nextAtt;
-        P.W.nextDirHot[2 * slot] = f4(ps.nextDir, __uint_as_float(ps.pendHot));
+    if (F & F_OPL)
+        P.W.opl[slot] = ps.opl;
+    if (ps.shadow != SHADOW_NONE) {
+        P.W.shD[2 * slot] = f4(ps.shDir, __uint_as_float(ps.pendHot));
         P.W.pendRad[2 * slot] = ps.pendRad;
-        if (F & F_OPL) {
-            P.W.nextRi[slot] = ps.nextRi;
+        if (F & F_OPL)
             P.W.shadowRi[slot] = ps.shadowRi;
-        }
     }
 }
 
 /* ---- per-group counters ---- */
 WPT_DEV unsigned long long* ctrTicket(const RenderParams& P) { return P.counters + CTR_TICKET + 16 * P.W.group; }
-WPT_DEV unsigned long long* ctrMaterial(const RenderParams& P) { return P.counters + CTR_MATERIAL + 16 * P.W.group; }
+WPT_DEV unsigned long long* ctrMaterial(const RenderParams& P, int cls) { return P.counters + CTR_MATERIAL + 16 * (P.W.group * MAT_CLASSES + cls); }
 WPT_DEV unsigned long long* ctrTraceCamera(const RenderParams& P) { return P.counters + CTR_TRACE_CAMERA + 16 * P.W.group; }
 WPT_DEV unsigned long long* ctrTraceOther(const RenderParams& P) { return P.counters + CTR_TRACE_OTHER + 16 * P.W.group; }
 
-/* Entry p of the trace queue (camera rays from the front, the others from the back). */
-WPT_DEV unsigned int traceQueueSlot(const RenderParams& P, unsigned int p, unsigned int nCamera)
+/* Entry p of the trace queue (camera rays from the front, the others from the back): slot << 1 | query (0 = B, 1 = S). */
+WPT_DEV unsigned int traceQueueEntry(const RenderParams& P, unsigned int p, unsigned int nCamera)
 {
-    return p < nCamera ? P.W.traceQueue[p] : P.W.traceQueue[P.W.nSlots - 1u - (p - nCamera)];
+    return p < nCamera ? P.W.traceQueue[p] : P.W.traceQueue[2u * P.W.nSlots - 1u - (p - nCamera)];
 }
 
 WPT_DEV void countSamples(const RenderParams& P, unsigned int newSamples)
@@ -305,29 +330,28 @@ WPT_DEV void countSamples(const RenderParams& P, unsigned int newSamples)
         atomicAdd(P.counters + CTR_SAMPLES, (unsigned long long)n);
 }
 
-/* Which kernel finishes an answered query: a camera or bounce ray that hit a surface which is still to
- * be shaded goes to waveMaterialKernel (the case in which processLogic() returns true), everything
- * else ("logic": misses, last path component, shadow-ray results) is finished by waveGenerateKernel. */
-enum { QUEUE_NONE = 0, QUEUE_MATERIAL = 1, QUEUE_LOGIC = 2 };
-WPT_DEV int queueOf(unsigned int code, uint32_t hitRef)
+/* Shading queue of a hit: the material class of the hitable (resolved on the host, scene_host.cpp). */
+WPT_DEV unsigned int hitMaterialClass(const DScene& S, uint32_t ref)
 {
-    const int state = codeState(code);
-    if (state != ST_MAIN && state != ST_SHADOW_HOT && state != ST_SHADOW_ENV)
-        return QUEUE_NONE;      /* idle or retired slot: no query was pending */
-    return (state == ST_MAIN && hitRef != NO_HIT && !(code & 8u)) ? QUEUE_MATERIAL : QUEUE_LOGIC;
+    const uint32_t type = ref >> REF_TYPE_SHIFT, slot = ref & REF_SLOT_MASK;
+    return type == PRIM_TRIANGLE ? __ldg(S.triClass + slot) : type == PRIM_SPHERE ? __ldg(S.sphClass + slot) : __ldg(S.medClass + slot);
 }
 
-/* Sort: after the trace kernel, every warp looks at a window of consecutive slots and lists the ones
- * whose camera or bounce ray hit a surface that is to be shaded (the material queue, W.queue). Entries
- * stay in slot order inside a window, so a warp of the material kernel reads near neighbours in the slot
- * arrays (whole sectors) and every one of its lanes has work. One atomic per window. Everything else
- * that was answered is left to waveGenerateKernel, which looks at every slot anyway. */
+/* Sort: after the trace kernel, every warp looks at a window of consecutive slots and lists the ones whose camera
+ * ray / path segment hit a surface that is to be shaded, one list per material class (the material queues,
+ * W.queue). Entries stay in slot order inside a window, so a warp of a material kernel reads near neighbours in the
+ * slot arrays (whole sectors), every one of its lanes has work, and all of them run the same material code.
+ * One atomic per window and class. Everything else that was answered (rays that left the scene or reached the
+ * last path component, paths that only wait for their last shadow query) is left to waveGenerateKernel, which
+ * looks at every slot anyway. */
 constexpr unsigned int SORT_WINDOW = 256;       /* slots per warp */
-constexpr unsigned int TRACE_CLASSES = 9;       /* see waveGenerateKernel */
+constexpr unsigned int TRACE_CLASSES = 8;       /* see waveGenerateKernel */
 constexpr unsigned int SORT_BLOCK = 128;
+static_assert(SORT_BLOCK == BLOCK && SORT_WINDOW == WAVE_WINDOW, "the sort and generate kernels share one launch geometry");
 
-__global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_constant__ RenderParams P)
+__global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
+    __shared__ uint8_t classOf[SORT_BLOCK / 32][SORT_WINDOW];
     __shared__ uint32_t lists[SORT_BLOCK / 32][SORT_WINDOW];
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -337,45 +361,64 @@ __global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_consta
         *ctrTraceCamera(P) = 0ull;  /* trace queue lengths: the trace kernel is done with them, the generate kernel */
         *ctrTraceOther(P) = 0ull;   /* of this round counts them up again */
     }
-    uint32_t* matList = lists[warp];
     const unsigned int windowBase = (blockIdx.x * (SORT_BLOCK / 32u) + warp) * SORT_WINDOW;
-    unsigned int nMat = 0;
+    if (windowBase >= P.W.nSlots)
+        return;
+    unsigned int present = 0;
 #pragma unroll
     for (unsigned int k = 0; k < SORT_WINDOW / 32u; k++) {
         const unsigned int slot = windowBase + k * 32u + lane;
-        int kind = QUEUE_NONE;
+        unsigned int cls = MAT_CLASSES;     /* not to be shaded */
         if (slot < P.W.nSlots) {
             const unsigned int code = P.W.code[slot];
-            if ((code & 0x0Fu) == (unsigned int)ST_MAIN)    /* a camera / bounce ray, not on the last path component */
-                kind = queueOf(code, P.W.hit[slot].y);
+            if ((code & 0x0Fu) == (unsigned int)ST_MAIN) {  /* a camera ray / path segment, not on the last path component */
+                const uint32_t ref = P.W.hit[slot].y;
+                if (ref != NO_HIT)
+                    cls = hitMaterialClass(S, ref);
+            }
         }
-        const unsigned matMask = __ballot_sync(FULL, kind == QUEUE_MATERIAL);
-        if (kind == QUEUE_MATERIAL)
-            matList[nMat + __popc(matMask & below)] = slot;
-        nMat += __popc(matMask);
+        classOf[warp][k * 32u + lane] = uint8_t(cls);
+        present |= (cls < MAT_CLASSES ? 1u << cls : 0u);
     }
+    present = __reduce_or_sync(FULL, present);
     __syncwarp();
-    unsigned int matBase = 0;
-    if (lane == 0 && nMat)
-        matBase = (unsigned int)atomicAdd(ctrMaterial(P), (unsigned long long)nMat);
-    matBase = __shfl_sync(FULL, matBase, 0);
-    for (unsigned int e = lane; e < nMat; e += 32u)
-        P.W.queue[matBase + e] = matList[e];
+    for (unsigned int c = 0; c < MAT_CLASSES; c++) {
+        if (!((present >> c) & 1u))
+            continue;
+        unsigned int n = 0;
+#pragma unroll
+        for (unsigned int k = 0; k < SORT_WINDOW / 32u; k++) {
+            const bool mine = (classOf[warp][k * 32u + lane] == c);
+            const unsigned mask = __ballot_sync(FULL, mine);
+            if (mine)
+                lists[warp][n + __popc(mask & below)] = windowBase + k * 32u + lane;
+            n += __popc(mask);
+        }
+        __syncwarp();
+        unsigned int base = 0;
+        if (lane == 0)
+            base = (unsigned int)atomicAdd(ctrMaterial(P, c), (unsigned long long)n);
+        base = __shfl_sync(FULL, base, 0);
+        uint32_t* q = P.W.queue + size_t(c) * P.W.queueStride;
+        for (unsigned int e = lane; e < n; e += 32u)
+            q[base + e] = lists[warp][e];
+        __syncwarp();
+    }
 }
 
-/* Generate: finishes the answered queries the material kernel did not take (processLogic(): rays that left
- * the scene, shadow-ray results, Russian roulette), starts the next sample (camera ray) of every slot whose path has ended, hands out work
- * items, retires slots when none are left, and lists the slots to trace. One warp per window of
- * WAVE_WINDOW consecutive slots; a window takes its work items from a block of WAVE_WINDOW consecutive
- * items at a time (MPICoordinator::getBlock, mpi.hpp:241-254, as a device atomic), so the slots of a
- * window always work on neighbouring pixels and their camera rays - listed first in the trace queue,
- * window by window - walk the tree together. */
+/* Generate: finishes the paths the material kernels did not continue (rays that left the scene or reached the last
+ * path component, the last shadow query of an ended path), starts the next sample (camera ray) of every slot whose
+ * path has ended, hands out work items, retires slots when none are left, and lists the queries to trace. One warp
+ * per window of WAVE_WINDOW consecutive slots; a window takes its work items from a block of WAVE_WINDOW
+ * consecutive items at a time (MPICoordinator::getBlock, mpi.hpp:241-254, as a device atomic), so the slots of a
+ * window always work on neighbouring pixels and their camera rays - listed first in the trace queue, window by
+ * window - walk the tree together. */
 template<int F>
 __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
-    /* per warp: the trace class of each slot of the window, then the slots listed class by class */
-    __shared__ uint8_t classOf[BLOCK / 32][WAVE_WINDOW];
-    __shared__ uint32_t lists[BLOCK / 32][WAVE_WINDOW];
+    /* per warp: the trace class of query B and of query S of each slot of the window, then the queries listed class by class */
+    __shared__ uint8_t classOf[BLOCK / 32][2 * WAVE_WINDOW];
+    __shared__ uint32_t lists[BLOCK / 32][2 * WAVE_WINDOW];
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned below = (1u << lane) - 1u;
@@ -390,28 +433,34 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
         const bool valid = slot < P.W.nSlots;
         const unsigned int code = valid ? (unsigned int)P.W.code[slot] : (unsigned int)ST_EXHAUSTED;
         int state = codeState(code);
-        unsigned int pathComponent = (code >> 4) & 7u;      /* min(path component, 4): all the class needs */
+        bool shadow = (state == ST_MAIN || state == ST_TAIL) && (code & CODE_SHADOW);
+        unsigned int pathComponent = code >> 6;     /* min(path component, 3): all the class needs */
+        const bool fresh = (state == ST_MAIN || state == ST_TAIL) && (code & CODE_FRESH);
         const bool generate = valid && (state == ST_NEW || state == ST_IDLE);
-        /* an answered query the material kernel did not take: a ray that left the scene or reached the last
-         * path component, or a shadow ray (everything processLogic() finishes on its own) */
-        bool logic = false;
-        if (state == ST_MAIN || state == ST_SHADOW_HOT || state == ST_SHADOW_ENV)
-            logic = (P.W.hit[slot].y != HIT_PENDING);
+        /* answered queries the material kernels did not take: the path ends here */
+        const bool logic = (state == ST_MAIN || state == ST_TAIL) && !fresh;
+        if (fresh)
+            P.W.code[slot] = uint8_t(code & ~CODE_FRESH);   /* answered by the next trace launch */
         if (__any_sync(FULL, generate || logic)) {
             Ctx<F> ctx;
             ctx.nested = 0;
             ctx.nodes = ctx.leaves = 0;
             PathState ps;
             ps.state = ST_EXHAUSTED;
+            ps.shadow = SHADOW_NONE;
             if (logic) {
-                const Hit hit = loadAnswered<F, true>(P, slot, ps, ctx);
+                Hit hitB, hitS;
+                loadAnswered<F, true>(P, slot, ps, ctx, hitB, hitS);
                 animationCacheInit<F>(S, ctx, ps.walkRay.time);
-                const RayHelper h = makeRayHelper(ps.walkRay);
-                processLogic<F>(S, P, ps, ctx, hit, h);
+                if (ps.shadow != SHADOW_NONE)
+                    consumeShadow<F>(S, P, ps, ctx, hitS);
+                if (ps.state == ST_MAIN)
+                    waveEndPath<F>(S, P, ps, hitB);
+                ps.state = ST_NEW;
             } else if (generate) {
-                loadItem<F>(P, slot, state == ST_IDLE ? make_int4(-1, -1, -1, -1) : P.W.item[slot], ps, ctx);
+                loadItem<F>(P, slot, state == ST_IDLE, ps, ctx);
             }
-            bool working = generate || (logic && ps.state == ST_NEW);
+            bool working = generate || logic;
             while (__any_sync(FULL, working)) {
                 if (working && ps.state == ST_NEW) {
                     if (startSample<F>(S, P, ps, ctx)) {
@@ -453,31 +502,34 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
                 }
             }
             if (generate || logic) {
-                storeSlot<F>(P, slot, ps, ctx);
+                ps.shadow = SHADOW_NONE;
+                storeSlot<F, true>(P, slot, ps, ctx, false);
                 state = ps.state;
-                pathComponent = ps.pathComponent;
+                shadow = false;
+                pathComponent = 0;
             }
         }
-        /* Trace class: rays of one class from one window (= a few neighbouring pixels) are similar rays.
-         * 0 = camera rays; 1..4 = shadow rays after path component 0, 1, 2, 3+ (same region of the scene,
-         * and most of them towards the brightest part of the environment); 5..8 = bounce rays likewise. */
-        unsigned int cls = TRACE_CLASSES;       /* nothing to trace */
+        /* Trace classes: rays of one class from one window (= a few neighbouring pixels) are similar rays.
+         * 0 = camera rays; 1..3 = shadow rays set up at path component 0, 1, 2+ (same region of the scene, and
+         * most of them towards the brightest part of the environment); 5..7 = path segments 1, 2, 3+. */
+        unsigned int clsB = TRACE_CLASSES, clsS = TRACE_CLASSES;       /* nothing to trace */
         if (state == ST_MAIN)
-            cls = (pathComponent == 0u ? 0u : 4u + min(pathComponent, 4u));
-        else if (state == ST_SHADOW_HOT || state == ST_SHADOW_ENV)
-            cls = 1u + min(pathComponent, 3u);
-        classOf[warp][k * 32u + lane] = uint8_t(cls);
+            clsB = (pathComponent == 0u ? 0u : 4u + pathComponent);
+        if (shadow)
+            clsS = max(pathComponent, 1u);     /* the slot's path component already counts the next segment */
+        classOf[warp][2u * (k * 32u + lane)] = uint8_t(clsB);
+        classOf[warp][2u * (k * 32u + lane) + 1u] = uint8_t(min(clsS, TRACE_CLASSES));
     }
     __syncwarp();
-    /* counting sort of the window's slots by class; slot order is kept inside a class */
+    /* counting sort of the window's queries by class; slot order is kept inside a class */
     unsigned int nCam = 0, nListed = 0;
     for (unsigned int c = 0; c < TRACE_CLASSES; c++) {
 #pragma unroll
-        for (unsigned int k = 0; k < WAVE_WINDOW / 32u; k++) {
+        for (unsigned int k = 0; k < 2u * WAVE_WINDOW / 32u; k++) {
             const bool mine = (classOf[warp][k * 32u + lane] == c);
             const unsigned mask = __ballot_sync(FULL, mine);
             if (mine)
-                lists[warp][nListed + __popc(mask & below)] = windowBase + k * 32u + lane;
+                lists[warp][nListed + __popc(mask & below)] = 2u * windowBase + k * 32u + lane;     /* slot << 1 | query */
             nListed += __popc(mask);
         }
         if (c == 0)
@@ -498,42 +550,53 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
     for (unsigned int e = lane; e < nCam; e += 32u)
         P.W.traceQueue[camBase + e] = lists[warp][e];
     for (unsigned int e = lane; e < nOther; e += 32u)
-        P.W.traceQueue[P.W.nSlots - 1u - (otherBase + e)] = lists[warp][nCam + e];
+        P.W.traceQueue[2u * P.W.nSlots - 1u - (otherBase + e)] = lists[warp][nCam + e];
     countSamples(P, newSamples);
     const unsigned int r = __reduce_add_sync(FULL, retired);
     if (lane == 0 && r != 0u)
         atomicAdd(P.counters + CTR_DONE, (unsigned long long)r);
 }
 
-/* Material: shade the surface hits of camera and bounce rays. One thread per entry of the material queue. */
-template<int F>
+/* Material: shade the surface hits of camera rays and path segments, one kernel per material class (MC_*; the
+ * material type is a compile-time constant in all but the generic one). A fixed grid strides over the class's queue. */
+template<int MC> struct ClassMaterialType { static constexpr int value = -1; };
+template<> struct ClassMaterialType<MC_LAMBERTIAN> { static constexpr int value = WPT_MAT_LAMBERTIAN; };
+template<> struct ClassMaterialType<MC_GGX> { static constexpr int value = WPT_MAT_GGX; };
+template<> struct ClassMaterialType<MC_GLASS> { static constexpr int value = WPT_MAT_GLASS; };
+template<> struct ClassMaterialType<MC_MODPHONG> { static constexpr int value = WPT_MAT_MODPHONG; };
+
+template<int F, int MC>
 __global__ void __launch_bounds__(BLOCK, WPT_MATERIAL_MIN_BLOCKS) waveMaterialKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
-    const unsigned int i = blockIdx.x * BLOCK + threadIdx.x;
-    const unsigned int count = (unsigned int)*ctrMaterial(P);
-    if (i < count) {
-        const unsigned int slot = P.W.queue[i];
+    const unsigned int count = (unsigned int)*ctrMaterial(P, MC);
+    const uint32_t* queue = P.W.queue + size_t(MC) * P.W.queueStride;
+    for (unsigned int i = blockIdx.x * BLOCK + threadIdx.x; i < count; i += gridDim.x * BLOCK) {
+        const unsigned int slot = queue[i];
         Ctx<F> ctx;
         ctx.nested = 0;
         ctx.nodes = ctx.leaves = 0;
         PathState ps;
-        const Hit hit = loadAnswered<F, false>(P, slot, ps, ctx);   /* material entries are camera / bounce rays */
+        Hit hitB, hitS;
+        loadAnswered<F, false>(P, slot, ps, ctx, hitB, hitS);
         animationCacheInit<F>(S, ctx, ps.walkRay.time);
+        if (ps.shadow != SHADOW_NONE)
+            consumeShadow<F>(S, P, ps, ctx, hitS);
         const RayHelper h = makeRayHelper(ps.walkRay);
-        processHit<F>(S, P, ps, ctx, hit, h);
-        storeSlot<F>(P, slot, ps, ctx);
+        waveShade<F, ClassMaterialType<MC>::value>(S, P, ps, ctx, hitB, h);
+        storeSlot<F, false>(P, slot, ps, ctx, true);
     }
 }
 
-/* Trace: the closest-hit query of every slot that has one pending. */
+/* Trace: the closest-hit query of every entry of the trace queue, one per thread (reference-order walk, and the
+ * wide walk without lane refill as an experiment). */
 template<int F>
 __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
     extern __shared__ uint2 smStackAll[];
     uint2* smStack = smStackAll + threadIdx.x;
-    const unsigned int p = blockIdx.x * BLOCK + threadIdx.x;
-    if (p == 0) {           /* queue lengths of this round (the sort kernel that follows counts them up) */
-        *ctrMaterial(P) = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  /* queue lengths of this round (the sort kernel that follows counts them up) */
+        for (int c = 0; c < MAT_CLASSES; c++)
+            *ctrMaterial(P, c) = 0ull;
     }
     const unsigned int nCamera = (unsigned int)*ctrTraceCamera(P);
     const unsigned int nQueued = nCamera + (unsigned int)*ctrTraceOther(P);
@@ -541,24 +604,23 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
     Ctx<F> ctx;
     ctx.nested = 0;
     ctx.nodes = ctx.leaves = 0;
-    if (p < nQueued) {
-        const unsigned int slot = traceQueueSlot(P, p, nCamera);
-        {
-            const float4 o = P.W.rayO[2 * slot], d = P.W.rayD[2 * slot];
-            Ray ray;
-            ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
-            if (F & F_MEDIA) {
-                const uint4 r = P.W.prng[2 * slot];
-                ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
-            }
-            animationCacheInit<F>(S, ctx, ray.time);
-            const RayHelper h = makeRayHelper(ray);
-            const Hit hit = closestHit<F>(S, P, ray, h, ctx, smStack);
-            P.W.hit[slot] = make_uint2(__float_as_uint(hit.a), hit.ref);
-            if (F & F_MEDIA)
-                P.W.prng[2 * slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
-            traced = 1;
+    for (unsigned int p = blockIdx.x * BLOCK + threadIdx.x; p < nQueued; p += gridDim.x * BLOCK) {
+        const unsigned int e = traceQueueEntry(P, p, nCamera);
+        const unsigned int slot = e >> 1, which = e & 1u;
+        const float4 o = P.W.rayO[2 * slot], d = (which ? P.W.shD[2 * slot] : P.W.rayD[2 * slot]);
+        Ray ray;
+        ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
+        if (F & F_MEDIA) {
+            const uint4 r = (which ? P.W.shPrng[slot] : P.W.prng[2 * slot]);
+            ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
         }
+        animationCacheInit<F>(S, ctx, ray.time);
+        const RayHelper h = makeRayHelper(ray);
+        const Hit hit = closestHit<F>(S, P, ray, h, ctx, smStack);
+        reinterpret_cast<uint2*>(P.W.hit)[e] = make_uint2(__float_as_uint(hit.a), hit.ref);
+        if ((F & F_MEDIA) && !which)
+            P.W.prng[2 * slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
+        traced++;
     }
     /* statistics: one atomic per warp */
     const unsigned int n = __reduce_add_sync(0xFFFFFFFFu, traced);
@@ -571,10 +633,10 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
     }
 }
 
-/* Trace, persistent form (4-wide walk only): every lane walks the tree for one slot's query and, the
- * moment its walk ends, stores the answer and takes the next slot from a ticket counter -- inside the
- * walk loop, so a lane never waits for the longest ray of its warp. One loop iteration handles one
- * inner node or one leaf. */
+/* Trace, persistent form (4-wide walk only): every lane walks the tree for one query and, the moment its walk
+ * ends, stores the answer and takes the next entry of the trace queue from a ticket counter -- inside the walk
+ * loop, so a lane never waits for the longest ray of its warp. One loop iteration handles one inner node or one
+ * primitive of a leaf. */
 template<int F>
 __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersistentKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
@@ -587,16 +649,18 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     ctx.nodes = ctx.leaves = 0;
     unsigned int traced = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {  /* queue lengths of this round (the sort kernel that follows counts them up) */
-        *ctrMaterial(P) = 0ull;
+        for (int c = 0; c < MAT_CLASSES; c++)
+            *ctrMaterial(P, c) = 0ull;
     }
 
     const unsigned int nCamera = (unsigned int)*ctrTraceCamera(P);
     const unsigned int nQueued = nCamera + (unsigned int)*ctrTraceOther(P);
-    unsigned int slot = 0;
+    unsigned int entry = 0;             /* slot << 1 | query of the walk in progress */
     bool active = false, exhausted = false;
     Ray ray;
     ray.o = f3(0.0f); ray.d = f3(0.0f, 0.0f, 1.0f); ray.time = 0.0f;
     RayHelper h = makeRayHelper(ray);
+    uint32_t rows = 0;                  /* octantRows(ray.d); only used with WPT_OCTANT_ROWS */
     WideBest best;
     best.hit.a = MAXVAL;
     best.hit.ref = NO_HIT;
@@ -617,7 +681,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     const unsigned int CHUNK = perWarp >= 2048u ? 256u : perWarp >= 512u ? 128u : perWarp >= 128u ? 64u : 32u;
     constexpr int REFILL_MIN = WPT_REFILL_MIN;
     unsigned int warpNext = 0, warpEnd = 0;
-    bool drained = false;           /* the global ticket counter has run past the last slot */
+    bool drained = false;           /* the global ticket counter has run past the last entry */
     for (;;) {
         const unsigned wantMask = __ballot_sync(FULL, !active && !exhausted);
         const unsigned busyMask = __ballot_sync(FULL, active);
@@ -640,16 +704,18 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
             const unsigned int rank = __popc(wantMask & laneBelow);
             if (!active && !exhausted) {
                 if (rank < avail) {
-                    const unsigned int s = traceQueueSlot(P, warpNext + rank, nCamera);
-                    const float4 o = P.W.rayO[2 * s], d = P.W.rayD[2 * s];
+                    const unsigned int e = traceQueueEntry(P, warpNext + rank, nCamera);
+                    const unsigned int s = e >> 1, which = e & 1u;
+                    const float4 o = P.W.rayO[2 * s], d = (which ? P.W.shD[2 * s] : P.W.rayD[2 * s]);
                     ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
                     if (F & F_MEDIA) {
-                        const uint4 r = P.W.prng[2 * s];
+                        const uint4 r = (which ? P.W.shPrng[s] : P.W.prng[2 * s]);
                         ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
                     }
                     animationCacheInit<F>(S, ctx, ray.time);
                     h = makeRayHelper(ray);
-                    slot = s;
+                    rows = octantRows(ray.d);
+                    entry = e;
                     active = true;
                     best.hit.a = MAXVAL;
                     best.hit.ref = NO_HIT;
@@ -665,7 +731,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
             break;
         /* One iteration runs EITHER the inner-node code OR the leaf code, never both: lanes that have
          * reached a leaf wait until LEAF_MIN lanes have one (or no lane has an inner node left), then
-         * those lanes test their primitives together. Without this, the ~4 lanes that are at a leaf in
+         * those lanes test one primitive each. Without this, the few lanes that are at a leaf in
          * any given iteration make the whole warp pay for the leaf code every time. */
         const bool atInner = active && cur >= 0 && cur != EMPTY_CHILD;
         const bool atLeaf = active && cur < 0;
@@ -677,40 +743,37 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
 
         if (!leafRound) {
             if (atInner) {
-            const float4* n = S.node4 + size_t(cur) * 8;
-            const float4 lox = __ldg(n + 0), hix = __ldg(n + 1);
-            const float4 loy = __ldg(n + 2), hiy = __ldg(n + 3);
-            const float4 loz = __ldg(n + 4), hiz = __ldg(n + 5);
-            const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
-            uint32_t k0 = childKey(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, ray.o, h.inv, amin, best.hit.a, 0);
-            uint32_t k1 = childKey(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, ray.o, h.inv, amin, best.hit.a, 1);
-            uint32_t k2 = childKey(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, ray.o, h.inv, amin, best.hit.a, 2);
-            uint32_t k3 = childKey(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, ray.o, h.inv, amin, best.hit.a, 3);
-            sort2(k0, k1); sort2(k2, k3); sort2(k0, k2); sort2(k1, k3); sort2(k1, k2);
-            if (k0 != 0xFFFFFFFFu) {
-                if (k3 != 0xFFFFFFFFu)
-                    st.push(uint32_t(sel4i(ch, k3 & 3u)), __uint_as_float(k3 & ~3u));
-                if (k2 != 0xFFFFFFFFu)
-                    st.push(uint32_t(sel4i(ch, k2 & 3u)), __uint_as_float(k2 & ~3u));
-                if (k1 != 0xFFFFFFFFu)
-                    st.push(uint32_t(sel4i(ch, k1 & 3u)), __uint_as_float(k1 & ~3u));
-                cur = sel4i(ch, k0 & 3u);
-            } else {
-                cur = popNext(st, best.hit.a);
-            }
+                const NodeKeys nk = nodeKeys(S, cur, ray.o, h.inv, amin, best.hit.a, rows);
+                if (nk.k0 != 0xFFFFFFFFu) {
+                    if (nk.k3 != 0xFFFFFFFFu)
+                        st.push(uint32_t(sel4i(nk.ch, nk.k3 & 3u)), __uint_as_float(nk.k3 & ~3u));
+                    if (nk.k2 != 0xFFFFFFFFu)
+                        st.push(uint32_t(sel4i(nk.ch, nk.k2 & 3u)), __uint_as_float(nk.k2 & ~3u));
+                    if (nk.k1 != 0xFFFFFFFFu)
+                        st.push(uint32_t(sel4i(nk.ch, nk.k1 & 3u)), __uint_as_float(nk.k1 & ~3u));
+                    cur = sel4i(nk.ch, nk.k0 & 3u);
+                } else {
+                    cur = popNext(st, best.hit.a);
+                }
             }
         } else if (atLeaf) {
+#if WPT_LEAF_UNIT
+            /* one primitive per lane and leaf round; what is left of a run stays this lane's leaf */
+            const uint32_t rest = wideLeafStep<F>(S, uint32_t(~cur), ray, h, amin, P.minHit, ctx, best);
+            cur = (rest != NO_HIT ? int32_t(~rest) : popNext(st, best.hit.a));
+#else
             wideLeaf<F>(S, uint32_t(~cur), ray, h, amin, P.minHit, ctx, best);
             cur = popNext(st, best.hit.a);
+#endif
         }
 #if WPT_PREFETCH_LEAF
         if (S.prefetchLeaves && cur < 0 && ((!leafRound && atInner) || (leafRound && atLeaf)))
             prefetchLeaf(S, uint32_t(~cur));
 #endif
         if (cur == EMPTY_CHILD) {
-            P.W.hit[slot] = make_uint2(__float_as_uint(best.hit.a), best.hit.ref);
-            if (F & F_MEDIA)
-                P.W.prng[2 * slot] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
+            reinterpret_cast<uint2*>(P.W.hit)[entry] = make_uint2(__float_as_uint(best.hit.a), best.hit.ref);
+            if ((F & F_MEDIA) && !(entry & 1u))
+                P.W.prng[2 * (entry >> 1)] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
             active = false;
             traced++;
         }
@@ -723,6 +786,271 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
         if (q)
             atomicAdd(P.counters + CTR_NESTED, (unsigned long long)q);
     }
+}
+
+/* ---- Trace, pooled form --------------------------------------------------------------------------------
+ *
+ * The persistent kernel above ties a query to a lane for the whole walk; in every iteration a lane either wants
+ * an inner-node step or a leaf step, and the warp can only run one of the two: measured on the 1M-triangle scene,
+ * node code runs with 18-21 of 32 lanes, leaf code with 7-13 (profiles/r2a_*).
+ *
+ * Here a WARP owns a pool of POOL_RAYS = 64 queries whose walk state lives in shared memory, and three FIFO queues
+ * of pool indices: queries whose next step is an inner node, queries whose next step is a leaf primitive, and free
+ * entries. Every iteration takes up to 32 entries from ONE of the two ready queues, so all lanes run the same
+ * code with (nearly) all lanes busy; a step ends by putting the query into the queue of its next step. The query
+ * that was just queued is not needed again before the others in front of it are done, so its next node / its
+ * leaf's triangles are prefetched while it waits.
+ *
+ * Per query in shared memory (64 B + stack):
+ *   A  origin xyz, distance of the best hit          B  1/direction xyz, next node or leaf (encoded child)
+ *   C  shear constants Sx Sy Sz, kx|ky<<2|kz<<4 | octant rows << 8 | stack size << 16
+ *   D  best hit's leaf reference, its T and |det| (near-tie rule), trace queue entry
+ *   stack  POOL_STACK entries (encoded child, entry distance); deeper entries go to a spill area in HBM
+ * Scenes with media or animated hitables (Prng draws and animation caches inside the walk) and scenes with
+ * spheres use the persistent kernel. Same tests, same answers as traverseWide (see considerHit). */
+constexpr int POOL_RAYS = 64;
+constexpr int POOL_STACK = 12;
+constexpr int POOL_WARPS = BLOCK / 32;
+#ifndef WPT_POOL_MIN_BLOCKS
+#define WPT_POOL_MIN_BLOCKS 5
+#endif
+#ifndef WPT_POOL_PREFETCH
+#define WPT_POOL_PREFETCH 1
+#endif
+
+struct PoolShared {
+    float4 A[POOL_WARPS][POOL_RAYS];
+    float4 B[POOL_WARPS][POOL_RAYS];
+    float4 C[POOL_WARPS][POOL_RAYS];
+    float4 D[POOL_WARPS][POOL_RAYS];
+    uint2 stack[POOL_WARPS][POOL_STACK][POOL_RAYS];
+    uint8_t qNode[POOL_WARPS][POOL_RAYS], qLeaf[POOL_WARPS][POOL_RAYS], qFree[POOL_WARPS][POOL_RAYS];
+};
+
+struct PoolWalk {       /* what a lane holds of its query during one step */
+    uint2* stack;       /* this query's column of the warp's stack array, stride POOL_RAYS */
+    uint2* spill;       /* this query's spill entries in HBM */
+    int sp;
+};
+
+WPT_DEV void poolPush(PoolWalk& w, uint32_t code, float tmin)
+{
+    const uint2 e = make_uint2(code, __float_as_uint(tmin));
+    if (w.sp < POOL_STACK)
+        w.stack[w.sp * POOL_RAYS] = e;
+    else
+        w.spill[w.sp - POOL_STACK] = e;
+    w.sp++;
+}
+
+WPT_DEV int32_t poolPopNext(PoolWalk& w, float limit)
+{
+    while (w.sp > 0) {
+        --w.sp;
+        const uint2 e = (w.sp < POOL_STACK ? w.stack[w.sp * POOL_RAYS] : w.spill[w.sp - POOL_STACK]);
+        if (__uint_as_float(e.y) <= limit)
+            return int32_t(e.x);
+    }
+    return EMPTY_CHILD;
+}
+
+enum { POOL_TO_NONE = 0, POOL_TO_NODE = 1, POOL_TO_LEAF = 2, POOL_TO_FREE = 3 };
+
+__global__ void __launch_bounds__(BLOCK, WPT_POOL_MIN_BLOCKS) waveTracePoolKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P,
+        uint2* spillArea, unsigned int spillPerRay)
+{
+    __shared__ PoolShared sm;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned below = (1u << lane) - 1u;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr unsigned QMASK = POOL_RAYS - 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  /* queue lengths of this round (the sort kernel that follows counts them up) */
+        for (int c = 0; c < MAT_CLASSES; c++)
+            *ctrMaterial(P, c) = 0ull;
+    }
+    float4* const sA = sm.A[warp];
+    float4* const sB = sm.B[warp];
+    float4* const sC = sm.C[warp];
+    float4* const sD = sm.D[warp];
+    uint8_t* const qNode = sm.qNode[warp];
+    uint8_t* const qLeaf = sm.qLeaf[warp];
+    uint8_t* const qFree = sm.qFree[warp];
+    uint2* const spillWarp = spillArea + size_t(blockIdx.x * POOL_WARPS + warp) * POOL_RAYS * spillPerRay;
+
+    const unsigned int nCamera = (unsigned int)*ctrTraceCamera(P);
+    const unsigned int nQueued = nCamera + (unsigned int)*ctrTraceOther(P);
+    const float amin = P.minHit;
+    /* queue state (warp-uniform): FIFO rings of POOL_RAYS entries */
+    unsigned int nodeHead = 0, nodeCnt = 0, leafHead = 0, leafCnt = 0, freeHead = 0, freeCnt = POOL_RAYS;
+    qFree[lane] = uint8_t(lane);
+    qFree[lane + 32] = uint8_t(lane + 32);
+    __syncwarp();
+
+    const unsigned int perWarp = nQueued / (gridDim.x * POOL_WARPS);
+    const unsigned int CHUNK = perWarp >= 2048u ? 256u : perWarp >= 512u ? 128u : perWarp >= 128u ? 64u : 32u;
+    unsigned int warpNext = 0, warpEnd = 0, traced = 0;
+    bool drained = false;
+    for (;;) {
+        /* ---- refill: new queries into free pool entries, 32 at a time (or whatever is needed to have a full pass) ---- */
+        if (!drained && (freeCnt >= 32u || nodeCnt + leafCnt < 32u) && freeCnt > 0u) {
+            if (warpNext >= warpEnd) {
+                unsigned int base = 0;
+                if (lane == 0)
+                    base = (unsigned int)atomicAdd(ctrTicket(P), (unsigned long long)CHUNK);
+                base = __shfl_sync(FULL, base, 0);
+                warpNext = base;
+                warpEnd = min(base + CHUNK, nQueued);
+                if (base >= nQueued) {
+                    drained = true;
+                    warpNext = warpEnd = 0;
+                }
+            }
+            const unsigned int take = min(min(32u, freeCnt), warpEnd - warpNext);
+            if (lane < take) {
+                const unsigned int r = qFree[(freeHead + lane) & QMASK];
+                const unsigned int e = traceQueueEntry(P, warpNext + lane, nCamera);
+                const unsigned int s = e >> 1, which = e & 1u;
+                const float4 o = P.W.rayO[2 * s], d = (which ? P.W.shD[2 * s] : P.W.rayD[2 * s]);
+                Ray ray;
+                ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
+                const RayHelper h = makeRayHelper(ray);
+                sA[r] = f4(ray.o, MAXVAL);
+                sB[r] = f4(h.inv, __int_as_float(S.root4));
+                sC[r] = f4(h.Sx, h.Sy, h.Sz, __uint_as_float(uint32_t(h.kx) | (uint32_t(h.ky) << 2) | (uint32_t(h.kz) << 4) | (octantRows(ray.d) << 8)));
+                sD[r] = f4(__uint_as_float(NO_HIT), 0.0f, 0.0f, __uint_as_float(e));
+                qNode[(nodeHead + nodeCnt + lane) & QMASK] = uint8_t(r);
+            }
+            freeHead += take; freeCnt -= take; nodeCnt += take; warpNext += take;
+            __syncwarp();
+        }
+        if (nodeCnt + leafCnt == 0u) {
+            if (drained)
+                break;
+            continue;
+        }
+        /* ---- one pass: inner nodes or leaf primitives, whichever fills the warp (else the longer queue) ---- */
+        const bool nodePass = (nodeCnt >= 32u) || (leafCnt < 32u && nodeCnt >= leafCnt);
+        int dest = POOL_TO_NONE;
+        unsigned int r = 0;
+        if (nodePass) {
+            const unsigned int n = min(nodeCnt, 32u);
+            if (lane < n) {
+                r = qNode[(nodeHead + lane) & QMASK];
+                const float4 a = sA[r], b = sB[r];
+                const uint32_t cw = __float_as_uint(sC[r].w);
+                PoolWalk w;
+                w.stack = &sm.stack[warp][0][r];
+                w.spill = spillWarp + size_t(r) * spillPerRay;
+                w.sp = int(cw >> 16);
+                int32_t cur = __float_as_int(b.w);
+                const NodeKeys nk = nodeKeys(S, cur, xyz(a), xyz(b), amin, a.w, (cw >> 8) & 7u);
+                if (nk.k0 != 0xFFFFFFFFu) {
+                    if (nk.k3 != 0xFFFFFFFFu)
+                        poolPush(w, uint32_t(sel4i(nk.ch, nk.k3 & 3u)), __uint_as_float(nk.k3 & ~3u));
+                    if (nk.k2 != 0xFFFFFFFFu)
+                        poolPush(w, uint32_t(sel4i(nk.ch, nk.k2 & 3u)), __uint_as_float(nk.k2 & ~3u));
+                    if (nk.k1 != 0xFFFFFFFFu)
+                        poolPush(w, uint32_t(sel4i(nk.ch, nk.k1 & 3u)), __uint_as_float(nk.k1 & ~3u));
+                    cur = sel4i(nk.ch, nk.k0 & 3u);
+                } else {
+                    cur = poolPopNext(w, a.w);
+                }
+                sB[r].w = __int_as_float(cur);
+                sC[r].w = __uint_as_float((cw & 0xFFFFu) | (uint32_t(w.sp) << 16));
+                dest = (cur == EMPTY_CHILD ? POOL_TO_FREE : cur < 0 ? POOL_TO_LEAF : POOL_TO_NODE);
+#if WPT_POOL_PREFETCH
+                if (dest == POOL_TO_NODE)
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(S.node4 + size_t(cur) * 8));
+                else if (dest == POOL_TO_LEAF)
+                    prefetchLeaf(S, uint32_t(~cur));
+#endif
+            }
+            nodeHead += n; nodeCnt -= n;
+        } else {
+            const unsigned int n = min(leafCnt, 32u);
+            if (lane < n) {
+                r = qLeaf[(leafHead + lane) & QMASK];
+                const float4 a = sA[r], b = sB[r], c = sC[r], dd = sD[r];
+                const uint32_t cw = __float_as_uint(c.w);
+                PoolWalk w;
+                w.stack = &sm.stack[warp][0][r];
+                w.spill = spillWarp + size_t(r) * spillPerRay;
+                w.sp = int(cw >> 16);
+                Ray ray;
+                ray.o = xyz(a); ray.d = f3(0.0f); ray.time = 0.0f;     /* the triangle test needs the origin and the shear constants only */
+                RayHelper h;
+                h.inv = xyz(b);
+                h.kx = int(cw & 3u); h.ky = int((cw >> 2) & 3u); h.kz = int((cw >> 4) & 3u);
+                h.Sx = c.x; h.Sy = c.y; h.Sz = c.z;
+                WideBest best;
+                best.hit.a = a.w;
+                best.hit.ref = __float_as_uint(dd.x);
+                best.Ts = dd.y;
+                best.det = dd.z;
+                /* one primitive of the leaf; what is left of a run of triangles stays this query's leaf */
+                const uint32_t ref = uint32_t(~__float_as_int(b.w));
+                uint32_t tref = ref, rest = NO_HIT;
+                if ((ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE_RUN) {
+                    const uint32_t first = ref & RUN_SLOT_MASK;
+                    const uint32_t more = (ref >> RUN_COUNT_SHIFT) & 3u;
+                    tref = (PRIM_TRIANGLE << REF_TYPE_SHIFT) | first;
+                    if (more != 0u)
+                        rest = (PRIM_TRIANGLE_RUN << REF_TYPE_SHIFT) | ((more - 1u) << RUN_COUNT_SHIFT) | (first + 1u);
+                }
+                bool found = false;
+                float ta = 0.0f, Ts = 0.0f, da = 0.0f;
+                if ((tref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE) {
+                    const float4* tp = S.tri + size_t(tref & REF_SLOT_MASK) * 3;
+                    const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                    float U, V, W, det;
+                    found = triangleTest(xyz(t0), xyz(t1), xyz(t2), ray, h, amin, best.hit.a, true, ta, U, V, W, det, Ts, da);
+                } else if ((tref >> REF_TYPE_SHIFT) == PRIM_SPHERE) {
+                    /* the sphere test needs the direction: it is still where the query came from */
+                    const uint32_t e = __float_as_uint(dd.w);
+                    ray.d = xyz((e & 1u) ? P.W.shD[2 * (e >> 1)] : P.W.rayD[2 * (e >> 1)]);
+                    const float4* p = S.sph + size_t(tref & REF_SLOT_MASK) * 3;
+                    const float4 s0 = __ldg(p);
+                    found = sphereTest(xyz(s0), s0.w, ray, amin, best.hit.a, ta);
+                }
+                if (found) {
+                    considerHit(best, tref, ta, Ts, da);
+                    sA[r].w = best.hit.a;
+                    sD[r] = f4(__uint_as_float(best.hit.ref), best.Ts, best.det, dd.w);
+                }
+                int32_t cur = (rest != NO_HIT ? int32_t(~rest) : poolPopNext(w, best.hit.a));
+                sB[r].w = __int_as_float(cur);
+                sC[r].w = __uint_as_float((cw & 0xFFFFu) | (uint32_t(w.sp) << 16));
+                dest = (cur == EMPTY_CHILD ? POOL_TO_FREE : cur < 0 ? POOL_TO_LEAF : POOL_TO_NODE);
+#if WPT_POOL_PREFETCH
+                if (dest == POOL_TO_NODE)
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(S.node4 + size_t(cur) * 8));
+                else if (dest == POOL_TO_LEAF && rest == NO_HIT)
+                    prefetchLeaf(S, uint32_t(~cur));
+#endif
+            }
+            leafHead += n; leafCnt -= n;
+        }
+        /* ---- the query's next step decides its queue; finished walks are answered and their entry freed ---- */
+        if (dest == POOL_TO_FREE) {
+            const float4 a = sA[r], dd = sD[r];
+            reinterpret_cast<uint2*>(P.W.hit)[__float_as_uint(dd.w)] = make_uint2(__float_as_uint(a.w), __float_as_uint(dd.x));
+            traced++;
+        }
+        const unsigned mN = __ballot_sync(FULL, dest == POOL_TO_NODE);
+        const unsigned mL = __ballot_sync(FULL, dest == POOL_TO_LEAF);
+        const unsigned mF = __ballot_sync(FULL, dest == POOL_TO_FREE);
+        if (dest == POOL_TO_NODE)
+            qNode[(nodeHead + nodeCnt + __popc(mN & below)) & QMASK] = uint8_t(r);
+        else if (dest == POOL_TO_LEAF)
+            qLeaf[(leafHead + leafCnt + __popc(mL & below)) & QMASK] = uint8_t(r);
+        else if (dest == POOL_TO_FREE)
+            qFree[(freeHead + freeCnt + __popc(mF & below)) & QMASK] = uint8_t(r);
+        nodeCnt += __popc(mN); leafCnt += __popc(mL); freeCnt += __popc(mF);
+        __syncwarp();
+    }
+    const unsigned int n = __reduce_add_sync(FULL, traced);
+    if (lane == 0 && n)
+        atomicAdd(P.counters + CTR_RAYS, (unsigned long long)n);
 }
 
 /* ------------------------------------------------------------ query kernels */
@@ -774,6 +1102,63 @@ __global__ void __launch_bounds__(BLOCK) queryKernel(const __grid_constant__ DSc
             atomicAdd(&stats->nested, q);
         }
     }
+}
+
+/* Closest-hit queries through the pooled trace kernel (WPT_TRAVERSAL_POOL): the rays are laid out like wavefront
+ * slots, traced by waveTracePoolKernel, and the answers converted to ids. This is how the bit-exact parity
+ * tests reach the kernel that renders. */
+__global__ void __launch_bounds__(BLOCK) poolQuerySetupKernel(const __grid_constant__ RenderParams P,
+        const float* origins, const float* directions, unsigned long long nRays, float time)
+{
+    const unsigned long long i = blockIdx.x * (unsigned long long)BLOCK + threadIdx.x;
+    if (i == 0) {
+        *ctrTicket(P) = 0ull;
+        *ctrTraceCamera(P) = nRays;
+        *ctrTraceOther(P) = 0ull;
+    }
+    if (i >= nRays)
+        return;
+    Ray ray;
+    if (origins) {
+        ray.o = f3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+        ray.d = f3(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
+        ray.time = time;
+    } else {
+        Prng prng = prngInit((unsigned int)i);
+        const unsigned int x = (unsigned int)(i % P.width), y = (unsigned int)(i / P.width);
+        ray = cameraRay(P, (float(x) + 0.5f) / float(P.width), (float(y) + 0.5f) / float(P.height), prng, false);
+    }
+    P.W.rayO[2 * i] = f4(ray.o, ray.time);
+    P.W.rayD[2 * i] = f4(ray.d, 0.0f);
+    P.W.traceQueue[i] = (unsigned int)(i << 1);
+}
+
+__global__ void __launch_bounds__(BLOCK) poolQueryFinishKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P,
+        unsigned long long nRays, int32_t* ids, float* dist)
+{
+    const unsigned long long i = blockIdx.x * (unsigned long long)BLOCK + threadIdx.x;
+    if (i >= nRays)
+        return;
+    const uint4 hw = P.W.hit[i];
+    int32_t id = -1;
+    if (hw.y != NO_HIT) {
+        const uint32_t type = hw.y >> REF_TYPE_SHIFT, slot = hw.y & REF_SLOT_MASK;
+        id = int32_t(type == PRIM_TRIANGLE ? S.triGlobal[slot] : type == PRIM_SPHERE ? S.sphGlobal[slot] : S.medGlobal[slot]);
+    }
+    ids[i] = id;
+    dist[i] = (hw.y != NO_HIT ? __uint_as_float(hw.x) : 0.0f);
+}
+
+cudaError_t launchPoolQuery(const DScene& S, const RenderParams& P, int numSMs, const float* origins, const float* directions,
+        unsigned long long nRays, float time, int32_t* ids, float* dist, cudaStream_t stream)
+{
+    const unsigned int grid = (unsigned int)((nRays + BLOCK - 1) / BLOCK);
+    if (grid == 0)
+        return cudaSuccess;
+    poolQuerySetupKernel<<<grid, BLOCK, 0, stream>>>(P, origins, directions, nRays, time);
+    waveTracePoolKernel<<<poolGridBlocks(numSMs), BLOCK, 0, stream>>>(S, P, P.poolSpill, P.poolSpillPerRay);
+    poolQueryFinishKernel<<<grid, BLOCK, 0, stream>>>(S, P, nRays, ids, dist);
+    return cudaGetLastError();
 }
 
 /* Animation index of a hitable (Hitable::animationIndex(), hitable.hpp:131): -1 = not animated. */
@@ -996,13 +1381,67 @@ static RenderParams slotGroup(const RenderParams& P, uint32_t group, uint32_t fi
     RenderParams G = P;
     G.W.group = group;
     G.W.nSlots = count;
-    G.W.item += first; G.W.prng += 2 * first; G.W.rayO += 2 * first; G.W.rayD += 2 * first; G.W.hit += first;
-    G.W.code += first; G.W.acc += 2 * first; G.W.att += first; G.W.nextAtt += first; G.W.nextDirHot += 2 * first; G.W.pendRad += 2 * first;
-    if (G.W.opl) { G.W.opl += first; G.W.rayRi += first; G.W.nextRi += first; G.W.shadowRi += first; }
-    G.W.queue += first;
-    G.W.traceQueue += first;
+    G.W.item += first; G.W.ctl += first; G.W.code += first;
+    G.W.prng += 2 * first; G.W.acc += 2 * first; G.W.rayO += 2 * first; G.W.rayD += 2 * first;
+    G.W.shD += 2 * first; G.W.pendRad += 2 * first; G.W.att += first; G.W.hit += first;
+    if (G.W.opl) { G.W.opl += first; G.W.rayRi += first; G.W.shadowRi += first; }
+    if (G.W.shPrng) G.W.shPrng += first;
+    G.W.queue += first;             /* every class's list of the group starts `first` entries into the class's array */
+    G.W.traceQueue += 2 * first;
     G.W.window += first / WAVE_WINDOW;
     return G;
+}
+
+/* Resident blocks of the pooled trace kernel: its grid, and what the spill area is sized for. */
+unsigned int poolGridBlocks(int numSMs)
+{
+    static int perSM = 0;
+    if (perSM == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, waveTracePoolKernel, BLOCK, 0) != cudaSuccess || perSM < 1)
+            perSM = 1;
+        if (const char* ev = std::getenv("WPT_POOL_CTAS")) {    /* experiment knob: resident pool CTAs per SM */
+            const int v = std::atoi(ev);
+            if (v >= 1 && v < perSM)
+                perSM = v;
+        }
+    }
+    return (unsigned int)(numSMs * perSM);
+}
+unsigned int poolRaysPerBlock() { return POOL_WARPS * POOL_RAYS; }
+unsigned int poolStackEntries() { return POOL_STACK; }
+unsigned int wideStackEntries() { return SM_STACK + LOCAL_STACK; }
+
+static bool wavePool(const DScene& S, const RenderParams& P)
+{
+    const char* e = std::getenv("WPT_WAVE_POOL");           /* experiment knob: 0 = persistent per-lane walks only */
+    return !(e && e[0] == '0') && S.simpleWalk && P.poolSpill != nullptr;
+}
+
+/* One material kernel per class present in the scene; fixed grids (resident blocks) that stride over the queues. */
+template<int F, int MC>
+static void launchMaterialClass(const DScene& S, const RenderParams& R, int numSMs, unsigned int maxBlocks, cudaStream_t stream)
+{
+    static int perSM = 0;
+    if (perSM == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, waveMaterialKernel<F, MC>, BLOCK, 0) != cudaSuccess || perSM < 1)
+            perSM = 1;
+    }
+    unsigned int grid = (unsigned int)(numSMs * perSM);
+    if (grid > maxBlocks)
+        grid = maxBlocks;
+    waveMaterialKernel<F, MC><<<grid, BLOCK, 0, stream>>>(S, R);
+}
+
+template<int F>
+static int launchMaterial(const DScene& S, const RenderParams& R, int numSMs, unsigned int maxBlocks, cudaStream_t stream)
+{
+    int n = 0;
+    if (S.classMask & (1u << MC_GENERIC)) { launchMaterialClass<F, MC_GENERIC>(S, R, numSMs, maxBlocks, stream); n++; }
+    if (S.classMask & (1u << MC_LAMBERTIAN)) { launchMaterialClass<F, MC_LAMBERTIAN>(S, R, numSMs, maxBlocks, stream); n++; }
+    if (S.classMask & (1u << MC_GGX)) { launchMaterialClass<F, MC_GGX>(S, R, numSMs, maxBlocks, stream); n++; }
+    if (S.classMask & (1u << MC_GLASS)) { launchMaterialClass<F, MC_GLASS>(S, R, numSMs, maxBlocks, stream); n++; }
+    if (S.classMask & (1u << MC_MODPHONG)) { launchMaterialClass<F, MC_MODPHONG>(S, R, numSMs, maxBlocks, stream); n++; }
+    return n;
 }
 
 /* Wavefront driver. The slots are split into two groups that run the same (trace, logic, material)
@@ -1027,6 +1466,8 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
             perSM = v;
     }
     const bool persistent = (P.traversal == WPT_TRAVERSAL_WIDE) && !wavePlainTrace();
+    const bool pool = wavePool(S, P);
+    const unsigned int poolGrid = poolGridBlocks(numSMs);
     const int nGroups = (waveGroups() >= 2 && P.W.nSlots >= 4096) ? 2 : 1;
     RenderParams G[2];
     unsigned int grid[2], sgrid[2], pgrid[2];
@@ -1057,20 +1498,28 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
         waveGenerateKernel<F><<<sgrid[g], BLOCK, 0, st[g]>>>(S, G[g]);      /* every slot gets an item and its first camera ray */
     n += nGroups;
     hostDone[0] = hostDone[1] = 0;
+    /* every round retires at least one path component of every live slot: a bound on the rounds of a frame */
+    const unsigned long long itemsPerSlot = (P.nItems + P.W.nSlots - 1) / P.W.nSlots;
+    const unsigned long long samplesPerItem = (P.samples + P.substreams - 1) / P.substreams;
+    const unsigned long long maxRounds = (itemsPerSlot + 1) * samplesPerItem * (P.maxPathComponents + 2ull) + 64ull;
     for (int k = 0;; k++) {
+        if ((unsigned long long)k * batch > maxRounds)
+            return cudaErrorLaunchFailure;      /* the slots never retired: a bug, not a long frame */
         for (int i = 0; i < batch; i++) {
             for (int g = 0; g < nGroups; g++) {
                 const RenderParams& R = G[g];
-                if (persistent)
+                if (persistent && pool)
+                    waveTracePoolKernel<<<poolGrid, BLOCK, 0, st[g]>>>(S, R,
+                            P.poolSpill + size_t(g) * poolGrid * poolRaysPerBlock() * P.poolSpillPerRay, P.poolSpillPerRay);
+                else if (persistent)
                     waveTracePersistentKernel<F><<<pgrid[g], BLOCK, stackBytes(), st[g]>>>(S, R);
                 else
-                    waveTraceKernel<F><<<grid[g], BLOCK, stackBytes(), st[g]>>>(S, R);
-                waveSortKernel<<<sgrid[g], SORT_BLOCK, 0, st[g]>>>(R);
-                waveMaterialKernel<F><<<grid[g], BLOCK, 0, st[g]>>>(S, R);
+                    waveTraceKernel<F><<<pgrid[g], BLOCK, stackBytes(), st[g]>>>(S, R);
+                waveSortKernel<<<sgrid[g], SORT_BLOCK, 0, st[g]>>>(S, R);
+                n += 3 + launchMaterial<F>(S, R, numSMs, grid[g], st[g]);
                 waveGenerateKernel<F><<<sgrid[g], BLOCK, 0, st[g]>>>(S, R);
             }
         }
-        n += 4 * batch * nGroups;
         if (nGroups == 2) {     /* join the second stream before reading the counter */
             if ((e = cudaEventRecord(events[3], stream2)) != cudaSuccess) return e;
             if ((e = cudaStreamWaitEvent(stream, events[3], 0)) != cudaSuccess) return e;

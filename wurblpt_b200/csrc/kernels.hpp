@@ -21,6 +21,15 @@ cudaError_t launchQuery(int features, bool count, const DScene& S, const RenderP
         const float* origins, const float* directions, unsigned long long nRays, float time,
         int32_t* ids, float* dist, TraceStats* stats, cudaStream_t stream);
 
+/* The same queries through the pooled trace kernel of the wavefront pipeline (scenes without media / animated hitables):
+ * P.W.rayO / rayD / traceQueue / hit must hold nRays slots, P.poolSpill the spill area, P.counters the counters. */
+cudaError_t launchPoolQuery(const DScene& S, const RenderParams& P, int numSMs, const float* origins, const float* directions,
+        unsigned long long nRays, float time, int32_t* ids, float* dist, cudaStream_t stream);
+unsigned int poolGridBlocks(int numSMs);
+unsigned int poolRaysPerBlock();
+unsigned int poolStackEntries();
+unsigned int wideStackEntries();     /* capacity of the per-lane walk's stack (shared memory + local spill) */
+
 /* getGroundTruth(): the images selected by G.bits for P.width x P.height pixels (device pointers in G). */
 cudaError_t launchGroundTruth(int features, const DScene& S, const RenderParams& P, const GroundTruthParams& G, cudaStream_t stream);
 

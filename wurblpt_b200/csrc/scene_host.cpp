@@ -589,6 +589,35 @@ struct Collapser {
 
 }
 
+/* Shading queue of a material (device_scene.cuh MC_*): the scattering types with a kernel of their own; a
+ * two-sided material belongs to its sides' class if they agree (a null side scatters nothing and fits any). */
+uint8_t HostScene::materialClass(int32_t material) const
+{
+    auto direct = [this](int32_t m) -> int {
+        if (m < 0 || size_t(m) >= materials.size())
+            return -1;      /* null: fits any class */
+        switch (materials[m].type) {
+        case WPT_MAT_LAMBERTIAN: return 1;
+        case WPT_MAT_GGX: return 2;
+        case WPT_MAT_GLASS: return 3;
+        case WPT_MAT_MODPHONG: return 4;
+        default: return 0;
+        }
+    };
+    if (material < 0 || size_t(material) >= materials.size())
+        return 0;
+    if (materials[material].type != WPT_MAT_TWOSIDED)
+        return uint8_t(direct(material));
+    const int f = direct(materials[material].front), b = direct(materials[material].back);
+    if (f < 0 && b < 0)
+        return 0;
+    if (f < 0)
+        return uint8_t(b);
+    if (b < 0 || b == f)
+        return uint8_t(f);
+    return 0;
+}
+
 /* --------------------------------------------------------------- updateBvh */
 
 int HostScene::updateBvh(float t0, float t1)
@@ -753,6 +782,26 @@ int HostScene::updateBvh(float t0, float t1)
     hotSpotRefs.clear();
     for (uint32_t id : hotSpotIds)
         hotSpotRefs.push_back(refOfGlobal[id]);
+
+    /* material class of every slot: which shading queue a hit on it goes to */
+    triClass.resize(triGlobal.size());
+    sphClass.resize(sphGlobal.size());
+    medClass.resize(medGlobal.size());
+    std::vector<uint8_t> classOfMaterial(materials.size());
+    for (size_t m = 0; m < materials.size(); m++)
+        classOfMaterial[m] = materialClass(int32_t(m));
+    auto cls = [&](int32_t material) { return material >= 0 && size_t(material) < classOfMaterial.size() ? classOfMaterial[material] : uint8_t(0); };
+    #pragma omp parallel for schedule(static)
+    for (size_t s = 0; s < triGlobal.size(); s++)
+        triClass[s] = cls(instances[prims[triGlobal[s]].ref].material);
+    for (size_t s = 0; s < sphGlobal.size(); s++)
+        sphClass[s] = cls(spheres[prims[sphGlobal[s]].ref].material);
+    for (size_t s = 0; s < medGlobal.size(); s++)
+        medClass[s] = cls(media[prims[medGlobal[s]].ref].material);
+    classMask = 0;
+    for (uint8_t c : triClass) classMask |= 1u << c;
+    for (uint8_t c : sphClass) classMask |= 1u << c;
+    for (uint8_t c : medClass) classMask |= 1u << c;
 
     haveBvh = true;
     bvhT0 = t0;

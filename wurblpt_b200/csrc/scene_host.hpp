@@ -100,6 +100,9 @@ struct HostScene {
     std::vector<float> sphData;             /* 12 floats per sphere slot */
     std::vector<float> medData;             /* 4 floats per medium slot */
     std::vector<uint32_t> hotSpotRefs;      /* device leaf references of the hot spots */
+    std::vector<uint8_t> triClass, sphClass, medClass;  /* material class of every slot (device_scene.cuh MC_*) */
+    uint32_t classMask = 0;                 /* classes present */
+    uint8_t materialClass(int32_t material) const;
     double buildSeconds = 0.0;
 
     std::string error;
