@@ -143,13 +143,23 @@ inline int Flattener::texture(const Texture* tex)
     std::memset(&t, 0, sizeof(t));
     t.src_texture = -1;
     if (!tex->flatten(*this, t)) {
-        /* A user-defined Texture: the device cannot call its value(). It is sampled at the texel centres of a
-         * bakeTextureSize^2 float RGBA image (bilinear lookup with fract() wrap, like TextureImage) at the time
-         * the description is made for; the scene re-bakes when updateBVH() is called for other times. */
+        /* A user-defined Texture: the device cannot call its value(). It is sampled at texel centres into a float
+         * RGBA image (bilinear lookup with fract() wrap, like TextureImage) at the time the description is made for;
+         * the scene re-bakes when updateBVH() is called for other times. The image has the size the reference itself
+         * gives such a texture when it writes it out (Texture::exportToObj, texture.hpp:100-105): 1 / texelSize() per
+         * axis where the texture reports one, bakeTextureSize (512) otherwise. */
         bakedTextures = true;
-        const unsigned int n = bakeTextureSize;
+        unsigned int w = bakeTextureSize, h = bakeTextureSize;
+        const vec2 ts = tex->texelSize();
+        if (ts.x() > 0.0f)
+            w = max(static_cast<unsigned int>(1.0f / ts.x()), 1u);
+        if (ts.y() > 0.0f)
+            h = max(static_cast<unsigned int>(1.0f / ts.y()), 1u);
+        w = min(w, 8192u);
+        h = min(h, 8192u);
         t.type = WPT_TEX_IMAGE;
-        t.width = t.height = int(n);
+        t.width = int(w);
+        t.height = int(h);
         t.components = 4;
         t.texel_type = WPT_TEXEL_F32;
         t.linearize_srgb = 0;
@@ -159,13 +169,13 @@ inline int Flattener::texture(const Texture* tex)
         while (texels.size() % 16 != 0)
             texels.push_back(0);
         t.texel_offset = texels.size();
-        texels.resize(texels.size() + size_t(n) * n * 4 * sizeof(float));
+        texels.resize(texels.size() + size_t(w) * h * 4 * sizeof(float));
         float* dst = reinterpret_cast<float*>(texels.data() + t.texel_offset);
-        for (unsigned int y = 0; y < n; y++) {
-            for (unsigned int x = 0; x < n; x++) {
-                const vec4 v = tex->value(vec2((x + 0.5f) / n, (y + 0.5f) / n), bakeTime);
+        for (unsigned int y = 0; y < h; y++) {
+            for (unsigned int x = 0; x < w; x++) {
+                const vec4 v = tex->value(vec2((x + 0.5f) / w, (y + 0.5f) / h), bakeTime);
                 for (int c = 0; c < 4; c++)
-                    dst[(size_t(y) * n + x) * 4 + c] = v[c];
+                    dst[(size_t(y) * w + x) * 4 + c] = v[c];
             }
         }
     }

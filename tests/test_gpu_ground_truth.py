@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from wurblpt_b200 import abi
-from util import GOLDEN, Golden, read_png, read_wptarray
+from util import GOLDEN, Golden, box_downsample, read_png, read_wptarray, rel_rmse
 
 pytestmark = pytest.mark.gpu
 
@@ -150,6 +150,17 @@ def test_reference_material_playground_app_runs_unchanged(gpu, tmp_path):
     assert a.shape == (600, 800, 3)
     assert 5 < a.mean() < 250 and a.std() > 5          # an image, not a constant
     assert np.abs(a.astype(np.int32) - b.astype(np.int32)).mean() > 0.5     # the camera and the objects moved
+    # against the same app rendered by the reference itself (tests/golden/make_app_golden.py): 8-bit sRGB frames,
+    # rows stored top to bottom in the file, 8x8 box filter
+    with np.load(os.path.join(GOLDEN, "app_material_playground.npz")) as z:
+        for k, frame in ((0, a), (2, b)):
+            ref_small = z["frame%d" % k].astype(np.float32)
+            dev_small = box_downsample(frame.astype(np.float32), int(z["box"]))
+            err = rel_rmse(dev_small, ref_small, floor=4.0)
+            m_dev, m_ref = dev_small.reshape(-1, 3).mean(axis=0), ref_small.reshape(-1, 3).mean(axis=0)
+            print("material-playground frame %d: relRMSE %.4f, means %s vs %s" % (k, err, m_dev, m_ref))
+            assert err <= 0.05, (k, err)
+            assert np.all(np.abs(m_dev - m_ref) <= 0.02 * m_ref), (k, m_dev, m_ref)
 
 
 def test_reference_toomuch_app_runs_unchanged(gpu, tmp_path):
@@ -165,6 +176,16 @@ def test_reference_toomuch_app_runs_unchanged(gpu, tmp_path):
     hdr = read_wptarray(str(tmp_path / "toomuch-0000.tgd"))
     assert hdr.shape == (300, 400, 3) and np.isfinite(hdr).all()
     assert hdr.mean() > 0.01 and (hdr > 0).mean() > 0.9      # a lit room, not a black frame
+    # against frame 0 of the same app rendered by the reference itself (tests/golden/make_app_golden.py): HDR frame,
+    # 4x4 box filter; both are 100-spp estimates of a scene lit by 21 small moving lights
+    with np.load(os.path.join(GOLDEN, "app_toomuch.npz")) as z:
+        ref_small = z["frame0"]
+        dev_small = box_downsample(hdr, int(z["box"]))
+    m_dev, m_ref = dev_small.reshape(-1, 3).mean(axis=0), ref_small.reshape(-1, 3).mean(axis=0)
+    err = rel_rmse(dev_small, ref_small, floor=1e-2 * float(m_ref.mean()) ** 2)
+    print("toomuch frame 0: relRMSE %.4f, means %s vs %s" % (err, m_dev, m_ref))
+    assert np.all(np.abs(m_dev - m_ref) <= 0.04 * m_ref), (m_dev, m_ref)
+    assert err <= 0.25, err
 
 
 def test_reference_noise_textures_app_runs_unchanged(gpu, tmp_path):
@@ -181,3 +202,15 @@ def test_reference_noise_textures_app_runs_unchanged(gpu, tmp_path):
     # the textures are functions of time: consecutive renders differ by more than Monte-Carlo noise
     d01 = np.abs(images[0].astype(np.int32) - images[1].astype(np.int32)).mean()
     assert d01 > 1.0, d01
+    # against the ten images of the same app rendered by the reference itself (tests/golden/make_app_golden.py):
+    # 8-bit sRGB, 8x8 box filter. The noise textures are evaluated on the host with the reference's arithmetic and
+    # sampled into images of the size the reference gives them (texture.hpp:100-105).
+    with np.load(os.path.join(GOLDEN, "app_noise_textures.npz")) as z:
+        for t in range(10):
+            ref_small = z["t%d" % t].astype(np.float32)
+            dev_small = box_downsample(images[t].astype(np.float32), int(z["box"]))
+            err = rel_rmse(dev_small, ref_small, floor=4.0)
+            m_dev, m_ref = dev_small.reshape(-1, 3).mean(axis=0), ref_small.reshape(-1, 3).mean(axis=0)
+            print("noise-textures t=%d: relRMSE %.4f, means %s vs %s" % (t, err, m_dev, m_ref))
+            assert err <= 0.06, (t, err)
+            assert np.all(np.abs(m_dev - m_ref) <= 0.02 * m_ref + 0.5), (t, m_dev, m_ref)

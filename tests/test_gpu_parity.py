@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 
 REFERENCE = abi.WPT_TRAVERSAL_REFERENCE
 WIDE = abi.WPT_TRAVERSAL_WIDE
+POOL = abi.WPT_TRAVERSAL_POOL
 
 
 @pytest.fixture(scope="module")
@@ -74,6 +75,37 @@ def test_primary_hits_wide_walk(gpu, name):
     assert np.array_equal(dist[hit].view(np.uint32), g.z["hit_dist"][hit].view(np.uint32))
 
 
+@pytest.mark.parametrize("name", GOLDEN_SCENES)
+def test_pooled_trace_kernel_answers_like_the_wide_walk(gpu, name):
+    """waveTracePoolKernel (the trace kernel of the wavefront pipeline: walk state in shared memory, node and
+    leaf steps run warp-wide from queues) runs the same tests in the same order per query as the per-lane wide
+    walk: ids and distance bits must be identical, ties included."""
+    g = Golden(name)
+    s = device_scene(gpu, g)
+    h, w = g.z["hit_ids"].shape
+    try:
+        ids, dist = s.primary_hits(g.camera, w, h, g.t0, g.params.min_hit_distance, gpu.make_opts(traversal=POOL))
+    except gpu.WptError as e:
+        assert e.code == abi.WPT_E_UNSUPPORTED      # media / animated hitables: served by the per-lane kernel
+        assert g.desc.n_media > 0 or g.desc.n_animations > 0, name
+        return
+    wids, wdist = s.primary_hits(g.camera, w, h, g.t0, g.params.min_hit_distance, gpu.make_opts(traversal=WIDE))
+    assert np.array_equal(ids, wids)
+    assert np.array_equal(dist.view(np.uint32), wdist.view(np.uint32))
+    # and a ragged count of incoherent rays (pool refills, drain, partial passes)
+    rng = np.random.default_rng(99)
+    for n in (1, 31, 33, 4097, 100003):
+        boxes, _, _ = s.binary_nodes()
+        lo, hi = np.maximum(boxes[0, :3], -25.0), np.minimum(boxes[0, 3:], 25.0)
+        o = (lo + rng.random((n, 3)) * (hi - lo)).astype(np.float32)
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        d = (d / np.sqrt((d ** 2).sum(axis=1, keepdims=True))).astype(np.float32)
+        a_ids, a_dist = s.trace_rays(o, d, g.t0, 1e-4, gpu.make_opts(traversal=POOL))
+        b_ids, b_dist = s.trace_rays(o, d, g.t0, 1e-4, gpu.make_opts(traversal=WIDE))
+        assert np.array_equal(a_ids, b_ids), (name, n)
+        assert np.array_equal(a_dist.view(np.uint32), b_dist.view(np.uint32)), (name, n)
+
+
 @pytest.mark.parametrize("name,scale", [("cornell", 1.0), ("rtiow", 1.0), ("mixed", 1.0), ("media", 1.0), ("synth", 0.05)])
 def test_secondary_ray_closest_hits_against_live_reference(gpu, ref, name, scale):
     """BVH::hit() parity on an incoherent ray set: random origins inside the scene box, random directions."""
@@ -93,7 +125,7 @@ def test_secondary_ray_closest_hits_against_live_reference(gpu, ref, name, scale
     d = (d / np.sqrt((d.astype(np.float32) ** 2).sum(axis=1, keepdims=True))).astype(np.float32)
     has_media = r.desc.n_media > 0
     rid, ra = r.trace_rays(o, d, 0.0, 1e-4)
-    for mode in (REFERENCE, WIDE):
+    for mode in (REFERENCE, WIDE) + (() if has_media else (POOL,)):
         ids, dist = s.trace_rays(o, d, 0.0, 1e-4, gpu.make_opts(traversal=mode))
         if has_media:
             # media hits are random free-flight samples (hitable_medium.hpp:89): compare surfaces only

@@ -113,3 +113,25 @@ def read_wptarray(path):
         dims = [int(x) for x in header[4:4 + ndims]]
         data = np.frombuffer(f.read(), dtype=dtype)
     return data.reshape(dims[1], dims[0], comps)
+
+
+VIEW_GOLDENS = ["cornell_radial_planar", "cornell_radial_only", "cornell_opencv", "mixed_opencv", "cornell_surround180",
+                "mixed_surround180_stereo", "cornell_gated", "mis_gated"]
+
+
+class GoldenView(Golden):
+    """tests/golden/view_<name>.npz (make_view_golden.py): a base fixture's scene seen through another camera /
+    sensor, with the reference's primary hits and render for that view."""
+
+    def __init__(self, name):
+        with np.load(os.path.join(GOLDEN, "view_" + name + ".npz")) as z:
+            v = {k: z[k] for k in z.files}
+        super().__init__(str(v["base"]))
+        self.view_name = name
+        self.camera = abi.wpt_camera_desc.from_buffer_copy(v["camera"].tobytes())
+        self.camera.keyframes = None
+        self.sensor = abi.wpt_sensor_desc.from_buffer_copy(v["sensor"].tobytes())
+        self.params = abi.wpt_params.from_buffer_copy(v["params"].tobytes())
+        self.t0, self.t1 = float(v["t0"]), float(v["t1"])
+        for k in ("hit_ids", "hit_dist", "render", "render_spp_sqrt"):
+            self.z[k] = v[k]

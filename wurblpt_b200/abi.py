@@ -23,6 +23,7 @@ WPT_COMP_MESH_INSTANCE, WPT_COMP_SPHERE, WPT_COMP_MEDIUM = range(3)
 WPT_COMPF_HITABLE, WPT_COMPF_HOTSPOT = 1, 2
 WPT_ENV_NONE, WPT_ENV_EQUIRECT, WPT_ENV_CUBE = range(3)
 WPT_SURROUND_OFF, WPT_SURROUND_180, WPT_SURROUND_360 = range(3)
+WPT_DISTORTION_NONE, WPT_DISTORTION_RADIAL_AND_PLANAR, WPT_DISTORTION_RADIAL_ONLY, WPT_DISTORTION_OPENCV = range(4)
 WPT_SENSOR_RGB, WPT_SENSOR_TOF_AMCW = range(2)
 WPT_TRAVERSAL_WIDE, WPT_TRAVERSAL_REFERENCE, WPT_TRAVERSAL_POOL = range(3)
 WPT_PIPELINE_AUTO, WPT_PIPELINE_MEGAKERNEL, WPT_PIPELINE_WAVEFRONT = range(3)

@@ -267,7 +267,7 @@ void refreshDeviceScene(wpt_scene* s)
     d.sphClass = s->sphClass.as<uint8_t>();
     d.medClass = s->medClass.as<uint8_t>();
     d.classMask = h.classMask;
-    d.simpleWalk = (s->sceneHasMedia || s->sceneHasAnimation) ? 0 : 1;
+    d.simpleWalk = (s->sceneHasMedia || s->sceneHasAnimation || h.root4 == 0x7FFFFFFF) ? 0 : 1;   /* (an empty scene has no root) */
     d.materials = s->materials.as<wpt_material>();
     d.instances = s->instances.as<wpt_instance>();
     d.meshes = s->meshes.as<wpt_mesh>();

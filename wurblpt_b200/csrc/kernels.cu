@@ -806,10 +806,15 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
  *   C  shear constants Sx Sy Sz, kx|ky<<2|kz<<4 | octant rows << 8 | stack size << 16
  *   D  best hit's leaf reference, its T and |det| (near-tie rule), trace queue entry
  *   stack  POOL_STACK entries (encoded child, entry distance); deeper entries go to a spill area in HBM
- * Scenes with media or animated hitables (Prng draws and animation caches inside the walk) and scenes with
- * spheres use the persistent kernel. Same tests, same answers as traverseWide (see considerHit). */
+ * Scenes with media or animated hitables (Prng draws and animation caches inside the walk) use the persistent
+ * kernel. Same tests, same answers as traverseWide (see considerHit); WPT_TRAVERSAL_POOL queries run through it
+ * (tests/test_gpu_parity.py::test_pooled_trace_kernel_answers_like_the_wide_walk). Renders use it only with
+ * WPT_WAVE_POOL=1: see wavePool() for the measurement that keeps the per-lane kernel the default. */
+#ifndef WPT_POOL_STACK
+#define WPT_POOL_STACK 12
+#endif
 constexpr int POOL_RAYS = 64;
-constexpr int POOL_STACK = 12;
+constexpr int POOL_STACK = WPT_POOL_STACK;
 constexpr int POOL_WARPS = BLOCK / 32;
 #ifndef WPT_POOL_MIN_BLOCKS
 #define WPT_POOL_MIN_BLOCKS 5
@@ -880,6 +885,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_POOL_MIN_BLOCKS) waveTracePoolKerne
     const unsigned int nCamera = (unsigned int)*ctrTraceCamera(P);
     const unsigned int nQueued = nCamera + (unsigned int)*ctrTraceOther(P);
     const float amin = P.minHit;
+    const bool rootIsNode = (S.root4 >= 0);     /* a scene of one hitable has a leaf for a root */
     /* queue state (warp-uniform): FIFO rings of POOL_RAYS entries */
     unsigned int nodeHead = 0, nodeCnt = 0, leafHead = 0, leafCnt = 0, freeHead = 0, freeCnt = POOL_RAYS;
     qFree[lane] = uint8_t(lane);
@@ -890,7 +896,8 @@ __global__ void __launch_bounds__(BLOCK, WPT_POOL_MIN_BLOCKS) waveTracePoolKerne
     const unsigned int CHUNK = perWarp >= 2048u ? 256u : perWarp >= 512u ? 128u : perWarp >= 128u ? 64u : 32u;
     unsigned int warpNext = 0, warpEnd = 0, traced = 0;
     bool drained = false;
-    for (;;) {
+    /* (the bound only guards against a walk that never ends: every pass ends a step of at least one query) */
+    for (unsigned long long pass = 0; pass < (1ull << 36); pass++) {
         /* ---- refill: new queries into free pool entries, 32 at a time (or whatever is needed to have a full pass) ---- */
         if (!drained && (freeCnt >= 32u || nodeCnt + leafCnt < 32u) && freeCnt > 0u) {
             if (warpNext >= warpEnd) {
@@ -918,9 +925,16 @@ __global__ void __launch_bounds__(BLOCK, WPT_POOL_MIN_BLOCKS) waveTracePoolKerne
                 sB[r] = f4(h.inv, __int_as_float(S.root4));
                 sC[r] = f4(h.Sx, h.Sy, h.Sz, __uint_as_float(uint32_t(h.kx) | (uint32_t(h.ky) << 2) | (uint32_t(h.kz) << 4) | (octantRows(ray.d) << 8)));
                 sD[r] = f4(__uint_as_float(NO_HIT), 0.0f, 0.0f, __uint_as_float(e));
-                qNode[(nodeHead + nodeCnt + lane) & QMASK] = uint8_t(r);
+                if (rootIsNode)
+                    qNode[(nodeHead + nodeCnt + lane) & QMASK] = uint8_t(r);
+                else
+                    qLeaf[(leafHead + leafCnt + lane) & QMASK] = uint8_t(r);
             }
-            freeHead += take; freeCnt -= take; nodeCnt += take; warpNext += take;
+            freeHead += take; freeCnt -= take; warpNext += take;
+            if (rootIsNode)
+                nodeCnt += take;
+            else
+                leafCnt += take;
             __syncwarp();
         }
         if (nodeCnt + leafCnt == 0u) {
@@ -1413,8 +1427,11 @@ unsigned int wideStackEntries() { return SM_STACK + LOCAL_STACK; }
 
 static bool wavePool(const DScene& S, const RenderParams& P)
 {
-    const char* e = std::getenv("WPT_WAVE_POOL");           /* experiment knob: 0 = persistent per-lane walks only */
-    return !(e && e[0] == '0') && S.simpleWalk && P.poolSpill != nullptr;
+    /* Opt-in (WPT_WAVE_POOL=1). Measured on the 1M-triangle scene (profiles/r2d_*): 20 of 32 lanes per instruction
+     * instead of 15, node passes at 29 lanes, but a pass costs ~350 warp instructions (queue bookkeeping, state
+     * round trips through shared memory, stack spills to HBM instead of local memory): 615 vs 679 Msamples/s. */
+    const char* e = std::getenv("WPT_WAVE_POOL");
+    return (e && e[0] == '1') && S.simpleWalk && P.poolSpill != nullptr;
 }
 
 /* One material kernel per class present in the scene; fixed grids (resident blocks) that stride over the queues. */
