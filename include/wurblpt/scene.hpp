@@ -44,13 +44,15 @@ namespace detail {
     abort();
 }
 
-/* WURBLPT_DEVICE selects the CUDA device (default 0); "none" prepares scenes on the host only
- * (flattening and tree build can then be inspected, rendering is refused). */
+/* Which GPUs render: by default ALL of the box (or those listed in WURBLPT_DEVICES, e.g. "0,1,2,3") work on every
+ * frame together (wurblpt_b200.h, WPT_DEVICE_ALL; MPICoordinator::worldSize() reports how many). WURBLPT_DEVICE
+ * selects a single CUDA device instead; "none" prepares scenes on the host only (flattening and tree build can
+ * then be inspected, rendering is refused). */
 inline int deviceFromEnvironment()
 {
     const char* e = std::getenv("WURBLPT_DEVICE");
     if (!e || !*e)
-        return 0;
+        return WPT_DEVICE_ALL;
     if (std::string(e) == "none")
         return WPT_DEVICE_NONE;
     return std::atoi(e);

@@ -36,6 +36,11 @@ public:
     /* Fill `out` (and append texels) for the C ABI; return false if this texture kind cannot be
      * expressed there. */
     virtual bool flatten(Flattener& /* F */, wpt_texture& /* out */) const { return false; }
+    /* true: flatten() expresses this texture exactly; false: it is a function only value() knows (a user-defined
+     * class, a noise texture), which the Flattener samples into an image */
+    virtual bool deviceNative() const { return false; }
+    /* how many times the unit square of this texture's coordinates a lookup in [0,1]^2 spans (see TextureTransformer) */
+    virtual vec2 bakeScale() const { return vec2(1.0f, 1.0f); }
 };
 
 class TextureConstant final : public Texture
@@ -55,6 +60,7 @@ public:
         detail::store(out.color0, _color, 4);
         return true;
     }
+    virtual bool deviceNative() const override { return true; }
 };
 
 class TextureChecker final : public Texture
@@ -90,6 +96,7 @@ public:
         out.vert = _vert;
         return true;
     }
+    virtual bool deviceNative() const override { return true; }
 };
 
 class TextureTransformer final : public Texture
@@ -120,8 +127,16 @@ public:
     virtual unsigned int componentCount() const override { return _texture->componentCount(); }
     virtual TGD::Type componentType() const override { return _texture->componentType(); }
 
+    virtual bool deviceNative() const override { return _texture->deviceNative(); }
+    virtual vec2 bakeScale() const override { return abs(_coordFactor) * _texture->bakeScale(); }
+
     virtual bool flatten(Flattener& F, wpt_texture& out) const override
     {
+        /* A sampled source is only known on the unit square of ITS coordinates (the image lookup wraps around), but
+         * it need not be periodic (e.g. a ramp clamped to [0,1]): then this texture as a whole is sampled instead,
+         * over the unit square of the coordinates it is looked up with. */
+        if (!_texture->deviceNative())
+            return false;
         out.type = WPT_TEX_TRANSFORMER;
         out.src_texture = F.texture(_texture);
         detail::store(out.coord_factor, _coordFactor, 2);
@@ -147,9 +162,12 @@ inline int Flattener::texture(const Texture* tex)
          * RGBA image (bilinear lookup with fract() wrap, like TextureImage) at the time the description is made for;
          * the scene re-bakes when updateBVH() is called for other times. The image has the size the reference itself
          * gives such a texture when it writes it out (Texture::exportToObj, texture.hpp:100-105): 1 / texelSize() per
-         * axis where the texture reports one, bakeTextureSize (512) otherwise. */
+         * axis where the texture reports one, bakeTextureSize (512) otherwise - times the number of repeats a
+         * TextureTransformer in front of a sampled texture asks for, so that its texels do not get coarser. */
         bakedTextures = true;
-        unsigned int w = bakeTextureSize, h = bakeTextureSize;
+        const vec2 scale = tex->bakeScale();
+        unsigned int w = max(static_cast<unsigned int>(bakeTextureSize * min(scale.x(), 8.0f)), 1u);
+        unsigned int h = max(static_cast<unsigned int>(bakeTextureSize * min(scale.y(), 8.0f)), 1u);
         const vec2 ts = tex->texelSize();
         if (ts.x() > 0.0f)
             w = max(static_cast<unsigned int>(1.0f / ts.x()), 1u);

@@ -87,6 +87,7 @@ public:
     virtual TGD::Type componentType() const override { return _img.componentType(); }
     virtual enum LinearizeSRGBType linearizeSRGBType() const override { return _linearizeSRGB ? LinearizeSRGB_On : LinearizeSRGB_Off; }
 
+    virtual bool deviceNative() const override { return true; }
     virtual bool flatten(Flattener& F, wpt_texture& out) const override
     {
         out.type = WPT_TEX_IMAGE;

@@ -376,13 +376,29 @@ int wpt_device_count(void);
 size_t wpt_abi_sizeof(int which);
 
 #define WPT_DEVICE_NONE (-1)
+#define WPT_DEVICE_ALL  (-2)
+
+/* Number of devices a scene created with WPT_DEVICE_ALL will use: every usable CUDA device, or those listed in the
+ * environment variable WURBLPT_DEVICES ("all", or comma separated device indices). This is what
+ * MPICoordinator::worldSize() reports (mpi.hpp:286). */
+int wpt_planned_device_count(void);
 
 /* Ingest a scene description: copies what it needs (the caller may free `desc`
  * afterwards) and uploads time-independent data to `device`. Replaces the sum of
  * Scene::take() calls (scene.hpp:86-141). */
 int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** scene);
 /* device = WPT_DEVICE_NONE creates a host-only scene: wpt_scene_update_bvh() and the inspection
- * calls work (they are pure host code), every rendering call fails with WPT_E_NO_DEVICE. */
+ * calls work (they are pure host code), every rendering call fails with WPT_E_NO_DEVICE.
+ * device = WPT_DEVICE_ALL replicates the scene on several GPUs of the box (see wpt_planned_device_count): the
+ * acceleration structure is built once on the host and uploaded to each; wpt_render() then renders ONE frame on
+ * all of them. This replaces running the reference under MPI (MPICoordinatorMain / MPICoordinatorChild,
+ * mpi.hpp:42-150): the block hand-out of the coordinator thread (mpi.hpp:74-107) is one atomic counter in the first
+ * device's memory that the windows of every device draw blocks of 256 work items from (over NVLink for the other
+ * devices), submitBlock()'s transfer of finished pixels (mpi.hpp:133-149) is one device-to-device copy of each
+ * frame, added on the first device. The other entry points (queries, ground truth) use the first device. */
+
+/* 1 + the number of replicas (0 for a host-only scene). */
+int wpt_scene_device_count(const wpt_scene* scene);
 
 /* Scene::updateBVH(t0, t1) (scene.hpp:151-169): bound every hitable over [t0,t1]
  * (hitable_triangle.hpp:336-395, hitable_sphere.hpp:97-110, hitable_medium.hpp:59-67),

@@ -17,7 +17,8 @@ LIB_PATH = os.environ.get("WPT_LIB") or os.path.join(_HERE, "lib", "libwurblpt_b
 
 EXPORTS = ["wpt_version", "wpt_last_error", "wpt_device_count", "wpt_abi_sizeof", "wpt_scene_create",
            "wpt_scene_update_bvh", "wpt_scene_get_info", "wpt_scene_destroy", "wpt_scene_get_binary_nodes",
-           "wpt_render", "wpt_primary_hits", "wpt_get_ground_truth", "wpt_trace_rays", "wpt_prng_kat"]
+           "wpt_render", "wpt_primary_hits", "wpt_get_ground_truth", "wpt_trace_rays", "wpt_prng_kat",
+           "wpt_planned_device_count", "wpt_scene_device_count"]
 
 _lib = None
 
@@ -58,6 +59,7 @@ def lib():
     L.wpt_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_float,
                                  C.POINTER(abi.wpt_render_opts), C.c_void_p, C.c_void_p, C.c_void_p]
     L.wpt_prng_kat.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.wpt_scene_device_count.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -96,6 +98,10 @@ class Scene:
         """Scene::updateBVH(t0, t1)."""
         _check(lib().wpt_scene_update_bvh(self._h, t0, t1))
         return self
+
+    def device_count(self):
+        """Devices that render a frame of this scene (more than one only for device=abi.WPT_DEVICE_ALL)."""
+        return lib().wpt_scene_device_count(self._h)
 
     def info(self):
         i = abi.wpt_scene_info()

@@ -11,6 +11,7 @@
 #include <limits>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -114,7 +115,15 @@ void decodeTexel(const wpt_texture& t, const uint8_t* base, size_t index, float*
 }
 
 struct wpt_scene {
-    wpt::HostScene host;
+    /* Several GPUs render one frame (wpt_scene_create with WPT_DEVICE_ALL): the scene the caller holds is the
+     * "master" on the first device; it owns the host-side scene and one replica (device arrays, scratch, streams)
+     * per further device. A replica's `host` refers to the master's. */
+    std::unique_ptr<wpt::HostScene> ownedHost;
+    wpt::HostScene& host;
+    wpt_scene* master = nullptr;
+    std::vector<std::unique_ptr<wpt_scene>> replicas;
+    wpt_scene() : ownedHost(new wpt::HostScene), host(*ownedHost) {}
+    explicit wpt_scene(wpt_scene& m) : host(m.host), master(&m) {}
     int device = 0;
     int numSMs = 0;
     bool sceneHasMedia = false, sceneHasAnimation = false;
@@ -125,7 +134,7 @@ struct wpt_scene {
     /* per updateBVH */
     DeviceBuf node4, bnode, tri, triShade, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs, triClass, sphClass, medClass;
     /* per call scratch */
-    DeviceBuf counters, camKeys, frame, partials, wave[17], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds, animTable, poolSpill;
+    DeviceBuf counters, camKeys, frame, partials, wave[17], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds, animTable, poolSpill, sharedCounter, blockDone, peerStage;
     cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaStream_t stream2 = nullptr;
     unsigned long long* hostDone = nullptr;     /* pinned, 2 counters */
@@ -471,6 +480,97 @@ size_t wpt_abi_sizeof(int which)
     return 0;
 }
 
+/* The devices a scene created with WPT_DEVICE_ALL uses: WURBLPT_DEVICES = "all" (default) or a comma separated
+ * list of CUDA device indices. */
+static std::vector<int> plannedDevices()
+{
+    std::vector<int> devices;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    const char* e = std::getenv("WURBLPT_DEVICES");
+    if (e && *e && std::string(e) != "all") {
+        const std::string list(e);
+        size_t pos = 0;
+        while (pos < list.size()) {
+            size_t comma = list.find(',', pos);
+            if (comma == std::string::npos)
+                comma = list.size();
+            const std::string item = list.substr(pos, comma - pos);
+            char* endp = nullptr;
+            const long v = std::strtol(item.c_str(), &endp, 10);
+            bool known = false;
+            for (int d : devices)
+                known = known || d == int(v);
+            if (endp != item.c_str() && v >= 0 && v < n && !known)
+                devices.push_back(int(v));
+            pos = comma + 1;
+        }
+    } else {
+        for (int d = 0; d < n; d++)
+            devices.push_back(d);
+    }
+    return devices;
+}
+
+int wpt_planned_device_count(void)
+{
+    return int(plannedDevices().size());
+}
+
+/* Everything a scene needs on its device that does not depend on the time range. */
+static int initDevice(wpt_scene* s, int device)
+{
+    int rc = selectDevice(device);
+    if (rc != WPT_OK)
+        return rc;
+    s->device = device;
+    cudaDeviceProp prop;
+    WPT_CUDA(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major < 10)
+        return fail(WPT_E_NO_DEVICE, std::string("device '") + prop.name + "' is not a Blackwell (sm_100) GPU; "
+                "this library ships sm_100a code only");
+    s->numSMs = prop.multiProcessorCount;
+    s->sceneHasMedia = !s->host.media.empty();
+    for (const wpt_instance& in : s->host.instances)
+        s->sceneHasAnimation = s->sceneHasAnimation || in.animation >= 0;
+    for (const wpt_sphere& sp : s->host.spheres)
+        s->sceneHasAnimation = s->sceneHasAnimation || sp.animation >= 0;
+    auto start = std::chrono::steady_clock::now();
+    rc = uploadStatic(s);
+    if (rc != WPT_OK)
+        return rc;
+    s->uploadSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    WPT_CUDA(cudaEventCreate(&s->evStart), "cudaEventCreate");
+    WPT_CUDA(cudaEventCreate(&s->evStop), "cudaEventCreate");
+    for (int i = 0; i < 4; i++)
+        WPT_CUDA(cudaEventCreateWithFlags(&s->evWave[i], cudaEventDisableTiming), "cudaEventCreate");
+    WPT_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking), "cudaStreamCreate");
+    WPT_CUDA(cudaMallocHost(&s->hostDone, 2 * sizeof(unsigned long long)), "allocate pinned counters");
+    WPT_CUDA(s->counters.reserve(wptd::CTR_WORDS * sizeof(unsigned long long)), "allocate counters");
+    return WPT_OK;
+}
+
+/* Lets `from` read and write `to`'s memory (the shared work item counter lives on the first device; frames are
+ * copied device to device). */
+static int enablePeer(int from, int to)
+{
+    int can = 0;
+    WPT_CUDA(cudaDeviceCanAccessPeer(&can, from, to), "cudaDeviceCanAccessPeer");
+    if (!can)
+        return fail(WPT_E_UNSUPPORTED, "devices " + std::to_string(from) + " and " + std::to_string(to)
+                + " cannot access each other's memory (no NVLink / P2P path): cannot render one frame on both");
+    WPT_CUDA(cudaSetDevice(from), "cudaSetDevice");
+    const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled)
+        cudaGetLastError();
+    else if (e != cudaSuccess)
+        return failCuda(e, "cudaDeviceEnablePeerAccess");
+    return WPT_OK;
+}
+
 int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** out)
 {
     if (!out)
@@ -491,48 +591,42 @@ int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** out)
         *out = s.release();
         return WPT_OK;
     }
-    rc = selectDevice(device);
+    std::vector<int> devices(1, device);
+    if (device == WPT_DEVICE_ALL) {
+        devices = plannedDevices();
+        if (devices.empty())
+            return fail(WPT_E_NO_DEVICE, "no CUDA device available (WURBLPT_DEVICES names none); this library has no CPU fallback");
+    }
+    rc = initDevice(s.get(), devices[0]);
     if (rc != WPT_OK)
         return rc;
-    s->device = device;
-    cudaDeviceProp prop;
-    WPT_CUDA(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
-    if (prop.major < 10)
-        return fail(WPT_E_NO_DEVICE, std::string("device '") + prop.name + "' is not a Blackwell (sm_100) GPU; "
-                "this library ships sm_100a code only");
-    s->numSMs = prop.multiProcessorCount;
-    s->sceneHasMedia = !s->host.media.empty();
-    for (const wpt_instance& in : s->host.instances)
-        s->sceneHasAnimation = s->sceneHasAnimation || in.animation >= 0;
-    for (const wpt_sphere& sp : s->host.spheres)
-        s->sceneHasAnimation = s->sceneHasAnimation || sp.animation >= 0;
-    auto start = std::chrono::steady_clock::now();
-    rc = uploadStatic(s.get());
-    if (rc != WPT_OK)
-        return rc;
-    s->uploadSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
-    WPT_CUDA(cudaEventCreate(&s->evStart), "cudaEventCreate");
-    WPT_CUDA(cudaEventCreate(&s->evStop), "cudaEventCreate");
-    for (int i = 0; i < 4; i++)
-        WPT_CUDA(cudaEventCreateWithFlags(&s->evWave[i], cudaEventDisableTiming), "cudaEventCreate");
-    WPT_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking), "cudaStreamCreate");
-    WPT_CUDA(cudaMallocHost(&s->hostDone, 2 * sizeof(unsigned long long)), "allocate pinned counters");
-    WPT_CUDA(s->counters.reserve(wptd::CTR_WORDS * sizeof(unsigned long long)), "allocate counters");
+    for (size_t i = 1; i < devices.size(); i++) {
+        std::unique_ptr<wpt_scene> r(new wpt_scene(*s));
+        rc = initDevice(r.get(), devices[i]);
+        if (rc == WPT_OK)
+            rc = enablePeer(devices[i], devices[0]);
+        if (rc == WPT_OK)
+            rc = enablePeer(devices[0], devices[i]);
+        if (rc != WPT_OK)
+            return rc;
+        s->replicas.push_back(std::move(r));
+    }
+    WPT_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
     *out = s.release();
     return WPT_OK;
 }
 
-int wpt_scene_update_bvh(wpt_scene* s, float t0, float t1)
+int wpt_scene_device_count(const wpt_scene* s)
 {
-    if (!s)
-        return fail(WPT_E_INVALID, "null scene");
-    if (s->device != WPT_DEVICE_NONE)
-        WPT_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
-    int rc = s->host.updateBvh(t0, t1);
-    if (rc != WPT_OK)
-        return fail(rc, s->host.error);
-    if (s->device == WPT_DEVICE_NONE)
-        return WPT_OK;
+    if (!s || s->device == WPT_DEVICE_NONE)
+        return 0;
+    return 1 + int(s->replicas.size());
+}
+
+/* The arrays that depend on the time range the acceleration structure was built for. */
+static int uploadBvh(wpt_scene* s)
+{
+    WPT_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
     auto start = std::chrono::steady_clock::now();
     const wpt::HostScene& h = s->host;
     WPT_CUDA(s->node4.upload(h.nodes4.data(), h.nodes4.size() * sizeof(wpt::Node4)), "upload wide nodes");
@@ -552,6 +646,24 @@ int wpt_scene_update_bvh(wpt_scene* s, float t0, float t1)
     refreshDeviceScene(s);
     s->uploadSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     return WPT_OK;
+}
+
+int wpt_scene_update_bvh(wpt_scene* s, float t0, float t1)
+{
+    if (!s)
+        return fail(WPT_E_INVALID, "null scene");
+    if (s->device != WPT_DEVICE_NONE)
+        WPT_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
+    int rc = s->host.updateBvh(t0, t1);     /* built once on the host, uploaded to every device */
+    if (rc != WPT_OK)
+        return fail(rc, s->host.error);
+    if (s->device == WPT_DEVICE_NONE)
+        return WPT_OK;
+    rc = uploadBvh(s);
+    for (size_t i = 0; i < s->replicas.size() && rc == WPT_OK; i++)
+        rc = uploadBvh(s->replicas[i].get());
+    WPT_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
+    return rc;
 }
 
 int wpt_scene_get_info(const wpt_scene* s, wpt_scene_info* info)
@@ -578,6 +690,11 @@ int wpt_scene_get_info(const wpt_scene* s, wpt_scene_info* info)
 void wpt_scene_destroy(wpt_scene* s)
 {
     if (s) {
+        for (auto& r : s->replicas) {
+            cudaSetDevice(r->device);
+            r.reset();
+        }
+        s->replicas.clear();
         if (s->device != WPT_DEVICE_NONE)
             cudaSetDevice(s->device);
         delete s;
@@ -612,9 +729,14 @@ int wpt_scene_get_binary_nodes(const wpt_scene* s, uint64_t capacity, float* box
     return WPT_OK;
 }
 
-int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_desc* sensor,
+/* One frame on several GPUs: what the scenes of the devices share. */
+struct MultiFrame {
+    unsigned long long* itemCounter;    /* in the first device's memory; every device draws its blocks of work items here */
+};
+
+static int renderSingle(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_desc* sensor,
         const wpt_params* params, uint32_t samplesSqrt, float t0, float t1,
-        const wpt_render_opts* opts, float* frame, wpt_stats* stats)
+        const wpt_render_opts* opts, float* frame, wpt_stats* stats, const MultiFrame* multi)
 {
     auto wallStart = std::chrono::steady_clock::now();
     int rc = checkReady(s);
@@ -737,6 +859,19 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
     }
     P.counters = static_cast<unsigned long long*>(s->counters.p);
     WPT_CUDA(cudaMemsetAsync(s->counters.p, 0, wptd::CTR_WORDS * sizeof(unsigned long long), stream), "clear counters");
+    P.itemCounter = P.counters + wptd::CTR_ITEM;
+    P.blockDone = nullptr;
+    if (multi) {
+        /* all devices draw blocks of WAVE_WINDOW work items from one counter; a block holds whole pixels (their
+         * sub-streams are consecutive items, at most 128), so this device resolves exactly the pixels of its blocks */
+        P.itemCounter = multi->itemCounter;
+        if (P.substreams > 1) {
+            const size_t blocks = size_t(P.nItems) / wptd::WAVE_WINDOW + 1;
+            WPT_CUDA(s->blockDone.reserve(blocks), "allocate block flags");
+            WPT_CUDA(cudaMemsetAsync(s->blockDone.p, 0, blocks, stream), "clear block flags");
+            P.blockDone = static_cast<uint8_t*>(s->blockDone.p);
+        }
+    }
 
     /* pipeline */
     int pipeline = o.pipeline;
@@ -744,6 +879,8 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
         return fail(WPT_E_INVALID, "unknown pipeline");
     if (pipeline == WPT_PIPELINE_AUTO)
         pipeline = defaultPipeline();
+    if (multi)
+        pipeline = WPT_PIPELINE_WAVEFRONT;      /* the shared counter hands out whole blocks of work items */
     const int features = sceneFeatures(s, needOpl);
     if (pipeline == WPT_PIPELINE_WAVEFRONT && P.nItems > 0) {
         /* slots: as many as the limit allows for big frames (long launches amortise their ramp and tail), but
@@ -834,6 +971,112 @@ int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_des
         }
     }
     return WPT_OK;
+}
+
+/* One frame on all devices of the scene (wpt_scene_create with WPT_DEVICE_ALL): one host thread per device renders
+ * into that device's own frame, the blocks of work items come from ONE atomic counter in the first device's memory
+ * (reached over NVLink by the others), the frames are added up on the first device. */
+static int renderMulti(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_desc* sensor,
+        const wpt_params* params, uint32_t samplesSqrt, float t0, float t1,
+        const wpt_render_opts* opts, float* frame, wpt_stats* stats)
+{
+    auto wallStart = std::chrono::steady_clock::now();
+    int rc = checkReady(s);
+    if (rc != WPT_OK)
+        return rc;
+    if (!camera || !sensor || !params || !frame)
+        return fail(WPT_E_INVALID, "null argument");
+    wpt_render_opts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts)
+        o = *opts;
+    if (o.tile_stride > 1)
+        return fail(WPT_E_INVALID, "a scene on several devices renders whole frames (tile_stride must be 0 or 1)");
+    cudaStream_t stream = static_cast<cudaStream_t>(o.stream);
+    const size_t n = 1 + s->replicas.size();
+    const size_t frameFloats = size_t(sensor->width) * sensor->height * 3;
+    const size_t frameBytes = frameFloats * sizeof(float);
+
+    WPT_CUDA(s->sharedCounter.reserve(128), "allocate shared work counter");
+    WPT_CUDA(cudaMemsetAsync(s->sharedCounter.p, 0, 128, stream), "clear shared work counter");
+    float* masterFrame = frame;
+    if (!o.frame_on_device) {
+        WPT_CUDA(s->frame.reserve(frameBytes), "allocate frame");
+        masterFrame = static_cast<float*>(s->frame.p);
+    }
+    WPT_CUDA(cudaMemsetAsync(masterFrame, 0, frameBytes, stream), "clear frame");
+    WPT_CUDA(cudaStreamSynchronize(stream), "prepare frame");      /* the counter is zero before any device draws from it */
+    MultiFrame multi;
+    multi.itemCounter = static_cast<unsigned long long*>(s->sharedCounter.p);
+
+    std::vector<int> rcs(n, WPT_OK);
+    std::vector<std::string> errors(n);
+    std::vector<wpt_stats> st(n);
+    auto work = [&](size_t i) {
+        wpt_scene* d = (i == 0 ? s : s->replicas[i - 1].get());
+        wpt_render_opts oi = o;
+        oi.frame_on_device = 1;
+        oi.tile_first = 0;
+        oi.tile_stride = 1;
+        float* target = masterFrame;
+        if (i > 0) {
+            oi.stream = nullptr;
+            if (cudaSetDevice(d->device) != cudaSuccess || d->frame.reserve(frameBytes) != cudaSuccess
+                    || cudaMemsetAsync(d->frame.p, 0, frameBytes, 0) != cudaSuccess) {
+                rcs[i] = WPT_E_CUDA;
+                errors[i] = "allocate frame on device " + std::to_string(d->device);
+                cudaGetLastError();
+                return;
+            }
+            target = static_cast<float*>(d->frame.p);
+        }
+        rcs[i] = renderSingle(d, camera, sensor, params, samplesSqrt, t0, t1, &oi, target, &st[i], &multi);
+        if (rcs[i] != WPT_OK)
+            errors[i] = g_lastError;
+    };
+    std::vector<std::thread> threads;
+    for (size_t i = 1; i < n; i++)
+        threads.emplace_back(work, i);
+    work(0);
+    for (std::thread& t : threads)
+        t.join();
+    WPT_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
+    for (size_t i = 0; i < n; i++)
+        if (rcs[i] != WPT_OK)
+            return fail(rcs[i], "device " + std::to_string(i == 0 ? s->device : s->replicas[i - 1]->device) + ": " + errors[i]);
+
+    /* every pixel was rendered by exactly one device and is zero in the other frames: the sum is an exact gather */
+    WPT_CUDA(s->peerStage.reserve(frameBytes), "allocate frame staging");
+    for (size_t i = 1; i < n; i++) {
+        wpt_scene* d = s->replicas[i - 1].get();
+        WPT_CUDA(cudaMemcpyPeerAsync(s->peerStage.p, s->device, d->frame.p, d->device, frameBytes, stream), "copy frame between devices");
+        WPT_CUDA(wptd::launchAddFrame(masterFrame, static_cast<const float*>(s->peerStage.p), frameFloats, stream), "add frames");
+    }
+    if (!o.frame_on_device)
+        WPT_CUDA(cudaMemcpyAsync(frame, masterFrame, frameBytes, cudaMemcpyDeviceToHost, stream), "copy frame to host");
+    WPT_CUDA(cudaStreamSynchronize(stream), "combine frames");
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        for (size_t i = 0; i < n; i++) {
+            stats->samples += st[i].samples;
+            stats->rays += st[i].rays;
+            stats->nested_queries += st[i].nested_queries;
+            stats->launches += st[i].launches;
+            stats->kernel_ms = std::max(stats->kernel_ms, st[i].kernel_ms);
+        }
+        stats->tiles = st[0].tiles;
+        stats->total_ms = float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wallStart).count());
+    }
+    return WPT_OK;
+}
+
+int wpt_render(wpt_scene* s, const wpt_camera_desc* camera, const wpt_sensor_desc* sensor,
+        const wpt_params* params, uint32_t samplesSqrt, float t0, float t1,
+        const wpt_render_opts* opts, float* frame, wpt_stats* stats)
+{
+    if (s && !s->replicas.empty())
+        return renderMulti(s, camera, sensor, params, samplesSqrt, t0, t1, opts, frame, stats);
+    return renderSingle(s, camera, sensor, params, samplesSqrt, t0, t1, opts, frame, stats, nullptr);
 }
 
 static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width, uint32_t height,

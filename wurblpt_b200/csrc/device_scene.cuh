@@ -175,6 +175,11 @@ struct RenderParams {
     float* frame;
     float* partials;                /* [pixel][sub-stream][3] partial sums when substreams > 1 */
     unsigned long long* counters;   /* CTR_WORDS words, see CTR_* */
+    unsigned long long* itemCounter;    /* the work item ticket: counters + CTR_ITEM, or - when several GPUs render one
+                                           frame - ONE counter in the first GPU's memory that all of them draw their
+                                           blocks of work items from over NVLink (the MPICoordinator block hand-out,
+                                           mpi.hpp:74-107, without the messages) */
+    uint8_t* blockDone;             /* several GPUs: [item / WAVE_WINDOW] = this GPU rendered that block of items */
     WaveState W;
     uint2* poolSpill;               /* pooled trace kernel: stack entries beyond POOL_STACK, per pool entry (2 groups) */
     uint32_t poolSpillPerRay;

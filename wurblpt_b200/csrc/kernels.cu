@@ -45,7 +45,7 @@ namespace wptd {
 #define WPT_LOGIC_MIN_BLOCKS WPT_SHADE_MIN_BLOCKS
 #endif
 #ifndef WPT_MATERIAL_MIN_BLOCKS
-#define WPT_MATERIAL_MIN_BLOCKS WPT_SHADE_MIN_BLOCKS
+#define WPT_MATERIAL_MIN_BLOCKS 6   /* 85 registers: +1.5 % on C3, +5 % on C1 over 4 blocks (128 registers), profiles/r2f_ab.txt */
 #endif
 #ifndef WPT_PREFETCH_LEAF
 #define WPT_PREFETCH_LEAF 1
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_MIN_BLOCKS) renderKernel(const __gr
             const int leader = __ffs(wantMask) - 1;
             unsigned int base = 0;
             if (int(lane) == leader)
-                base = (unsigned int)atomicAdd(P.counters + CTR_ITEM, (unsigned long long)__popc(wantMask));
+                base = (unsigned int)atomicAdd(P.itemCounter, (unsigned long long)__popc(wantMask));
             base = __shfl_sync(FULL, base, leader);
             if (ps.state == ST_IDLE && !exhausted) {
                 const unsigned int item = base + __popc(wantMask & laneBelow);
@@ -165,7 +165,10 @@ __global__ void resolveKernel(const __grid_constant__ RenderParams P)
     if (i >= P.nLocalTiles * pixelsPerTile)
         return;
     const unsigned int localTile = i / pixelsPerTile, pit = i % pixelsPerTile;
-    const WorkItem w = decodeItem(P, (localTile << P.tileShift) | (pit << P.subShift));
+    const unsigned int item = (localTile << P.tileShift) | (pit << P.subShift);
+    if (P.blockDone && !P.blockDone[item / WAVE_WINDOW])
+        return;         /* another GPU rendered this pixel */
+    const WorkItem w = decodeItem(P, item);
     if (!w.valid)
         return;
     const float* part = P.partials + size_t(w.pixel) * P.substreams * 3;
@@ -179,6 +182,31 @@ __global__ void resolveKernel(const __grid_constant__ RenderParams P)
     out[0] = P.invSamples * r;
     out[1] = P.invSamples * g;
     out[2] = P.invSamples * b;
+}
+
+/* Several GPUs: adds another GPU's frame (zero wherever that GPU rendered nothing) to this one's. Every pixel is
+ * rendered by exactly one GPU, so the sum is an exact gather (x + 0 = x). */
+__global__ void addFrameKernel(float4* frame, const float4* other, size_t n4, float* tail, const float* otherTail, unsigned int nTail)
+{
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < n4) {
+        const float4 a = frame[i], b = other[i];
+        frame[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+    if (i < nTail)
+        tail[i] += otherTail[i];
+}
+
+cudaError_t launchAddFrame(float* frame, const float* other, size_t nFloats, cudaStream_t stream)
+{
+    const size_t n4 = nFloats / 4;
+    const unsigned int nTail = (unsigned int)(nFloats % 4);
+    if (nFloats == 0)
+        return cudaSuccess;
+    const size_t threads = n4 > nTail ? n4 : nTail;
+    addFrameKernel<<<(unsigned int)((threads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<float4*>(frame),
+            reinterpret_cast<const float4*>(other), n4, frame + n4 * 4, other + n4 * 4, nTail);
+    return cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------- wavefront */
@@ -476,8 +504,11 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
                 if (wantMask != 0u) {
                     if (block.x == block.y && block.x != 0xFFFFFFFFu) {     /* the window's block is used up */
                         unsigned int base = 0;
-                        if (lane == 0)
-                            base = (unsigned int)atomicAdd(P.counters + CTR_ITEM, (unsigned long long)WAVE_WINDOW);
+                        if (lane == 0) {
+                            base = (unsigned int)atomicAdd_system(P.itemCounter, (unsigned long long)WAVE_WINDOW);
+                            if (P.blockDone && base < P.nItems)
+                                P.blockDone[base / WAVE_WINDOW] = 1;    /* this GPU renders (and resolves) these items' pixels */
+                        }
                         base = __shfl_sync(FULL, base, 0);
                         if (base >= P.nItems)
                             block = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -656,7 +687,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     const unsigned int nCamera = (unsigned int)*ctrTraceCamera(P);
     const unsigned int nQueued = nCamera + (unsigned int)*ctrTraceOther(P);
     unsigned int entry = 0;             /* slot << 1 | query of the walk in progress */
-    bool active = false, exhausted = false;
+    bool active = false;
     Ray ray;
     ray.o = f3(0.0f); ray.d = f3(0.0f, 0.0f, 1.0f); ray.time = 0.0f;
     RayHelper h = makeRayHelper(ray);
@@ -682,9 +713,11 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     constexpr int REFILL_MIN = WPT_REFILL_MIN;
     unsigned int warpNext = 0, warpEnd = 0;
     bool drained = false;           /* the global ticket counter has run past the last entry */
+    unsigned exhaustedMask = 0u;    /* lanes that found the queue empty (warp-uniform; only a refill changes it) */
     for (;;) {
-        const unsigned wantMask = __ballot_sync(FULL, !active && !exhausted);
         const unsigned busyMask = __ballot_sync(FULL, active);
+        const unsigned wantMask = ~busyMask & ~exhaustedMask;
+        unsigned activeMask = busyMask;
         /* camera rays of one window are coherent: they are started 32 at a time so that they stay together */
         const int refillMin = (warpNext < warpEnd && warpNext < nCamera) ? WPT_CAMERA_REFILL_MIN : REFILL_MIN;
         if (wantMask != 0u && (__popc(wantMask) >= refillMin || busyMask == 0u)) {
@@ -702,41 +735,42 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
             }
             const unsigned int avail = warpEnd - warpNext;
             const unsigned int rank = __popc(wantMask & laneBelow);
-            if (!active && !exhausted) {
-                if (rank < avail) {
-                    const unsigned int e = traceQueueEntry(P, warpNext + rank, nCamera);
-                    const unsigned int s = e >> 1, which = e & 1u;
-                    const float4 o = P.W.rayO[2 * s], d = (which ? P.W.shD[2 * s] : P.W.rayD[2 * s]);
-                    ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
-                    if (F & F_MEDIA) {
-                        const uint4 r = (which ? P.W.shPrng[s] : P.W.prng[2 * s]);
-                        ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
-                    }
-                    animationCacheInit<F>(S, ctx, ray.time);
-                    h = makeRayHelper(ray);
-                    rows = octantRows(ray.d);
-                    entry = e;
-                    active = true;
-                    best.hit.a = MAXVAL;
-                    best.hit.ref = NO_HIT;
-                    st.sp = 0;
-                    cur = S.root4;
-                } else if (drained) {
-                    exhausted = true;
+            const bool got = ((wantMask >> lane) & 1u) && rank < avail;
+            if (got) {
+                const unsigned int e = traceQueueEntry(P, warpNext + rank, nCamera);
+                const unsigned int s = e >> 1, which = e & 1u;
+                const float4 o = P.W.rayO[2 * s], d = (which ? P.W.shD[2 * s] : P.W.rayD[2 * s]);
+                ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
+                if (F & F_MEDIA) {
+                    const uint4 r = (which ? P.W.shPrng[s] : P.W.prng[2 * s]);
+                    ctx.prng.s0 = r.x; ctx.prng.s1 = r.y; ctx.prng.s2 = r.z; ctx.prng.s3 = r.w;
                 }
+                animationCacheInit<F>(S, ctx, ray.time);
+                h = makeRayHelper(ray);
+                rows = octantRows(ray.d);
+                entry = e;
+                active = true;
+                best.hit.a = MAXVAL;
+                best.hit.ref = NO_HIT;
+                st.sp = 0;
+                cur = S.root4;
             }
+            const unsigned gotMask = __ballot_sync(FULL, got);
+            activeMask |= gotMask;
+            if (drained)        /* the lanes that got nothing will never get anything */
+                exhaustedMask |= wantMask & ~gotMask;
             warpNext += min((unsigned int)__popc(wantMask), avail);
         }
-        if (__all_sync(FULL, exhausted))
+        if (exhaustedMask == FULL)
             break;
         /* One iteration runs EITHER the inner-node code OR the leaf code, never both: lanes that have
          * reached a leaf wait until LEAF_MIN lanes have one (or no lane has an inner node left), then
-         * those lanes test one primitive each. Without this, the few lanes that are at a leaf in
+         * those lanes test their primitives together. Without this, the few lanes that are at a leaf in
          * any given iteration make the whole warp pay for the leaf code every time. */
-        const bool atInner = active && cur >= 0 && cur != EMPTY_CHILD;
         const bool atLeaf = active && cur < 0;
-        const unsigned innerMask = __ballot_sync(FULL, atInner);
+        const bool atInner = active && cur >= 0 && cur != EMPTY_CHILD;   /* (EMPTY_CHILD: the root of an empty scene) */
         const unsigned leafMask = __ballot_sync(FULL, atLeaf);
+        const unsigned innerMask = activeMask & ~leafMask;
         const bool leafRound = (__popc(leafMask) >= WPT_LEAF_MIN) || innerMask == 0u;
         if (!active)
             continue;

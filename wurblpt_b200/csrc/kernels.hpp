@@ -33,6 +33,9 @@ unsigned int wideStackEntries();     /* capacity of the per-lane walk's stack (s
 /* getGroundTruth(): the images selected by G.bits for P.width x P.height pixels (device pointers in G). */
 cudaError_t launchGroundTruth(int features, const DScene& S, const RenderParams& P, const GroundTruthParams& G, cudaStream_t stream);
 
+/* frame[i] += other[i] (both on the current device; combining the frames of several GPUs) */
+cudaError_t launchAddFrame(float* frame, const float* other, size_t nFloats, cudaStream_t stream);
+
 cudaError_t launchPrng(const uint32_t* seeds, uint32_t nSeeds, uint32_t nDraws, float* out, cudaStream_t stream);
 
 }
