@@ -98,10 +98,26 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def reference_timing(workload, samples_sqrt, flavour="fast"):
+def host_reference_flavour():
+    """The build of the reference this host's CPU runs fastest: the reference is compiled with -march=native
+    (wurblpt-cornellbox/CMakeLists.txt:17); the binaries are built elsewhere, so the ISA level is chosen here."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((line for line in f if line.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    need = ["avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"]
+    return "fast_v4" if all((" " + n) in flags for n in need) else "fast"
+
+
+def reference_timing(workload, samples_sqrt, flavour=None):
     """mcpt() of the unmodified reference on the host cores: (Msamples/s, threads, seconds, sample text)."""
     from oracle import refapi
     scene_name, scale, width, height, _ = WORKLOADS[workload]
+    if flavour is None:
+        flavour = host_reference_flavour()
+    if not refapi.available(flavour):
+        flavour = "fast"
     if not refapi.available(flavour):
         flavour = "strict"
     view = refapi.View(scene_name, flavour=flavour)
@@ -160,6 +176,34 @@ def run_reference_arm(args):
     return 0
 
 
+def measure_config(workload, device, stream, args):
+    """Msamples/s and Mrays/s of one mcpt() of another config (frame resident, CUDA events; 1 warm-up + 2 timed)."""
+    import torch
+    from wurblpt_b200 import capi, scenes
+    scene_name, scale, width, height, samples_sqrt = WORKLOADS[workload]
+    built = scenes.BuiltScene(scene_name, scale)
+    view = scenes.View(scene_name)
+    view.sensor.width, view.sensor.height = width, height
+    scene = capi.Scene(built.desc, device=device.index)
+    scene.update_bvh(view.t0, view.t1)
+    built.close()
+    frame = torch.zeros((height, width, 3), dtype=torch.float32, device=device)
+    opts = capi.make_opts(frame_on_device=True, stream=stream.cuda_stream, traversal=args.traversal)
+    ms, rays = [], 0
+    for i in range(3):
+        frame.zero_()
+        st = scene.render_device(view.camera, view.sensor, view.params, samples_sqrt, frame.data_ptr(), view.t0, view.t1,
+                                 opts, want_stats=True)
+        if i > 0:
+            ms.append(st.kernel_ms)
+            rays = st.rays
+    scene.close()
+    samples = width * height * samples_sqrt * samples_sqrt
+    t = sum(ms) / len(ms)
+    return {"workload": "%s %dx%d %dspp" % (workload, width, height, samples_sqrt ** 2), "msamples_per_s": samples / t / 1e3,
+            "mrays_per_s": rays / t / 1e3, "ms_per_step": t, "launches": int(st.launches)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,9 +213,13 @@ def main():
     ap.add_argument("--workload", default="synth", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-samples-sqrt", type=int, default=4, help="samples_sqrt of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short measurements of the other configs")
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--substreams", type=int, default=0)
     ap.add_argument("--pipeline", default="auto", choices=["auto", "megakernel", "wavefront"])
+    ap.add_argument("--inprocess", action="store_true",
+                    help="one process renders each frame on ALL visible GPUs (wpt_scene_create with WPT_DEVICE_ALL, "
+                         "the path the reference's apps take through mcpt()); not for use under torchrun")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -194,8 +242,11 @@ def main():
     view = scenes.View(scene_name)
     view.sensor.width, view.sensor.height = width, height
     build_scene_s = time.time() - t
-    scene = capi.Scene(built.desc, device=local)
+    if args.inprocess and world > 1:
+        raise SystemExit("--inprocess drives all GPUs from one process; do not start it under torchrun")
+    scene = capi.Scene(built.desc, device=abi.WPT_DEVICE_ALL if args.inprocess else local)
     scene.update_bvh(view.t0, view.t1)
+    devices_used = scene.device_count()
     built.close()
     info = scene.info()
 
@@ -321,6 +372,46 @@ def main():
                     "nodes_per_query": work["nodes_per_query"], "leaves_per_query": work["leaves_per_query"],
                     "mrays_per_s": rays_rank / kernel_ms / 1e3}
 
+    # ---- issue-slot roofline: the pipeline is bound by instruction issue, not by HBM ----
+    issue = None
+    iw = load_json(os.path.join(ROOT, "profiles", "r2_issue_work.json"), {}).get(scene_name)
+    if iw and clocks and clocks.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(device).multi_processor_count
+        peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6                      # warp instructions per second, 4 schedulers per SM
+        achieved_issue = rays_rank * iw["warp_instr_per_query"] / (kernel_ms * 1e-3)
+        issue = {"bound": "issue", "achieved": achieved_issue / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instr/s",
+                 "frac": achieved_issue / peak_issue, "warp_instr_per_query": iw["warp_instr_per_query"],
+                 "lanes_per_instr": iw["lanes_per_instr"], "thread_slot_frac": achieved_issue / peak_issue * iw["lanes_per_instr"] / 32.0,
+                 "source": iw.get("source")}
+
+    # ---- frame check: bit pattern of the frame; on several GPUs it must equal the frame ONE GPU renders ----
+    import zlib
+    frame_check = None
+    if rank == 0:
+        combined = frame.cpu().numpy()
+        frame_check = {"crc32": "%08x" % (zlib.crc32(combined.tobytes()) & 0xFFFFFFFF)}
+        if world > 1:
+            solo = torch.zeros_like(frame)
+            solo_opts = multi.rank_opts(0, 1, substreams=args.substreams, stream=stream.cuda_stream, traversal=args.traversal,
+                                        pipeline=pipeline)
+            scene.render_device(view.camera, view.sensor, view.params, samples_sqrt, solo.data_ptr(), view.t0, view.t1, solo_opts)
+            torch.cuda.synchronize(device)
+            solo_np = solo.cpu().numpy()
+            frame_check["single_gpu_crc32"] = "%08x" % (zlib.crc32(solo_np.tobytes()) & 0xFFFFFFFF)
+            frame_check["equals_single_gpu"] = bool(np.array_equal(solo_np.view(np.uint32), combined.view(np.uint32)))
+
+    # ---- the other configs BASELINE.json names, one short measurement each (N = 1 only) ----
+    configs = None
+    if world == 1 and not args.no_configs and not args.inprocess:
+        configs = {}
+        for w in ("cornell", "rtiow", "tof", "media"):
+            if w == args.workload:
+                continue
+            try:
+                configs[w] = measure_config(w, device, stream, args)
+            except Exception as ex:
+                configs[w] = {"error": str(ex)}
+
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
@@ -331,23 +422,29 @@ def main():
             cpu = {"value": None, "unit": "Msamples/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
 
     line = {
-        "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+        "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": devices_used if args.inprocess else world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s %dx%d %dspp" % (args.workload, width, height, samples_sqrt ** 2),
                    "triangles": int(info.triangles), "hitables": int(info.hitables),
                    "wide_nodes": int(info.wide_nodes), "device_mb": info.device_bytes / 1e6,
-                   "parallelism": "tiles interleaved over %d GPU(s), one NCCL reduce per frame" % world,
+                   "parallelism": ("one process, %d GPU(s): blocks of work items from one device-side counter, frames added "
+                                   "device to device" % devices_used) if args.inprocess else
+                   "tiles interleaved over %d GPU(s), one NCCL reduce per frame" % world,
                    "cache": "256 MiB buffer written between timed steps (L2 flush); scene 250 MB > 126 MB L2",
                    "traversal": "wide4" if args.traversal == 0 else "reference-order",
                    "pipeline": "megakernel" if launches_per_step <= 2 else "wavefront",
                    "scene_build_s": build_scene_s, "bvh_build_s": info.build_seconds, "upload_s": info.upload_seconds},
         "mrays_per_s": rays_total / (ms_per_step * 1e3), "rays_per_sample": rays_total / samples_per_step,
-        "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks, "roofline": roofline,
+        "issue_roofline": issue, "frame": frame_check, "configs": configs, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if frame_check and frame_check.get("equals_single_gpu") is False:
+        sys.stderr.write("bench.py: the %d-GPU frame differs from the single-GPU frame\n" % world)
+        return 1
     return 0
 
 

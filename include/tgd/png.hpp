@@ -199,7 +199,7 @@ public:
     }
 };
 
-inline bool inflateBlockData(BitReader& in, std::vector<unsigned char>& out, const Huffman& literals, const Huffman& distances)
+inline bool inflateBlockData(BitReader& in, std::vector<unsigned char>& out, const Huffman& literals, const Huffman& distances, size_t limit)
 {
     static const uint16_t lengthBase[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
     static const uint16_t lengthExtra[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
@@ -209,6 +209,8 @@ inline bool inflateBlockData(BitReader& in, std::vector<unsigned char>& out, con
         const int symbol = literals.decode(in);
         if (symbol < 0)
             return false;
+        if (out.size() >= limit && symbol != 256)
+            return false;       /* the image is full: anything but end-of-block is too much (decompression bomb) */
         if (symbol < 256) {
             out.push_back((unsigned char)symbol);
         } else if (symbol == 256) {
@@ -222,7 +224,7 @@ inline bool inflateBlockData(BitReader& in, std::vector<unsigned char>& out, con
             if (di < 0 || di >= 30)
                 return false;
             const size_t distance = distBase[di] + in.bits(distExtra[di]);
-            if (in.overrun || distance > out.size())
+            if (in.overrun || distance > out.size() || out.size() + size_t(length) > limit)
                 return false;
             for (int k = 0; k < length; k++)
                 out.push_back(out[out.size() - distance]);
@@ -231,7 +233,7 @@ inline bool inflateBlockData(BitReader& in, std::vector<unsigned char>& out, con
 }
 
 /* raw deflate stream -> bytes */
-inline bool inflate(const unsigned char* data, size_t size, std::vector<unsigned char>& out)
+inline bool inflate(const unsigned char* data, size_t size, std::vector<unsigned char>& out, size_t limit = ~size_t(0))
 {
     BitReader in(data, size);
     bool last = false;
@@ -249,6 +251,8 @@ inline bool inflate(const unsigned char* data, size_t size, std::vector<unsigned
             in.pos += 4;
             if ((n ^ inverted) != 0xFFFFu || in.pos + n > in.size)
                 return false;
+            if (out.size() + n > limit)
+                return false;       /* more data than the image can hold: refuse (decompression bomb) */
             out.insert(out.end(), in.data + in.pos, in.data + in.pos + n);
             in.pos += n;
         } else if (type == 1) {
@@ -261,7 +265,7 @@ inline bool inflate(const unsigned char* data, size_t size, std::vector<unsigned
             literals.build(lengths, 288);
             for (int i = 0; i < 30; i++) lengths[i] = 5;
             distances.build(lengths, 30);
-            if (!inflateBlockData(in, out, literals, distances))
+            if (!inflateBlockData(in, out, literals, distances, limit))
                 return false;
         } else if (type == 2) {
             static const unsigned char order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
@@ -308,7 +312,7 @@ inline bool inflate(const unsigned char* data, size_t size, std::vector<unsigned
             Huffman literals, distances;
             if (!literals.build(lengths, nLiterals) || !distances.build(lengths + nLiterals, nDistances))
                 return false;
-            if (!inflateBlockData(in, out, literals, distances))
+            if (!inflateBlockData(in, out, literals, distances, limit))
                 return false;
         } else {
             return false;
@@ -343,6 +347,8 @@ inline ArrayContainer read(const std::vector<unsigned char>& file)
         const size_t payload = pos + 8;
         if (payload + length + 4 > file.size())
             return ArrayContainer();
+        if (crc32(file.data() + pos + 4, length + 4) != bigEndian(payload + length))
+            return ArrayContainer();        /* damaged chunk */
         if (type == "IHDR" && length >= 13) {
             w = bigEndian(payload);
             h = bigEndian(payload + 4);
@@ -367,16 +373,43 @@ inline ArrayContainer read(const std::vector<unsigned char>& file)
     case 6: channels = 4; break;
     }
     const bool depthOk = (colourType == 3 ? depth == 8 : (depth == 8 || depth == 16));
-    if (w == 0 || h == 0 || channels == 0 || !depthOk || interlace != 0 || compressed.size() < 6)
+    if (w == 0 || h == 0 || channels == 0 || compressed.size() < 6)
+        return ArrayContainer();
+    /* Images this reader does not decode are refused loudly: the caller would otherwise get an empty array where
+     * the reference's libpng-based loader returns the image. */
+    if (!depthOk || interlace != 0) {
+        std::fprintf(stderr, "tgd png reader: unsupported PNG variant (bit depth %d, colour type %d, %s): "
+                "convert the file to 8 or 16 bit, non-interlaced\n", depth, colourType, interlace ? "interlaced" : "non-interlaced");
+        return ArrayContainer();
+    }
+    /* sizes: bounded so that the products below cannot wrap and a crafted header cannot ask for terabytes */
+    if (w > (size_t(1) << 20) || h > (size_t(1) << 20) || w * h > (size_t(1) << 32))
+        return ArrayContainer();
+    const size_t expected = h * (w * size_t(channels) * size_t(depth / 8) + 1);
+    /* zlib header (RFC 1950): compression method 8, window <= 32 KiB, no preset dictionary, check bits */
+    const unsigned cmf = compressed[0], flg = compressed[1];
+    if ((cmf & 0x0F) != 8 || (cmf >> 4) > 7 || (flg & 0x20) != 0 || ((cmf << 8) | flg) % 31 != 0)
         return ArrayContainer();
     std::vector<unsigned char> raw;
-    raw.reserve(h * (w * channels * (depth / 8) + 1));
-    if (!inflate(compressed.data() + 2, compressed.size() - 2, raw))    /* skip the two zlib header bytes */
+    raw.reserve(expected);
+    if (!inflate(compressed.data() + 2, compressed.size() - 6, raw, expected))   /* between the zlib header and the Adler-32 */
         return ArrayContainer();
+    if (raw.size() != expected)
+        return ArrayContainer();
+    {
+        uint32_t a = 1, b = 0;
+        for (size_t i = 0; i < raw.size(); i++) {
+            a = (a + raw[i]) % 65521u;
+            b = (b + a) % 65521u;
+        }
+        const size_t at = compressed.size() - 4;
+        const uint32_t stored = (uint32_t(compressed[at]) << 24) | (uint32_t(compressed[at + 1]) << 16)
+            | (uint32_t(compressed[at + 2]) << 8) | uint32_t(compressed[at + 3]);
+        if (stored != ((b << 16) | a))
+            return ArrayContainer();
+    }
     const size_t bpp = size_t(channels) * (depth / 8);
     const size_t rowBytes = w * bpp;
-    if (raw.size() < h * (rowBytes + 1))
-        return ArrayContainer();
     /* undo the row filters in place */
     std::vector<unsigned char> previous(rowBytes, 0);
     for (size_t y = 0; y < h; y++) {

@@ -220,6 +220,16 @@ private:
         c.v = resolve(values[0], positions.size() / 3);
         c.t = resolve(values[1], texcoords.size() / 2);
         c.n = resolve(values[2], normals.size() / 3);
+        /* a texture coordinate or normal index that points past what has been read so far is treated as absent
+         * (the collector would read outside the arrays); the position index must be valid */
+        if (c.t >= 0 && size_t(c.t) >= texcoords.size() / 2) {
+            std::fprintf(stderr, "OBJ import: texture coordinate index %d out of range, ignored\n", values[1]);
+            c.t = -1;
+        }
+        if (c.n >= 0 && size_t(c.n) >= normals.size() / 3) {
+            std::fprintf(stderr, "OBJ import: normal index %d out of range, ignored\n", values[2]);
+            c.n = -1;
+        }
         return c.v >= 0 && size_t(c.v) < positions.size() / 3;
     }
 

@@ -51,6 +51,9 @@ def test_devices_share_the_work(gpu):
     frame, stats = many.render(g.camera, sensor, g.params, 8, g.t0, g.t1)
     assert stats.samples == 512 * 512 * 64
     assert np.isfinite(frame).all() and frame.mean() > 0.01
+    one = gpu.Scene(g.desc, device=0).update_bvh(g.t0, g.t1)
     ids, dist = many.primary_hits(g.camera, 96, 96, g.t0, g.params.min_hit_distance)
-    assert np.array_equal(ids, g.z["hit_ids"])
+    ids1, dist1 = one.primary_hits(g.camera, 96, 96, g.t0, g.params.min_hit_distance)
+    assert np.array_equal(ids, ids1) and np.array_equal(dist.view(np.uint32), dist1.view(np.uint32))
+    one.close()
     many.close()

@@ -125,3 +125,54 @@ def test_png_files_round_trip_through_the_stand_in(tmp_path):
         n = struct.unpack(">I", data[pos:pos + 4])[0]
         assert zlib.crc32(data[pos + 4:pos + 8 + n]) & 0xFFFFFFFF == struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0]
         pos += 12 + n
+
+
+MALFORMED_PROBE = r'''
+#include <cstdio>
+#include <tgd/array.hpp>
+#include <tgd/io.hpp>
+int main(int argc, char** argv) {
+    for (int i = 1; i < argc; i++) {
+        TGD::Error err = TGD::ErrorNone;
+        TGD::ArrayContainer a = TGD::load(argv[i], TGD::TagList(), &err);
+        std::printf("%d %zu\n", int(err), a.elementCount());
+    }
+    return 0;
+}
+'''
+
+
+def test_png_reader_refuses_malformed_files(tmp_path):
+    """Crafted headers (dimensions whose products wrap), a decompression bomb, a wrong Adler-32, a damaged chunk and
+    an interlaced file must come back as load errors, not crashes or out-of-bounds accesses; a good file still loads."""
+    sig = b"\x89PNG\r\n\x1a\n"
+    good_raw = b"".join(b"\x00" + bytes([1, 2, 3] * 4) for _ in range(2))      # 4x2 rgb, filter 0
+    def ihdr(w, h, depth=8, colour=2, interlace=0):
+        return chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, colour, 0, 0, interlace))
+    bad_adler = bytearray(zlib.compress(good_raw))
+    bad_adler[-1] ^= 0xFF
+    damaged = bytearray(sig + ihdr(4, 2) + chunk(b"IDAT", zlib.compress(good_raw)) + chunk(b"IEND", b""))
+    damaged[45] ^= 0x01
+    files = {
+        "huge.png": sig + ihdr(0x7FFFFFFF, 0x7FFFFFFF, 16, 6) + chunk(b"IDAT", zlib.compress(good_raw)) + chunk(b"IEND", b""),
+        "bomb.png": sig + ihdr(4, 2) + chunk(b"IDAT", zlib.compress(b"\x00" * 5_000_000)) + chunk(b"IEND", b""),
+        "adler.png": sig + ihdr(4, 2) + chunk(b"IDAT", bytes(bad_adler)) + chunk(b"IEND", b""),
+        "damaged.png": bytes(damaged),
+        "interlaced.png": sig + ihdr(4, 2, interlace=1) + chunk(b"IDAT", zlib.compress(good_raw)) + chunk(b"IEND", b""),
+        "short.png": sig + ihdr(4, 2) + chunk(b"IDAT", zlib.compress(good_raw[:-5])) + chunk(b"IEND", b""),
+        "ok.png": sig + ihdr(4, 2) + chunk(b"IDAT", zlib.compress(good_raw)) + chunk(b"IEND", b""),
+    }
+    for name, data in files.items():
+        (tmp_path / name).write_bytes(data)
+    (tmp_path / "probe.cpp").write_text(MALFORMED_PROBE)
+    subprocess.run(["g++", "-std=c++20", "-O1", "-fsanitize=address", "-I" + os.path.join(ROOT, "include"),
+                    str(tmp_path / "probe.cpp"), "-o", str(tmp_path / "probe")], check=True)
+    r = subprocess.run([str(tmp_path / "probe")] + [str(tmp_path / n) for n in files], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [line.split() for line in r.stdout.strip().splitlines()]
+    assert len(lines) == len(files)
+    for (name, _), (err, count) in zip(files.items(), lines):
+        if name == "ok.png":
+            assert err == "0" and count == "8"
+        else:
+            assert err != "0" and count == "0", name

@@ -42,7 +42,7 @@ namespace wptd {
 #define WPT_SHADE_MIN_BLOCKS 4
 #endif
 #ifndef WPT_LOGIC_MIN_BLOCKS
-#define WPT_LOGIC_MIN_BLOCKS WPT_SHADE_MIN_BLOCKS
+#define WPT_LOGIC_MIN_BLOCKS 6
 #endif
 #ifndef WPT_MATERIAL_MIN_BLOCKS
 #define WPT_MATERIAL_MIN_BLOCKS 6   /* 85 registers: +1.5 % on C3, +5 % on C1 over 4 blocks (128 registers), profiles/r2f_ab.txt */
@@ -822,6 +822,106 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     }
 }
 
+/* Drain: the last rounds of a frame hold few live slots but cost a full round each (five launches that scan or
+ * stride over all slots, ~70 us). Once the work items have run out and few slots are alive, this kernel finishes
+ * every one of them in a thread of its own: the slot's pending queries, the rest of its path, the remaining samples
+ * of its item and whatever items are left in its window's block - the same functions in the same order with the
+ * same Prng draws as the rounds would run, so the frame does not depend on when the host switches over. */
+template<int F>
+__global__ void __launch_bounds__(BLOCK, 4) waveDrainKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+{
+    extern __shared__ uint2 smStackAll[];
+    uint2* smStack = smStackAll + threadIdx.x;
+    const unsigned int slot = blockIdx.x * BLOCK + threadIdx.x;
+    unsigned int nSamples = 0, nRays = 0, retired = 0;
+    Ctx<F> ctx;
+    ctx.nested = 0;
+    ctx.nodes = ctx.leaves = 0;
+    int state = ST_EXHAUSTED;
+    if (slot < P.W.nSlots)
+        state = codeState((unsigned int)P.W.code[slot]);
+    if (state == ST_MAIN || state == ST_TAIL || state == ST_NEW) {
+        PathState ps;
+        Hit hitB, hitS;
+        uint4 forked = make_uint4(0u, 0u, 0u, 0u);
+        if (state == ST_NEW) {
+            loadItem<F>(P, slot, false, ps, ctx);
+        } else {
+            loadAnswered<F, true>(P, slot, ps, ctx, hitB, hitS);    /* (the answers are not in yet: traced below) */
+            if ((F & F_MEDIA) && ps.shadow != SHADOW_NONE)
+                forked = P.W.shPrng[slot];
+        }
+        uint2* window = P.W.window + slot / WAVE_WINDOW;
+        for (;;) {
+            if (ps.state == ST_MAIN || ps.state == ST_TAIL) {
+                animationCacheInit<F>(S, ctx, ps.walkRay.time);
+                if (ps.shadow != SHADOW_NONE) {
+                    Ray ray = ps.walkRay;
+                    ray.d = ps.shDir;
+                    const Prng mine = ctx.prng;
+                    if (F & F_MEDIA) {
+                        ctx.prng.s0 = forked.x; ctx.prng.s1 = forked.y; ctx.prng.s2 = forked.z; ctx.prng.s3 = forked.w;
+                    }
+                    hitS = closestHit<F>(S, P, ray, makeRayHelper(ray), ctx, smStack);
+                    ctx.prng = mine;
+                    nRays++;
+                }
+                if (ps.state == ST_MAIN) {
+                    const RayHelper h = makeRayHelper(ps.walkRay);
+                    hitB = closestHit<F>(S, P, ps.walkRay, h, ctx, smStack);
+                    nRays++;
+                    if (ps.shadow != SHADOW_NONE)
+                        consumeShadow<F>(S, P, ps, ctx, hitS);
+                    if (hitB.ref == NO_HIT || !(ps.pathComponent + 1 < P.maxPathComponents)) {
+                        waveEndPath<F>(S, P, ps, hitB);
+                    } else {
+                        waveShade<F, -1>(S, P, ps, ctx, hitB, h);
+                        if ((F & F_MEDIA) && ps.shadow != SHADOW_NONE)
+                            forked = forkPrng(ctx.prng);
+                    }
+                } else {
+                    consumeShadow<F>(S, P, ps, ctx, hitS);
+                    ps.state = ST_NEW;
+                }
+            }
+            if (ps.state == ST_NEW) {
+                if (startSample<F>(S, P, ps, ctx)) {
+                    nSamples++;
+                    continue;
+                }
+                finishItem(P, ps);
+                /* another item of this window's block, if any is left (the global counter has run out) */
+                const uint2 block = *window;
+                unsigned int item = 0xFFFFFFFFu;
+                if (block.x != 0xFFFFFFFFu && block.x < block.y) {
+                    item = atomicAdd(&window->x, 1u);
+                    if (item >= block.y)
+                        item = 0xFFFFFFFFu;
+                }
+                if (item == 0xFFFFFFFFu)
+                    break;
+                const WorkItem wi = decodeItem(P, item);
+                if (!wi.valid)
+                    continue;       /* ps.state stays ST_NEW with no samples left... */
+                beginItem<F>(ps, ctx, wi);
+            }
+        }
+        P.W.code[slot] = uint8_t(ST_EXHAUSTED);
+        P.W.ctl[slot] = makeCtl(ST_EXHAUSTED, SHADOW_NONE, 0u);
+        retired = 1;
+    }
+    const unsigned int ns = __reduce_add_sync(0xFFFFFFFFu, nSamples);
+    const unsigned int nr = __reduce_add_sync(0xFFFFFFFFu, nRays);
+    const unsigned int nq = __reduce_add_sync(0xFFFFFFFFu, ctx.nested);
+    const unsigned int nd = __reduce_add_sync(0xFFFFFFFFu, retired);
+    if ((threadIdx.x & 31u) == 0u) {
+        if (ns) atomicAdd(P.counters + CTR_SAMPLES, (unsigned long long)ns);
+        if (nr) atomicAdd(P.counters + CTR_RAYS, (unsigned long long)nr);
+        if (nq) atomicAdd(P.counters + CTR_NESTED, (unsigned long long)nq);
+        if (nd) atomicAdd(P.counters + CTR_DONE, (unsigned long long)nd);
+    }
+}
+
 /* ---- Trace, pooled form --------------------------------------------------------------------------------
  *
  * The persistent kernel above ties a query to a lane for the whole walk; in every iteration a lane either wants
@@ -1519,6 +1619,10 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
     const bool persistent = (P.traversal == WPT_TRAVERSAL_WIDE) && !wavePlainTrace();
     const bool pool = wavePool(S, P);
     const unsigned int poolGrid = poolGridBlocks(numSMs);
+    unsigned long long drainSlots = 32768;      /* live slots at which waveDrainKernel takes over (0: never); C1 +6 %,
+                                                   media +2 %, larger values cost media up to 6 % (profiles/r2h_ab.txt) */
+    if (const char* ev = std::getenv("WPT_DRAIN_SLOTS"))
+        drainSlots = std::strtoull(ev, nullptr, 10);
     const int nGroups = (waveGroups() >= 2 && P.W.nSlots >= 4096) ? 2 : 1;
     RenderParams G[2];
     unsigned int grid[2], sgrid[2], pgrid[2];
@@ -1588,8 +1692,17 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
             e = cudaEventSynchronize(events[(k - 1) & 1]);
             if (e != cudaSuccess)
                 return e;
-            if (hostDone[(k - 1) & 1] >= P.W.nSlots)
+            const unsigned long long done = hostDone[(k - 1) & 1];
+            if (done >= P.W.nSlots)
                 break;
+            if (done > 0 && P.W.nSlots - done <= drainSlots) {
+                /* the work items have run out (a slot only retires when it finds none) and few slots are alive:
+                 * finish them without further rounds, behind the batch that is already queued */
+                for (int g = 0; g < nGroups; g++)
+                    waveDrainKernel<F><<<grid[g], BLOCK, stackBytes(), st[g]>>>(S, G[g]);
+                n += nGroups;
+                break;
+            }
         }
     }
     if (nGroups == 2) {     /* final join: everything queued on the second stream precedes what follows on `stream` */
