@@ -400,6 +400,18 @@ int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** scene);
 /* 1 + the number of replicas (0 for a host-only scene). */
 int wpt_scene_device_count(const wpt_scene* scene);
 
+/* Which builder wpt_scene_update_bvh() runs (default: host; the environment variable WURBLPT_BVH_BUILDER=device selects
+ * the device builder for every scene):
+ *   WPT_BUILDER_HOST_SAH     the reference's builder restated on the host (bvh.hpp:93-193): the tree equals the
+ *                            reference's node for node, both walks are available
+ *   WPT_BUILDER_DEVICE_LBVH  bounds on the host with the reference's formulas, tree on the device (Morton codes,
+ *                            sort, binary radix tree, bottom-up boxes, 4-wide collapse; wurblpt_b200/csrc/bvh_device.cu):
+ *                            milliseconds instead of 0.3 s for 1 M triangles, for scenes that are rebuilt every frame.
+ *                            Closest hits are those of the host-built tree (exact distance ties may be settled differently);
+ *                            only the 4-wide walk is available; scenes with media use the host builder regardless. */
+enum { WPT_BUILDER_HOST_SAH = 0, WPT_BUILDER_DEVICE_LBVH = 1 };
+int wpt_scene_set_builder(wpt_scene* scene, int builder);
+
 /* Scene::updateBVH(t0, t1) (scene.hpp:151-169): bound every hitable over [t0,t1]
  * (hitable_triangle.hpp:336-395, hitable_sphere.hpp:97-110, hitable_medium.hpp:59-67),
  * build the SAH tree (bvh.hpp:93-193), derive the device layouts and upload them. */

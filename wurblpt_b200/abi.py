@@ -14,6 +14,7 @@ WPT_E_CUDA = -3
 WPT_E_UNSUPPORTED = -4
 WPT_E_STATE = -5
 WPT_DEVICE_NONE, WPT_DEVICE_ALL = -1, -2
+WPT_BUILDER_HOST_SAH, WPT_BUILDER_DEVICE_LBVH = 0, 1
 
 WPT_TEX_CONSTANT, WPT_TEX_CHECKER, WPT_TEX_IMAGE, WPT_TEX_TRANSFORMER = range(4)
 WPT_TEXEL_U8, WPT_TEXEL_U16, WPT_TEXEL_F32 = range(3)

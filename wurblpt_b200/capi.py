@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("WPT_LIB") or os.path.join(_HERE, "lib", "libwurblpt_b
 EXPORTS = ["wpt_version", "wpt_last_error", "wpt_device_count", "wpt_abi_sizeof", "wpt_scene_create",
            "wpt_scene_update_bvh", "wpt_scene_get_info", "wpt_scene_destroy", "wpt_scene_get_binary_nodes",
            "wpt_render", "wpt_primary_hits", "wpt_get_ground_truth", "wpt_trace_rays", "wpt_prng_kat",
-           "wpt_planned_device_count", "wpt_scene_device_count"]
+           "wpt_planned_device_count", "wpt_scene_device_count", "wpt_scene_set_builder"]
 
 _lib = None
 
@@ -60,6 +60,7 @@ def lib():
                                  C.POINTER(abi.wpt_render_opts), C.c_void_p, C.c_void_p, C.c_void_p]
     L.wpt_prng_kat.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     L.wpt_scene_device_count.argtypes = [C.c_void_p]
+    L.wpt_scene_set_builder.argtypes = [C.c_void_p, C.c_int]
     _lib = L
     return L
 
@@ -93,6 +94,11 @@ class Scene:
         self._h = C.c_void_p()
         self.device = device
         _check(lib().wpt_scene_create(C.byref(desc), device, C.byref(self._h)))
+
+    def set_builder(self, builder):
+        """abi.WPT_BUILDER_HOST_SAH (default) or abi.WPT_BUILDER_DEVICE_LBVH for the following update_bvh() calls."""
+        _check(lib().wpt_scene_set_builder(self._h, builder))
+        return self
 
     def update_bvh(self, t0=0.0, t1=0.0):
         """Scene::updateBVH(t0, t1)."""

@@ -20,6 +20,7 @@
 #include "scene_host.hpp"
 #include "device_scene.cuh"
 #include "kernels.hpp"
+#include "bvh_device.hpp"
 
 namespace {
 
@@ -135,6 +136,9 @@ struct wpt_scene {
     DeviceBuf node4, bnode, tri, triShade, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs, triClass, sphClass, medClass;
     /* per call scratch */
     DeviceBuf counters, camKeys, frame, partials, wave[17], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds, animTable, poolSpill, sharedCounter, blockDone, peerStage;
+    /* device builder: inputs in hitable order, scratch */
+    DeviceBuf bBox, bTri, bTriShade, bTriClass, bSph, bSphClass, bHot, bScratch;
+    int builder = WPT_BUILDER_HOST_SAH;
     cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaStream_t stream2 = nullptr;
     unsigned long long* hostDone = nullptr;     /* pinned, 2 counters */
@@ -292,8 +296,8 @@ void refreshDeviceScene(wpt_scene* s)
     d.envGuide = s->envGuide.as<uint32_t>();
     d.envGuideBits = s->envGuideBits;
     d.root4 = h.root4;
-    d.prefetchLeaves = (h.triData.size() * sizeof(float) > (128u << 10)) ? 1 : 0;
-    d.nHot = uint32_t(h.hotSpotRefs.size());
+    d.prefetchLeaves = (h.nTriSlots * 12 * sizeof(float) > (128u << 10)) ? 1 : 0;
+    d.nHot = uint32_t(h.hotSpotIds.size());
     d.nAnimations = uint32_t(h.animations.size());
     d.envType = h.env.type;
     d.envCompat = h.env.compat;
@@ -585,6 +589,8 @@ int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** out)
         if (v >= 1 && v <= 4)
             s->host.wideLeafTriangles = uint32_t(v);
     }
+    if (const char* e = std::getenv("WURBLPT_BVH_BUILDER"))     /* "device": build the tree on the GPU (wpt_scene_set_builder) */
+        s->builder = (std::string(e) == "device" ? WPT_BUILDER_DEVICE_LBVH : WPT_BUILDER_HOST_SAH);
     if (device == WPT_DEVICE_NONE) {
         /* host-only scene: bounds and tree can be built and inspected, nothing can be rendered */
         s->device = WPT_DEVICE_NONE;
@@ -648,13 +654,102 @@ static int uploadBvh(wpt_scene* s)
     return WPT_OK;
 }
 
+/* Scene::updateBVH() with the tree built on the device (bvh_device.cu): uploads the bounds and the primitive data
+ * in hitable order, builds, and leaves the arrays the kernels read in slot order. */
+static int buildOnDevice(wpt_scene* s, uint32_t* wideNodes, uint32_t* depth, uint32_t* triangles)
+{
+    WPT_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
+    auto start = std::chrono::steady_clock::now();
+    const wpt::HostScene& h = s->host;
+    const uint32_t n = uint32_t(h.prims.size());
+    const size_t nTri = h.nTriSlots, nSph = h.nSphSlots;
+    WPT_CUDA(s->bBox.upload(h.devBox.data(), h.devBox.size() * sizeof(float)), "upload bounds");
+    WPT_CUDA(s->bTri.upload(h.devTriPrim.data(), h.devTriPrim.size() * sizeof(float)), "upload triangles");
+    WPT_CUDA(s->bTriShade.upload(h.devTriShadePrim.data(), h.devTriShadePrim.size() * sizeof(uint32_t)), "upload triangle shading records");
+    WPT_CUDA(s->bTriClass.upload(h.devTriClassPrim.data(), h.devTriClassPrim.size()), "upload triangle material classes");
+    WPT_CUDA(s->bSph.upload(h.devSphPrim.data(), h.devSphPrim.size() * sizeof(float)), "upload spheres");
+    WPT_CUDA(s->bSphClass.upload(h.devSphClassPrim.data(), h.devSphClassPrim.size()), "upload sphere material classes");
+    WPT_CUDA(s->bHot.upload(h.hotSpotIds.data(), h.hotSpotIds.size() * sizeof(uint32_t)), "upload hot spot ids");
+    WPT_CUDA(s->node4.reserve(size_t(n) * sizeof(wpt::Node4)), "allocate wide nodes");
+    WPT_CUDA(s->tri.reserve(nTri * 12 * sizeof(float)), "allocate triangles");
+    WPT_CUDA(s->triShade.reserve(nTri * 4 * sizeof(uint32_t)), "allocate triangle shading records");
+    WPT_CUDA(s->triClass.reserve(nTri), "allocate triangle material classes");
+    WPT_CUDA(s->triGlobal.reserve(nTri * sizeof(uint32_t)), "allocate triangle ids");
+    WPT_CUDA(s->sph.reserve(nSph * 12 * sizeof(float)), "allocate spheres");
+    WPT_CUDA(s->sphClass.reserve(nSph), "allocate sphere material classes");
+    WPT_CUDA(s->sphGlobal.reserve(nSph * sizeof(uint32_t)), "allocate sphere ids");
+    WPT_CUDA(s->hotRefs.reserve(h.hotSpotIds.size() * sizeof(uint32_t)), "allocate hot spots");
+    WPT_CUDA(s->bnode.reserve(64), "allocate binary nodes");
+    WPT_CUDA(s->med.reserve(64), "allocate media");
+    WPT_CUDA(s->medGlobal.reserve(64), "allocate medium ids");
+    WPT_CUDA(s->medClass.reserve(64), "allocate medium classes");
+    WPT_CUDA(s->bScratch.reserve(wptd::deviceBuildScratchBytes(n)), "allocate build scratch");
+    wptd::BuildIO io;
+    io.n = n;
+    io.box = s->bBox.as<float4>();
+    io.triPrim = s->bTri.as<float4>();
+    io.triShadePrim = s->bTriShade.as<uint4>();
+    io.triClassPrim = s->bTriClass.as<uint8_t>();
+    io.sphPrim = s->bSph.as<float4>();
+    io.sphClassPrim = s->bSphClass.as<uint8_t>();
+    io.hotPrims = s->bHot.as<uint32_t>();
+    io.nHot = uint32_t(h.hotSpotIds.size());
+    io.node4 = static_cast<float4*>(s->node4.p);
+    io.tri = static_cast<float4*>(s->tri.p);
+    io.triShade = static_cast<uint4*>(s->triShade.p);
+    io.triClass = static_cast<uint8_t*>(s->triClass.p);
+    io.triGlobal = static_cast<uint32_t*>(s->triGlobal.p);
+    io.sph = static_cast<float4*>(s->sph.p);
+    io.sphClass = static_cast<uint8_t*>(s->sphClass.p);
+    io.sphGlobal = static_cast<uint32_t*>(s->sphGlobal.p);
+    io.hotRefs = static_cast<uint32_t*>(s->hotRefs.p);
+    WPT_CUDA(wptd::launchDeviceBuild(io, s->bScratch.p, h.wideLeafTriangles, 0, wideNodes, depth, triangles), "device tree build");
+    WPT_CUDA(cudaDeviceSynchronize(), "device tree build");
+    s->uploadSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    return WPT_OK;
+}
+
+int wpt_scene_set_builder(wpt_scene* s, int builder)
+{
+    if (!s)
+        return fail(WPT_E_INVALID, "null scene");
+    if (builder != WPT_BUILDER_HOST_SAH && builder != WPT_BUILDER_DEVICE_LBVH)
+        return fail(WPT_E_INVALID, "unknown builder");
+    s->builder = builder;
+    return WPT_OK;
+}
+
 int wpt_scene_update_bvh(wpt_scene* s, float t0, float t1)
 {
     if (!s)
         return fail(WPT_E_INVALID, "null scene");
     if (s->device != WPT_DEVICE_NONE)
         WPT_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
-    int rc = s->host.updateBvh(t0, t1);     /* built once on the host, uploaded to every device */
+    int rc = WPT_OK;
+    if (s->device != WPT_DEVICE_NONE && s->builder == WPT_BUILDER_DEVICE_LBVH) {
+        /* bounds on the host, tree and slot order on every device */
+        auto start = std::chrono::steady_clock::now();
+        rc = s->host.prepareDeviceBuild(t0, t1);
+        if (rc == WPT_OK) {
+            uint32_t wideNodes = 0, depth = 0, triangles = 0;
+            rc = buildOnDevice(s, &wideNodes, &depth, &triangles);
+            for (size_t i = 0; i < s->replicas.size() && rc == WPT_OK; i++)
+                rc = buildOnDevice(s->replicas[i].get(), &wideNodes, &depth, &triangles);
+            if (rc != WPT_OK)
+                return rc;
+            s->host.finishDeviceBuild(t0, t1, wideNodes, depth, triangles,
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count());
+            refreshDeviceScene(s);
+            for (auto& r : s->replicas)
+                refreshDeviceScene(r.get());
+            WPT_CUDA(cudaSetDevice(s->device), "cudaSetDevice");
+            return WPT_OK;
+        }
+        if (rc != WPT_E_UNSUPPORTED)
+            return fail(rc, s->host.error);
+        /* media (nested boundary trees) or fewer than two hitables: the host builder */
+    }
+    rc = s->host.updateBvh(t0, t1);     /* built once on the host, uploaded to every device */
     if (rc != WPT_OK)
         return fail(rc, s->host.error);
     if (s->device == WPT_DEVICE_NONE)
@@ -673,11 +768,11 @@ int wpt_scene_get_info(const wpt_scene* s, wpt_scene_info* info)
     std::memset(info, 0, sizeof(*info));
     const wpt::HostScene& h = s->host;
     info->hitables = h.topLevel.size();
-    info->triangles = h.triGlobal.size();
-    info->spheres = h.sphGlobal.size();
+    info->triangles = h.nTriSlots;
+    info->spheres = h.nSphSlots;
     info->media = h.medGlobal.size();
     info->binary_nodes = h.topLevelNodes;
-    info->wide_nodes = h.nodes4.size();
+    info->wide_nodes = h.nWideNodes;
     info->binary_depth = h.binaryDepth;
     info->wide_depth = h.wideDepth;
     info->hot_spots = uint32_t(h.hotSpotIds.size());
@@ -708,6 +803,8 @@ int wpt_scene_get_binary_nodes(const wpt_scene* s, uint64_t capacity, float* box
     const wpt::HostScene& h = s->host;
     if (!h.haveBvh)
         return fail(WPT_E_STATE, "wpt_scene_update_bvh() has not been called");
+    if (h.deviceBuilt)
+        return fail(WPT_E_UNSUPPORTED, "the tree was built on the device: there is no binary tree in the reference's layout");
     if (capacity < h.topLevelNodes)
         return fail(WPT_E_INVALID, "capacity too small");
     for (uint64_t i = 0; i < h.topLevelNodes; i++) {
@@ -804,6 +901,9 @@ static int renderSingle(wpt_scene* s, const wpt_camera_desc* camera, const wpt_s
         P.traversal = WPT_TRAVERSAL_REFERENCE;  /* the ordered walk needs a positive lower bound */
     if (P.traversal == WPT_TRAVERSAL_WIDE && 3 * s->host.wideDepth + 1 > wptd::wideStackEntries())
         P.traversal = WPT_TRAVERSAL_REFERENCE;  /* deeper than the wide walk's stack */
+    if (P.traversal == WPT_TRAVERSAL_REFERENCE && s->host.deviceBuilt)
+        return fail(WPT_E_UNSUPPORTED, "this tree was built on the device (WPT_BUILDER_DEVICE_LBVH): the reference-order walk needs the "
+                "host builder's binary tree; it is also what a non-positive minimum hit distance or a very deep tree falls back to");
 
     /* sub-streams per pixel: enough lanes to fill the GPU a few times over */
     uint32_t sub = 1;
@@ -1108,6 +1208,9 @@ static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width,
     P.traversal = o.traversal;
     if (o.traversal != WPT_TRAVERSAL_REFERENCE && (!(minHit > 0.0f) || 3 * s->host.wideDepth + 1 > wptd::wideStackEntries()))
         P.traversal = WPT_TRAVERSAL_REFERENCE;
+    if (P.traversal == WPT_TRAVERSAL_REFERENCE && s->host.deviceBuilt)
+        return fail(WPT_E_UNSUPPORTED, "this tree was built on the device (WPT_BUILDER_DEVICE_LBVH): the reference-order walk needs the "
+                "host builder's binary tree; it is also what a non-positive minimum hit distance or a very deep tree falls back to");
     if (P.traversal == WPT_TRAVERSAL_POOL && (!s->d.simpleWalk || counters))
         return fail(WPT_E_UNSUPPORTED, "WPT_TRAVERSAL_POOL: the pooled trace kernel serves scenes without media and animated "
                 "hitables, and does not count node visits");
@@ -1225,6 +1328,9 @@ int wpt_get_ground_truth(wpt_scene* s, const wpt_camera_desc* camera, uint32_t w
     P.traversal = (o.traversal == WPT_TRAVERSAL_REFERENCE ? WPT_TRAVERSAL_REFERENCE : WPT_TRAVERSAL_WIDE);
     if (P.traversal == WPT_TRAVERSAL_WIDE && (!(minHitDistance > 0.0f) || 3 * s->host.wideDepth + 1 > wptd::wideStackEntries()))
         P.traversal = WPT_TRAVERSAL_REFERENCE;
+    if (P.traversal == WPT_TRAVERSAL_REFERENCE && s->host.deviceBuilt)
+        return fail(WPT_E_UNSUPPORTED, "this tree was built on the device (WPT_BUILDER_DEVICE_LBVH): the reference-order walk needs the "
+                "host builder's binary tree; it is also what a non-positive minimum hit distance or a very deep tree falls back to");
 
     wptd::GroundTruthParams G;
     std::memset(&G, 0, sizeof(G));

@@ -804,10 +804,102 @@ int HostScene::updateBvh(float t0, float t1)
     for (uint8_t c : medClass) classMask |= 1u << c;
 
     haveBvh = true;
+    deviceBuilt = false;
+    nTriSlots = triGlobal.size();
+    nSphSlots = sphGlobal.size();
+    nWideNodes = nodes4.size();
     bvhT0 = t0;
     bvhT1 = t1;
     buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     return WPT_OK;
+}
+
+/* ------------------------------------------------------ device builder, host part */
+
+int HostScene::prepareDeviceBuild(float t0, float t1)
+{
+    if (!media.empty() || prims.size() < 2 || topLevel.size() != prims.size() || prims.size() >= (1u << RUN_COUNT_SHIFT))
+        return WPT_E_UNSUPPORTED;
+    BoundsContext ctx(*this, t0, t1);
+    const size_t n = prims.size();
+    /* index of every hitable among the hitables of its type */
+    std::vector<uint32_t> typeIndex(n);
+    uint32_t nTri = 0, nSph = 0;
+    for (size_t i = 0; i < n; i++)
+        typeIndex[i] = (prims[i].type == PRIM_TRIANGLE ? nTri++ : nSph++);
+    if (vertices.size() >= (size_t(1) << 32)) {
+        error = "more than 2^32 vertex attribute floats";
+        return WPT_E_INVALID;
+    }
+    auto bits = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+    devBox.resize(n * 8);
+    devTriPrim.resize(size_t(nTri) * 12);
+    devTriShadePrim.resize(size_t(nTri) * 4);
+    devTriClassPrim.resize(nTri);
+    devSphPrim.resize(size_t(nSph) * 12);
+    devSphClassPrim.resize(nSph);
+    std::vector<uint8_t> classOfMaterial(materials.size());
+    for (size_t m = 0; m < materials.size(); m++)
+        classOfMaterial[m] = materialClass(int32_t(m));
+    auto cls = [&](int32_t material) { return material >= 0 && size_t(material) < classOfMaterial.size() ? classOfMaterial[material] : uint8_t(0); };
+    uint32_t mask = 0;
+    #pragma omp parallel for schedule(static) reduction(|:mask)
+    for (size_t i = 0; i < n; i++) {
+        const Prim& p = prims[i];
+        const uint32_t ti = typeIndex[i];
+        Box b;
+        if (p.type == PRIM_TRIANGLE) {
+            b = ctx.triangleBox(p);
+            V3 v[3];
+            ctx.triangleCorners(p, v);
+            const wpt_instance& in = instances[p.ref];
+            float* d = devTriPrim.data() + size_t(ti) * 12;
+            d[0] = v[0].x; d[1] = v[0].y; d[2] = v[0].z; d[3] = bits(p.ref);
+            d[4] = v[1].x; d[5] = v[1].y; d[6] = v[1].z; d[7] = bits(p.tri);
+            d[8] = v[2].x; d[9] = v[2].y; d[10] = v[2].z; d[11] = bits(uint32_t(in.animation + 1));
+            const wpt_mesh& mesh = meshes[in.mesh];
+            const uint32_t* ix = indices.data() + mesh.index_offset + size_t(p.tri) * 3;
+            uint32_t* sh = devTriShadePrim.data() + size_t(ti) * 4;
+            for (int k = 0; k < 3; k++)
+                sh[k] = uint32_t(mesh.vertex_offset + size_t(ix[k]) * mesh.vertex_stride);
+            sh[3] = mesh.flags;
+            devTriClassPrim[ti] = cls(in.material);
+            mask |= 1u << devTriClassPrim[ti];
+        } else {
+            b = ctx.sphereBox(p);
+            const wpt_sphere& sp = spheres[p.ref];
+            float* d = devSphPrim.data() + size_t(ti) * 12;
+            d[0] = sp.center[0]; d[1] = sp.center[1]; d[2] = sp.center[2]; d[3] = sp.radius;
+            d[4] = sp.rotation[0]; d[5] = sp.rotation[1]; d[6] = sp.rotation[2]; d[7] = sp.rotation[3];
+            d[8] = bits(uint32_t(sp.material)); d[9] = bits(uint32_t(sp.animation + 1)); d[10] = 0.0f; d[11] = 0.0f;
+            devSphClassPrim[ti] = cls(sp.material);
+            mask |= 1u << devSphClassPrim[ti];
+        }
+        float* o = devBox.data() + i * 8;
+        o[0] = b.lo.x; o[1] = b.lo.y; o[2] = b.lo.z; o[3] = bits(p.type);
+        o[4] = b.hi.x; o[5] = b.hi.y; o[6] = b.hi.z; o[7] = bits(ti);
+    }
+    classMask = mask;
+    nTriSlots = nTri;
+    nSphSlots = nSph;
+    return WPT_OK;
+}
+
+void HostScene::finishDeviceBuild(float t0, float t1, uint32_t wideNodes, uint32_t depth, uint32_t triangles, double seconds)
+{
+    (void)triangles;
+    haveBvh = true;
+    deviceBuilt = true;
+    bvhT0 = t0;
+    bvhT1 = t1;
+    root4 = 0;
+    wideDepth = depth;
+    nWideNodes = wideNodes;
+    binaryDepth = 0;
+    topLevelNodes = 0;
+    bnodes.clear();
+    nodes4.clear();
+    buildSeconds = seconds;
 }
 
 }

@@ -104,6 +104,15 @@ struct HostScene {
     uint32_t classMask = 0;                 /* classes present */
     uint8_t materialClass(int32_t material) const;
     double buildSeconds = 0.0;
+    uint64_t nTriSlots = 0, nSphSlots = 0, nWideNodes = 0;  /* sizes of the device arrays (either builder) */
+
+    /* ---- inputs of the device builder (bvh_device.cu), in hitable order ---- */
+    bool deviceBuilt = false;               /* the current tree was built on the device: there is no binary tree */
+    std::vector<float> devBox;              /* 8 floats per hitable: lo xyz | type, hi xyz | index among its type */
+    std::vector<float> devTriPrim;          /* 12 floats per triangle (hitable order) */
+    std::vector<uint32_t> devTriShadePrim;  /* 4 words per triangle */
+    std::vector<uint8_t> devTriClassPrim, devSphClassPrim;
+    std::vector<float> devSphPrim;          /* 12 floats per sphere */
 
     std::string error;
 
@@ -112,6 +121,13 @@ struct HostScene {
 
     /* Scene::updateBVH(t0, t1). */
     int updateBvh(float t0, float t1);
+
+    /* The host part of Scene::updateBVH(t0, t1) when the tree is built on the device: bounds of every hitable
+     * over [t0,t1] and the primitive data in hitable order. WPT_E_UNSUPPORTED (no message): this scene needs the
+     * host builder (media with nested boundary trees, fewer than two hitables). */
+    int prepareDeviceBuild(float t0, float t1);
+    /* Book-keeping after launchDeviceBuild(). */
+    void finishDeviceBuild(float t0, float t1, uint32_t wideNodes, uint32_t depth, uint32_t triangles, double seconds);
 
     /* AnimationKeyframes::at(t) (animation_keyframes.hpp:191-215) for scene animation `index`. */
     Trs animationAt(int index, float t) const;
