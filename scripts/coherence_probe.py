@@ -34,10 +34,9 @@ def main():
     view = scenes.View("synth")
     scene = capi.Scene(built.desc, device=0).update_bvh(view.t0, view.t1)
     built.close()
-    gt = scene.ground_truth(view.camera, w, h, view.t0, bits=abi.WPT_GT_WORLD_POSITIONS | abi.WPT_GT_WORLD_GEOMETRY_NORMALS)
-    names = list(gt.keys())
-    pos = gt[names[0]].reshape(-1, 3)
-    nrm = gt[names[1]].reshape(-1, 3)
+    gt = scene.ground_truth(view.camera, w, h, view.t0, bits=3)      # world positions, world geometry normals
+    pos = gt["world_positions"].reshape(-1, 3)
+    nrm = gt["world_geometry_normals"].reshape(-1, 3)
     ok = np.linalg.norm(nrm, axis=1) > 0.5
     pos, nrm = pos[ok], nrm[ok]
     n = pos.shape[0]

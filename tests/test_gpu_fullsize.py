@@ -93,3 +93,43 @@ def test_ods_camera_primary_ids_at_full_resolution(capi, ref):
     rel = np.abs(dist[same] - ra[same]) / ra[same]
     # a direction that differs in the last bits moves the hit point along the surface: more at grazing incidence
     assert np.quantile(rel, 0.999) <= 2e-5 and rel.max() <= 2e-3, (float(np.quantile(rel, 0.999)), float(rel.max()))
+
+
+# name, width, height, reference spp_sqrt, device spp_sqrt, box, tolerance of the channel means, of the box-filtered relRMSE
+FULL_SIZE_RENDERS = [
+    # C1: the Cornell box at its benchmark size; the reference at 36 spp
+    ("cornell", 512, 512, 6, 16, 32, 0.015, 0.05),
+    # C2: rtiow at 1920x1080; the reference at 9 spp (the sky is an emissive sphere: low variance)
+    ("rtiow", 1920, 1080, 3, 8, 64, 0.015, 0.05),
+    # C5: participating media at 512x512; paths are long and the free-flight samples are drawn inside the walk in a
+    # different order than the reference draws them (ordered walk), so only the expectation is shared
+    ("media", 512, 512, 6, 16, 32, 0.03, 0.08),
+]
+
+
+@pytest.mark.parametrize("name,w,h,ref_spp,dev_spp,box,tol_mean,tol_rmse", FULL_SIZE_RENDERS)
+def test_full_size_render_agrees_with_reference_render(capi, ref, name, w, h, ref_spp, dev_spp, box, tol_mean, tol_rmse):
+    """C1, C2 and C5-media at BASELINE.json's image sizes: the device render against the reference's own render of the
+    same view at the sample count the host cores finish in seconds. Both are unbiased estimates of the same image."""
+    from util import box_downsample, rel_rmse
+    if capi.device_count() == 0:
+        pytest.fail("no CUDA device")
+    r = ref.RefScene(name, 1.0, 0)
+    view = ref.View(name)
+    r.update_bvh(view.t0, view.t1)
+    s = capi.Scene(r.desc, device=0).update_bvh(view.t0, view.t1)
+    sensor = view.sensor
+    sensor.width, sensor.height = w, h
+    ref_img, seconds = r.render(view.camera, sensor, view.params, ref_spp, view.t0, view.t1)
+    dev_img, stats = s.render(view.camera, sensor, view.params, dev_spp, view.t0, view.t1)
+    assert stats.samples == w * h * dev_spp * dev_spp
+    m_ref = ref_img.reshape(-1, 3).mean(axis=0)
+    m_dev = dev_img.reshape(-1, 3).mean(axis=0)
+    e = rel_rmse(box_downsample(dev_img, box), box_downsample(ref_img, box), floor=1e-2 * float(m_ref.mean()) ** 2)
+    print("%s %dx%d: reference %d spp in %.1f s; channel means device %s reference %s; %dx%d-box relRMSE %.4f" % (
+        name, w, h, ref_spp * ref_spp, seconds, m_dev, m_ref, box, box, e))
+    assert np.isfinite(dev_img).all()
+    assert np.all(np.abs(m_dev - m_ref) <= tol_mean * m_ref), (name, m_dev, m_ref)
+    assert e <= tol_rmse, (name, e)
+    s.close()
+    r.close()
