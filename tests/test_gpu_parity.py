@@ -325,3 +325,41 @@ def test_reference_mis_app_runs_unchanged(gpu, tmp_path):
     b = read_wptarray(str(tmp_path / "img-with-multiple-importance-sampling.tgd"))
     assert a.shape == b.shape == (540, 960, 3)
     assert abs(a.mean() - b.mean()) <= 0.05 * b.mean()
+
+
+def test_more_animations_than_cache_entries_with_motion_blur(gpu):
+    """The per-thread animation cache (AnimationCache, animation.hpp:52-125) has 16 entries; animations beyond the
+    first 15 share the last one. A copy of the ToF scene whose hitables use copies number 17.. and 18.. of the two
+    animations must render the same frame as the original, with an exposure interval (every thread evaluates the key
+    frames at its ray's time)."""
+    import ctypes as C
+    from wurblpt_b200 import scene_desc as sd
+    g = Golden("tof")
+    arrays = {k: v.copy() for k, v in g.host.arrays.items()}
+    n_anim = g.desc.n_animations
+    assert n_anim >= 1
+    copies = 10
+    arrays["animations"] = np.tile(arrays["animations"], copies)
+    inst = sd.struct_view(arrays["instances"], abi.wpt_instance)
+    moved = 0
+    for i in range(len(inst)):
+        if inst[i].animation >= 0:
+            inst[i].animation += n_anim * (copies - 1 - (i % 2))      # the last two copies, alternating
+            moved += 1
+    sph = sd.struct_view(arrays["spheres"], abi.wpt_sphere)
+    for i in range(len(sph)):
+        if sph[i].animation >= 0:
+            sph[i].animation += n_anim * (copies - 1)
+    assert moved > 0 and n_anim * (copies - 1) >= 16
+    many = sd.HostScene(arrays)
+    t0, t1 = g.t0, g.t0 + 0.02
+    sensor = g.sensor
+    sensor.height, sensor.width = g.z["render"].shape[:2]
+    frames = []
+    for desc in (g.desc, many.desc):
+        s = gpu.Scene(desc, device=0).update_bvh(t0, t1)
+        f, _ = s.render(g.camera, sensor, g.params, 6, t0, t1, gpu.make_opts(substreams=1))
+        frames.append(f)
+        s.close()
+    assert np.isfinite(frames[0]).all() and frames[0].mean() > 0
+    assert np.array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32))

@@ -138,6 +138,7 @@ struct wpt_scene {
     DeviceBuf counters, camKeys, frame, partials, wave[17], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds, animTable, poolSpill, sharedCounter, blockDone, peerStage;
     /* device builder: inputs in hitable order, scratch */
     DeviceBuf bBox, bTri, bTriShade, bTriClass, bSph, bSphClass, bHot, bScratch;
+    DeviceBuf waveBin[4];       /* ray cells, binned trace queue, bin counters, bin offsets + cursors */
     int builder = WPT_BUILDER_HOST_SAH;
     cudaEvent_t evStart = nullptr, evStop = nullptr, evWave[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaStream_t stream2 = nullptr;
@@ -280,6 +281,16 @@ void refreshDeviceScene(wpt_scene* s)
     d.sphClass = s->sphClass.as<uint8_t>();
     d.medClass = s->medClass.as<uint8_t>();
     d.classMask = h.classMask;
+    {
+        const float lo[3] = { h.sceneLo[0], h.sceneLo[1], h.sceneLo[2] };
+        float scale[3];
+        for (int k = 0; k < 3; k++) {
+            const float extent = h.sceneHi[k] - h.sceneLo[k];
+            scale[k] = (extent > 0.0f && std::isfinite(extent)) ? float(wptd::RAY_CELLS) / extent : 0.0f;
+        }
+        d.cellLo = make_float3(lo[0], lo[1], lo[2]);
+        d.cellScale = make_float3(scale[0], scale[1], scale[2]);
+    }
     d.simpleWalk = (s->sceneHasMedia || s->sceneHasAnimation || h.root4 == 0x7FFFFFFF) ? 0 : 1;   /* (an empty scene has no root) */
     d.materials = s->materials.as<wpt_material>();
     d.instances = s->instances.as<wpt_instance>();
@@ -362,6 +373,16 @@ int defaultPipeline()
 #define WPT_ITEMS_PER_SLOT 4u
 #endif
 
+bool waveBinning()
+{
+    /* Opt-in (WPT_WAVE_BIN=1): the bounce / shadow queries are handed to the trace kernel grid cell by grid cell. The walk
+     * itself gains (+22 ... +33 % rays/s in the query kernel, profiles/r2l_coherence_probe.txt), but the queries of a
+     * warp then belong to slots all over the 1.9 GB of path state (ray loads and answer stores lose their locality) and
+     * the counting sort costs two passes over the queue: C3 660 vs 696 Msamples/s, C1 448 vs 582 (profiles/r2m_bin_ab.txt). */
+    const char* e = std::getenv("WPT_WAVE_BIN");
+    return e && e[0] == '1';
+}
+
 uint32_t waveSlotLimit()
 {
     const char* e = std::getenv("WPT_WAVE_SLOTS");
@@ -403,9 +424,7 @@ int launchScene(wpt_scene* s, float t0, float t1, cudaStream_t stream, wptd::DSc
         d.animTable = s->animTable.as<float>();
         return WPT_OK;
     }
-    if (n > size_t(wptd::MAX_CACHED_ANIMATIONS))
-        return fail(WPT_E_UNSUPPORTED, "more than " + std::to_string(wptd::MAX_CACHED_ANIMATIONS)
-                + " scene animations are only supported for t0 == t1 (no motion blur)");
+    /* (more than MAX_CACHED_ANIMATIONS - 1 animations: the others share the cache's last entry, device_trace.cuh) */
     return WPT_OK;
 }
 
@@ -1030,6 +1049,20 @@ static int renderSingle(wpt_scene* s, const wpt_camera_desc* camera, const wpt_s
         WPT_CUDA(cudaMemsetAsync(s->wave[W_WINDOW].p, 0, windows * sizeof(uint2), stream), "clear window state");
         P.W.window = static_cast<uint2*>(s->wave[W_WINDOW].p);
         P.W.group = 0;
+        P.W.cell = nullptr;
+        P.W.sortedQueue = nullptr;
+        P.W.binCount = P.W.binBase = nullptr;
+        if (waveBinning()) {
+            WPT_CUDA(s->waveBin[0].reserve(n * sizeof(uint16_t)), "allocate ray cells");
+            WPT_CUDA(s->waveBin[1].reserve(2 * n * sizeof(uint32_t)), "allocate binned trace queue");
+            WPT_CUDA(s->waveBin[2].reserve(size_t(2) * wptd::RAY_BINS * sizeof(uint32_t)), "allocate bin counters");
+            WPT_CUDA(s->waveBin[3].reserve(size_t(4) * wptd::RAY_BINS * sizeof(uint32_t)), "allocate bin offsets");
+            WPT_CUDA(cudaMemsetAsync(s->waveBin[2].p, 0, size_t(2) * wptd::RAY_BINS * sizeof(uint32_t), stream), "clear bin counters");
+            P.W.cell = static_cast<uint16_t*>(s->waveBin[0].p);
+            P.W.sortedQueue = static_cast<uint32_t*>(s->waveBin[1].p);
+            P.W.binCount = static_cast<uint32_t*>(s->waveBin[2].p);
+            P.W.binBase = static_cast<uint32_t*>(s->waveBin[3].p);
+        }
         if (s->d.simpleWalk) {
             rc = reservePoolSpill(s, P);
             if (rc != WPT_OK)

@@ -78,13 +78,15 @@ struct DScene {
     int32_t prefetchLeaves;     /* triangle data is larger than an SM's L1: ask for a leaf's triangles on arrival */
     uint32_t classMask;         /* bit c: some hitable of the scene has material class c */
     int32_t simpleWalk;         /* no media, no animated hitables: a walk needs no Prng and no animation cache */
+    float3 cellLo, cellScale;   /* grid of RAY_CELLS^3 cells over the scene's box: cell = (p - cellLo) * cellScale */
     uint32_t nHot;
     uint32_t nAnimations;
     int32_t envType, envCompat, envN;
     int32_t envTex[6];
 };
 
-constexpr int MAX_CACHED_ANIMATIONS = 16;   /* per-thread animation cache entries (AnimationCache), filled lazily */
+constexpr int MAX_CACHED_ANIMATIONS = 16;   /* per-thread animation cache entries (AnimationCache), filled lazily; the last
+                                               one is shared by all animations beyond the first 15 */
 
 /* Wavefront slot arrays (structure of arrays). The kernels reach the slots through queues, i.e. in
  * scattered order, so fields that are always used together are interleaved in pairs that fill one
@@ -114,11 +116,19 @@ struct WaveState {
     uint32_t* traceQueue;   /* 2 * nSlots entries (slot << 1 | query) filled by the generate kernel: camera rays
                                from the front, bounce and shadow rays from the back */
     uint2* window;      /* per window of WAVE_WINDOW slots: the block of work items it hands out (next, end) */
+    /* Binning of the bounce and shadow queries by the grid cell of their origin (rays that start close to each other
+     * walk the same part of the tree): nullptr = the trace kernel takes them in the order the windows listed them. */
+    uint16_t* cell;         /* per slot: Morton number of the cell of rayO (written with the queries) */
+    uint32_t* sortedQueue;  /* the bounce / shadow part of the trace queue, bin by bin */
+    uint32_t* binCount;     /* RAY_BINS counters (generate kernel), zeroed by the scan kernel */
+    uint32_t* binBase;      /* RAY_BINS start offsets + RAY_BINS cursors (scan / scatter kernels) */
     uint32_t nSlots;
     uint32_t group;     /* slot group (0 or 1): selects the group's trace ticket / queue length counters */
     uint32_t queueStride;
 };
 constexpr uint32_t WAVE_WINDOW = 256;       /* slots per window = work items per block */
+constexpr uint32_t RAY_CELLS = 32;          /* grid cells per axis for the binning of queries */
+constexpr uint32_t RAY_BINS = RAY_CELLS * RAY_CELLS * RAY_CELLS * 2;   /* cell x (path segment | shadow ray) */
 
 /* Material classes of the shading queues: a class has a kernel of its own in which the material type is a
  * compile-time constant. Everything else (lights, mirrors, phase functions, two-sided materials whose sides differ)

@@ -98,7 +98,8 @@ struct Ctx {
     unsigned int nodes, leaves;
     /* AnimationCache (animation.hpp:52-125): filled lazily, entry by entry, for the time `animTime` */
     mutable float animTime;
-    mutable uint32_t animValid;     /* bit i: entry i holds animation i at animTime */
+    mutable uint32_t animValid;     /* bit e: cache entry e holds an animation at animTime */
+    mutable uint32_t animShared;    /* which animation the last (shared) entry holds */
     mutable Trs animT[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
     mutable Mat34 animM[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
     mutable Mat33 animN[(F & F_ANIM) ? MAX_CACHED_ANIMATIONS : 1];
@@ -162,18 +163,31 @@ WPT_DEV void animationCacheInit(const DScene& S, Ctx<F>& ctx, float t)
     }
 }
 
-template<int F>
-WPT_DEV void animationCacheEnsure(const DScene& S, const Ctx<F>& ctx, uint32_t i)
+/* Cache entry of animation i: the first MAX_CACHED_ANIMATIONS - 1 animations have an entry of their own, all the others
+ * share the last one (it then holds whichever of them was used last: correct for any number of animations, slower when
+ * several of the shared ones alternate). */
+WPT_DEV uint32_t animationCacheEntry(uint32_t i)
 {
-    if (!(ctx.animValid & (1u << i))) {
+    return i < uint32_t(MAX_CACHED_ANIMATIONS - 1) ? i : uint32_t(MAX_CACHED_ANIMATIONS - 1);
+}
+
+template<int F>
+WPT_DEV uint32_t animationCacheEnsure(const DScene& S, const Ctx<F>& ctx, uint32_t i)
+{
+    const uint32_t e = animationCacheEntry(i);
+    const bool shared = (e == uint32_t(MAX_CACHED_ANIMATIONS - 1));
+    if (!(ctx.animValid & (1u << e)) || (shared && ctx.animShared != i)) {
         const wpt_animation an = S.animations[i];
         const Trs T = keyframesAt(S.keyframes + an.first_keyframe, an.keyframe_count, ctx.animTime);
         const Mat33 N = toMat33(T.r);
-        ctx.animT[i] = T;
-        ctx.animN[i] = N;
-        ctx.animM[i] = toMat34(T, N);
-        ctx.animValid |= (1u << i);
+        ctx.animT[e] = T;
+        ctx.animN[e] = N;
+        ctx.animM[e] = toMat34(T, N);
+        ctx.animValid |= (1u << e);
+        if (shared)
+            ctx.animShared = i;
     }
+    return e;
 }
 
 /* Transformation of animation `anim` (1-based, as stored with the primitives) at the thread's current time:
@@ -189,24 +203,21 @@ WPT_DEV Trs animTrs(const DScene& S, const Ctx<F>& ctx, uint32_t anim)
         T.s = f3(e[7], e[8], e[9]);
         return T;
     }
-    animationCacheEnsure<F>(S, ctx, anim - 1u);
-    return ctx.animT[anim - 1u];
+    return ctx.animT[animationCacheEnsure<F>(S, ctx, anim - 1u)];
 }
 template<int F>
 WPT_DEV const float* animMatrix(const DScene& S, const Ctx<F>& ctx, uint32_t anim)
 {
     if (S.animTable)
         return S.animTable + size_t(anim - 1u) * 32u + 10u;
-    animationCacheEnsure<F>(S, ctx, anim - 1u);
-    return ctx.animM[anim - 1u].m;
+    return ctx.animM[animationCacheEnsure<F>(S, ctx, anim - 1u)].m;
 }
 template<int F>
 WPT_DEV const float* animNormalMatrix(const DScene& S, const Ctx<F>& ctx, uint32_t anim)
 {
     if (S.animTable)
         return S.animTable + size_t(anim - 1u) * 32u + 22u;
-    animationCacheEnsure<F>(S, ctx, anim - 1u);
-    return ctx.animN[anim - 1u].m;
+    return ctx.animN[animationCacheEnsure<F>(S, ctx, anim - 1u)].m;
 }
 
 /* ------------------------------------------------------------ ray / triangle */

@@ -306,9 +306,23 @@ WPT_DEV uint4 forkPrng(Prng& prng)
     return make_uint4(uint32_t(s01 >> 32), uint32_t(s01), uint32_t(s23 >> 32), uint32_t(s23));
 }
 
+/* Morton number (15 bits) of the grid cell of a point: the binning key of the queries that start there. */
+WPT_DEV unsigned int rayCell(const DScene& S, float3 p)
+{
+    const float top = float(RAY_CELLS) - 1.0f;
+    const unsigned int x = (unsigned int)fminf(fmaxf((p.x - S.cellLo.x) * S.cellScale.x, 0.0f), top);
+    const unsigned int y = (unsigned int)fminf(fmaxf((p.y - S.cellLo.y) * S.cellScale.y, 0.0f), top);
+    const unsigned int z = (unsigned int)fminf(fmaxf((p.z - S.cellLo.z) * S.cellScale.z, 0.0f), top);
+    unsigned int key = 0;
+#pragma unroll
+    for (int b = 0; b < 5; b++)
+        key |= (((x >> b) & 1u) << (3 * b + 2)) | (((y >> b) & 1u) << (3 * b + 1)) | (((z >> b) & 1u) << (3 * b));
+    return key;
+}
+
 /* ITEM: the work item's fields may have changed (generate kernel). `fresh`: see slotCode(). */
 template<int F, bool ITEM>
-WPT_DEV void storeSlot(const RenderParams& P, unsigned int slot, PathState& ps, Ctx<F>& ctx, bool fresh)
+WPT_DEV void storeSlot(const DScene& S, const RenderParams& P, unsigned int slot, PathState& ps, Ctx<F>& ctx, bool fresh)
 {
     if (ITEM)
         P.W.item[slot] = make_int4(int(ps.pixel), int(ps.sampleIndex), int(ps.sub), 0);
@@ -323,6 +337,8 @@ WPT_DEV void storeSlot(const RenderParams& P, unsigned int slot, PathState& ps, 
     if (ps.state == ST_NEW)
         return;     /* path ended: the generate kernel starts the next sample */
     P.W.rayO[2 * slot] = f4(ps.walkRay.o, ps.walkRay.time);
+    if (!ITEM && P.W.cell)
+        P.W.cell[slot] = uint16_t(rayCell(S, ps.walkRay.o));
     if (ps.state == ST_MAIN) {
         P.W.rayD[2 * slot] = f4(ps.walkRay.d, ps.pathLength);
         P.W.att[slot] = ps.att;
@@ -348,7 +364,28 @@ WPT_DEV unsigned long long* ctrTraceOther(const RenderParams& P) { return P.coun
 /* Entry p of the trace queue (camera rays from the front, the others from the back): slot << 1 | query (0 = B, 1 = S). */
 WPT_DEV unsigned int traceQueueEntry(const RenderParams& P, unsigned int p, unsigned int nCamera)
 {
-    return p < nCamera ? P.W.traceQueue[p] : P.W.traceQueue[2u * P.W.nSlots - 1u - (p - nCamera)];
+    if (p < nCamera)
+        return P.W.traceQueue[p];
+    return P.W.sortedQueue ? P.W.sortedQueue[p - nCamera] : P.W.traceQueue[2u * P.W.nSlots - 1u - (p - nCamera)];
+}
+
+/* Adds one to the counter of every lane's bin (lanes with `valid`), one atomic per distinct bin of the warp; returns
+ * the lane's rank among the warp's lanes of the same bin plus the counter's value before the warp's add. */
+WPT_DEV unsigned int binAdd(uint32_t* counters, unsigned int bin, bool valid)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned active = __ballot_sync(0xFFFFFFFFu, valid);
+    unsigned int result = 0;
+    if (valid) {
+        const unsigned peers = __match_any_sync(active, bin);
+        const int leader = __ffs(peers) - 1;
+        unsigned int base = 0;
+        if (int(lane) == leader)
+            base = atomicAdd(counters + bin, (unsigned int)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        result = base + __popc(peers & ((1u << lane) - 1u));
+    }
+    return result;
 }
 
 WPT_DEV void countSamples(const RenderParams& P, unsigned int newSamples)
@@ -534,7 +571,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
             }
             if (generate || logic) {
                 ps.shadow = SHADOW_NONE;
-                storeSlot<F, true>(P, slot, ps, ctx, false);
+                storeSlot<F, true>(S, P, slot, ps, ctx, false);
                 state = ps.state;
                 shadow = false;
                 pathComponent = 0;
@@ -580,12 +617,74 @@ __global__ void __launch_bounds__(BLOCK, WPT_LOGIC_MIN_BLOCKS) waveGenerateKerne
     otherBase = __shfl_sync(FULL, otherBase, 0);
     for (unsigned int e = lane; e < nCam; e += 32u)
         P.W.traceQueue[camBase + e] = lists[warp][e];
-    for (unsigned int e = lane; e < nOther; e += 32u)
-        P.W.traceQueue[2u * P.W.nSlots - 1u - (otherBase + e)] = lists[warp][nCam + e];
+    for (unsigned int e0 = 0; e0 < nOther; e0 += 32u) {
+        const unsigned int e = e0 + lane;
+        const bool valid = e < nOther;
+        const unsigned int entry = valid ? lists[warp][nCam + e] : 0u;
+        if (valid)
+            P.W.traceQueue[2u * P.W.nSlots - 1u - (otherBase + e)] = entry;
+        if (P.W.binCount)      /* how many queries start in each grid cell (bounce and shadow rays apart) */
+            binAdd(P.W.binCount, valid ? ((unsigned int)P.W.cell[entry >> 1] << 1) | (entry & 1u) : 0u, valid);
+    }
     countSamples(P, newSamples);
     const unsigned int r = __reduce_add_sync(FULL, retired);
     if (lane == 0 && r != 0u)
         atomicAdd(P.counters + CTR_DONE, (unsigned long long)r);
+}
+
+/* Binning of the bounce / shadow queries by the grid cell of their origin, after the generate kernel has counted
+ * them per bin: start offset of every bin (one block), then every query goes to the next free place of its bin. The
+ * order inside a bin does not matter (every query is answered on its own). Measured with the query kernel on C3's
+ * bounce rays: +22 ... +33 % rays/s when the rays are taken cell by cell (profiles/r2l_coherence_probe.txt). */
+__global__ void __launch_bounds__(1024) waveBinScanKernel(const __grid_constant__ RenderParams P)
+{
+    __shared__ unsigned int warpSums[32];
+    constexpr unsigned int PER = RAY_BINS / 1024;
+    const unsigned int first = threadIdx.x * PER;
+    unsigned int sum = 0;
+    for (unsigned int k = 0; k < PER; k++)
+        sum += P.W.binCount[first + k];
+    unsigned int x = sum;
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, x, off);
+        if ((threadIdx.x & 31u) >= (unsigned)off)
+            x += y;
+    }
+    if ((threadIdx.x & 31u) == 31u)
+        warpSums[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned int w = warpSums[threadIdx.x];
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xFFFFFFFFu, w, off);
+            if (threadIdx.x >= (unsigned)off)
+                w += y;
+        }
+        warpSums[threadIdx.x] = w;
+    }
+    __syncthreads();
+    unsigned int run = ((threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u) + x - sum;
+    for (unsigned int k = 0; k < PER; k++) {
+        const unsigned int c = P.W.binCount[first + k];
+        P.W.binBase[first + k] = run;
+        P.W.binBase[RAY_BINS + first + k] = 0u;     /* cursor */
+        P.W.binCount[first + k] = 0u;               /* for the next round's generate kernel */
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(256) waveBinScatterKernel(const __grid_constant__ RenderParams P)
+{
+    const unsigned int nOther = (unsigned int)*ctrTraceOther(P);
+    const unsigned int rounded = (nOther + 31u) & ~31u;
+    for (unsigned int p = blockIdx.x * 256u + threadIdx.x; p < rounded; p += gridDim.x * 256u) {
+        const bool valid = p < nOther;
+        const unsigned int entry = valid ? P.W.traceQueue[2u * P.W.nSlots - 1u - p] : 0u;
+        const unsigned int bin = valid ? ((unsigned int)P.W.cell[entry >> 1] << 1) | (entry & 1u) : 0u;
+        const unsigned int pos = binAdd(P.W.binBase + RAY_BINS, bin, valid);
+        if (valid)
+            P.W.sortedQueue[P.W.binBase[bin] + pos] = entry;
+    }
 }
 
 /* Material: shade the surface hits of camera rays and path segments, one kernel per material class (MC_*; the
@@ -614,7 +713,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_MATERIAL_MIN_BLOCKS) waveMaterialKe
             consumeShadow<F>(S, P, ps, ctx, hitS);
         const RayHelper h = makeRayHelper(ps.walkRay);
         waveShade<F, ClassMaterialType<MC>::value>(S, P, ps, ctx, hitB, h);
-        storeSlot<F, false>(P, slot, ps, ctx, true);
+        storeSlot<F, false>(S, P, slot, ps, ctx, true);
     }
 }
 
@@ -1537,6 +1636,12 @@ static RenderParams slotGroup(const RenderParams& P, uint32_t group, uint32_t fi
     G.W.queue += first;             /* every class's list of the group starts `first` entries into the class's array */
     G.W.traceQueue += 2 * first;
     G.W.window += first / WAVE_WINDOW;
+    if (G.W.cell) {
+        G.W.cell += first;
+        G.W.sortedQueue += 2 * first;
+        G.W.binCount += size_t(group) * RAY_BINS;
+        G.W.binBase += size_t(group) * 2 * RAY_BINS;
+    }
     return G;
 }
 
@@ -1673,6 +1778,11 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
                 waveSortKernel<<<sgrid[g], SORT_BLOCK, 0, st[g]>>>(S, R);
                 n += 3 + launchMaterial<F>(S, R, numSMs, grid[g], st[g]);
                 waveGenerateKernel<F><<<sgrid[g], BLOCK, 0, st[g]>>>(S, R);
+                if (R.W.cell) {
+                    waveBinScanKernel<<<1, 1024, 0, st[g]>>>(R);
+                    waveBinScatterKernel<<<numSMs * 4, 256, 0, st[g]>>>(R);
+                    n += 2;
+                }
             }
         }
         if (nGroups == 2) {     /* join the second stream before reading the counter */

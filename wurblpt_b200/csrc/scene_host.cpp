@@ -805,6 +805,10 @@ int HostScene::updateBvh(float t0, float t1)
 
     haveBvh = true;
     deviceBuilt = false;
+    for (int k = 0; k < 3; k++) {
+        sceneLo[k] = topLevel.empty() ? 0.0f : bnodes[0].lo[k];
+        sceneHi[k] = topLevel.empty() ? 0.0f : bnodes[0].hi[k];
+    }
     nTriSlots = triGlobal.size();
     nSphSlots = sphGlobal.size();
     nWideNodes = nodes4.size();
@@ -882,6 +886,15 @@ int HostScene::prepareDeviceBuild(float t0, float t1)
     classMask = mask;
     nTriSlots = nTri;
     nSphSlots = nSph;
+    for (int k = 0; k < 3; k++) {
+        float lo = devBox[k], hi = devBox[4 + k];
+        for (size_t i = 1; i < n; i++) {
+            lo = std::min(lo, devBox[i * 8 + k]);
+            hi = std::max(hi, devBox[i * 8 + 4 + k]);
+        }
+        sceneLo[k] = lo;
+        sceneHi[k] = hi;
+    }
     return WPT_OK;
 }
 

@@ -105,6 +105,7 @@ struct HostScene {
     uint8_t materialClass(int32_t material) const;
     double buildSeconds = 0.0;
     uint64_t nTriSlots = 0, nSphSlots = 0, nWideNodes = 0;  /* sizes of the device arrays (either builder) */
+    float sceneLo[3] = { 0, 0, 0 }, sceneHi[3] = { 0, 0, 0 };  /* box of the top level (either builder) */
 
     /* ---- inputs of the device builder (bvh_device.cu), in hitable order ---- */
     bool deviceBuilt = false;               /* the current tree was built on the device: there is no binary tree */
