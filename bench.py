@@ -217,6 +217,9 @@ def main():
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--substreams", type=int, default=0)
     ap.add_argument("--pipeline", default="auto", choices=["auto", "megakernel", "wavefront"])
+    ap.add_argument("--work", default="dynamic", choices=["dynamic", "static"],
+                    help="N > 1 ranks: 'dynamic' = every rank draws blocks of work items from one counter in rank 0's GPU "
+                         "memory (CUDA IPC, NVLink); 'static' = rank r renders the tiles r, r+N, ...")
     ap.add_argument("--inprocess", action="store_true",
                     help="one process renders each frame on ALL visible GPUs (wpt_scene_create with WPT_DEVICE_ALL, "
                          "the path the reference's apps take through mcpt()); not for use under torchrun")
@@ -255,8 +258,14 @@ def main():
     host_frame = torch.zeros((height, width, 3), dtype=torch.float32).pin_memory()
     pipeline = {"auto": abi.WPT_PIPELINE_AUTO, "megakernel": abi.WPT_PIPELINE_MEGAKERNEL,
                 "wavefront": abi.WPT_PIPELINE_WAVEFRONT}[args.pipeline]
-    opts = multi.rank_opts(rank, world, substreams=args.substreams, stream=stream.cuda_stream, traversal=args.traversal,
-                           pipeline=pipeline)
+    shared = None
+    if world > 1 and args.work == "dynamic":
+        shared = multi.SharedWork(rank, world, local)
+        opts = capi.make_opts(traversal=args.traversal, substreams=args.substreams, frame_on_device=True,
+                              stream=stream.cuda_stream, pipeline=pipeline)
+    else:
+        opts = multi.rank_opts(rank, world, substreams=args.substreams, stream=stream.cuda_stream, traversal=args.traversal,
+                               pipeline=pipeline)
     # > 126 MB so that node / triangle lines cached in L2 by the previous step are gone
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
 
@@ -268,6 +277,8 @@ def main():
     def step():
         """one mcpt(): clear the rank's frame, render its tiles, combine the frames on rank 0"""
         frame.zero_()
+        if shared:
+            opts.shared_counter = shared.begin_frame(stream.cuda_stream)
         scene.render_device(view.camera, view.sensor, view.params, samples_sqrt, frame.data_ptr(), view.t0, view.t1, opts)
         multi.reduce_frame(frame)
 
@@ -305,8 +316,11 @@ def main():
     l2_flush.fill_(1)
     frame.zero_()
     torch.cuda.synchronize(device)
+    if shared:
+        opts.shared_counter = shared.begin_frame(stream.cuda_stream)
     st = scene.render_device(view.camera, view.sensor, view.params, samples_sqrt, frame.data_ptr(), view.t0, view.t1,
                              opts, want_stats=True)
+    multi.reduce_frame(frame)       # (keeps the frames of the ranks in step: see multi.SharedWork)
     kernel_ms, rays_rank, samples_rank = st.kernel_ms, st.rays, st.samples
     launches_per_step = int(st.launches)
     c = torch.tensor([float(rays_rank), float(samples_rank)], dtype=torch.float64, device=device)
@@ -360,10 +374,15 @@ def main():
         achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
         # DRAM bytes per closest-hit query from the committed ncu capture (all kernels of the step), scaled to
         # this launch's query count like `achieved`; None for workloads without a capture
-        measured = load_json(os.path.join(ROOT, "profiles", "r1_dram_traffic.json"), {}).get(scene_name)
-        traffic = rays_rank * measured["bytes_per_query"] if (measured and launches_per_step > 2) else None
+        measured = load_json(os.path.join(ROOT, "profiles", "r2_issue_work.json"), {}).get(scene_name)
+        traffic = None
+        if measured and measured.get("dram_bytes_per_query") and launches_per_step > 2:
+            traffic = rays_rank * measured["dram_bytes_per_query"]
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src,
+                    "traffic": traffic,
+                    "traffic_source": "committed ncu capture (profiles/r2_issue_work.json: dram bytes of all launches of one frame / "
+                                      "queries), scaled to this launch's query count; not measured in this run",
+                    "peak_source": peak_src,
                     "kernel": "renderKernel (megakernel)" if launches_per_step <= 2 else
                     "one mcpt() = %d launches of waveTracePersistentKernel (dominant, ~65 %% of the time), waveSortKernel, "
                     "waveMaterialKernel, waveGenerateKernel; timed as a whole" % launches_per_step,
@@ -430,6 +449,8 @@ def main():
                    "wide_nodes": int(info.wide_nodes), "device_mb": info.device_bytes / 1e6,
                    "parallelism": ("one process, %d GPU(s): blocks of work items from one device-side counter, frames added "
                                    "device to device" % devices_used) if args.inprocess else
+                   ("%d ranks draw blocks of 256 work items from one counter in rank 0's GPU memory (CUDA IPC over NVLink), "
+                    "one NCCL reduce per frame" % world) if shared else
                    "tiles interleaved over %d GPU(s), one NCCL reduce per frame" % world,
                    "cache": "256 MiB buffer written between timed steps (L2 flush); scene 250 MB > 126 MB L2",
                    "traversal": "wide4" if args.traversal == 0 else "reference-order",

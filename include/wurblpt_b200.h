@@ -332,6 +332,12 @@ typedef struct wpt_render_opts {
     int32_t frame_on_device;    /* `frame` is a device pointer; untouched tiles are left as they are */
     int32_t pipeline;           /* WPT_PIPELINE_* */
     void* stream;               /* cudaStream_t to launch on (NULL = default stream) */
+    void* shared_counter;       /* NULL, or a device pointer to a zeroed 64-bit counter that the GPUs of SEVERAL
+                                   calls rendering the same frame draw their blocks of work items from (memory of this
+                                   device, of a peer, or opened with wpt_ipc_counter_open in another process): the
+                                   MPICoordinator hand-out (mpi.hpp:74-107) as one atomic. tile_stride must be 0 or 1;
+                                   every call renders whatever blocks it draws, into a frame that is zero elsewhere,
+                                   and the frames are added up (one NCCL reduce in bench.py) */
 } wpt_render_opts;
 
 typedef struct wpt_stats {
@@ -397,6 +403,15 @@ int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** scene);
  * devices), submitBlock()'s transfer of finished pixels (mpi.hpp:133-149) is one device-to-device copy of each
  * frame, added on the first device. The other entry points (queries, ground truth) use the first device. */
 
+/* A work-item counter shared by several PROCESSES (one per GPU): 256 bytes of device memory on `device` holding two
+ * counters (offsets 0 and 128, used for alternate frames so that one can be cleared while the other is in use),
+ * exported / imported with CUDA IPC handles (64 bytes). The pointers go into wpt_render_opts::shared_counter. */
+int wpt_ipc_counter_create(int device, void** counters, unsigned char handle[64]);
+int wpt_ipc_counter_open(int device, const unsigned char handle[64], void** counters);
+int wpt_ipc_counter_close(int device, void* counters, int opened);
+/* Zeroes ONE of the two counters (`counter` = counters or counters + 128 bytes) on `stream` (a cudaStream_t). */
+int wpt_ipc_counter_clear(void* counter, void* stream);
+
 /* 1 + the number of replicas (0 for a host-only scene). */
 int wpt_scene_device_count(const wpt_scene* scene);
 
@@ -427,7 +442,16 @@ void wpt_scene_destroy(wpt_scene* scene);
 int wpt_scene_get_binary_nodes(const wpt_scene* scene, uint64_t capacity, float* boxes, uint32_t* link, int32_t* leaf);
 
 /* mcpt() (wurblpt.hpp:279-436): render samples_sqrt^2 paths per pixel into `frame`
- * (w*h*3 floats; host memory unless opts->frame_on_device). `opts` and `stats` may be NULL. */
+ * (w*h*3 floats; host memory unless opts->frame_on_device). `opts` and `stats` may be NULL.
+ *
+ * Concurrency: a scene owns the scratch memory of its calls (counters, path state, queues, staging buffers), so
+ * only ONE call per scene (wpt_render, wpt_primary_hits, wpt_trace_rays, wpt_get_ground_truth) may be in flight
+ * at a time, from any thread or stream; different scenes are independent. With opts->frame_on_device and
+ * stats == NULL the call returns when the work has been queued on opts->stream: synchronise that stream before
+ * the next call on the same scene.
+ * opts->frame_on_device: `frame` is device memory on the scene's (first) device and the caller clears it first;
+ * pixels outside the tiles selected by tile_first / tile_stride are left as they are (that is what lets the frames
+ * of several processes be added up). */
 int wpt_render(wpt_scene* scene, const wpt_camera_desc* camera, const wpt_sensor_desc* sensor,
         const wpt_params* params, uint32_t samples_sqrt, float t0, float t1,
         const wpt_render_opts* opts, float* frame, wpt_stats* stats);

@@ -1,6 +1,7 @@
 """Warp instructions per closest-hit query of a whole frame, from an ncu launch list with instruction counters:
 
-    ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum --clock-control none \
+    ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+        --clock-control none \
         --csv --log-file launches.csv python scripts/one_frame.py synth_profile > frame.json
     python scripts/issue_work.py launches.csv frame.json   ->  profiles/r2_issue_work.json entry + per-kernel shares
 """
@@ -25,10 +26,12 @@ for r in rows:
         agg[k]["launches:" + r[hdr["Metric Name"]]] += 1
     except ValueError:
         pass
+dram = sum(m.get("dram__bytes_read.sum", 0.0) + m.get("dram__bytes_write.sum", 0.0) for m in agg.values())
 inst = sum(m["smsp__inst_executed.sum"] for m in agg.values())
 tinst = sum(m["smsp__thread_inst_executed.sum"] for m in agg.values())
 time_ns = sum(m["gpu__time_duration.sum"] for m in agg.values())
 out = {frame["scene"]: {"warp_instr_per_query": inst / frame["rays"], "lanes_per_instr": tinst / inst,
+                         "dram_bytes_per_query": (dram / frame["rays"]) if dram else None,
                          "queries": frame["rays"], "samples": frame["samples"], "workload": frame["workload"],
                          "kernels": {k: {"launches": int(m["launches:gpu__time_duration.sum"]),
                                          "time_share": m["gpu__time_duration.sum"] / time_ns,

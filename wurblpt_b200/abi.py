@@ -129,7 +129,7 @@ class wpt_params(C.Structure):
 
 class wpt_render_opts(C.Structure):
     _fields_ = [("traversal", i32), ("substreams", i32), ("tile_first", u32), ("tile_stride", u32),
-                ("frame_on_device", i32), ("pipeline", i32), ("stream", C.c_void_p)]
+                ("frame_on_device", i32), ("pipeline", i32), ("stream", C.c_void_p), ("shared_counter", C.c_void_p)]
 
 
 class wpt_stats(C.Structure):

@@ -18,7 +18,8 @@ LIB_PATH = os.environ.get("WPT_LIB") or os.path.join(_HERE, "lib", "libwurblpt_b
 EXPORTS = ["wpt_version", "wpt_last_error", "wpt_device_count", "wpt_abi_sizeof", "wpt_scene_create",
            "wpt_scene_update_bvh", "wpt_scene_get_info", "wpt_scene_destroy", "wpt_scene_get_binary_nodes",
            "wpt_render", "wpt_primary_hits", "wpt_get_ground_truth", "wpt_trace_rays", "wpt_prng_kat",
-           "wpt_planned_device_count", "wpt_scene_device_count", "wpt_scene_set_builder"]
+           "wpt_planned_device_count", "wpt_scene_device_count", "wpt_scene_set_builder",
+           "wpt_ipc_counter_create", "wpt_ipc_counter_open", "wpt_ipc_counter_close", "wpt_ipc_counter_clear"]
 
 _lib = None
 
@@ -61,6 +62,10 @@ def lib():
     L.wpt_prng_kat.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     L.wpt_scene_device_count.argtypes = [C.c_void_p]
     L.wpt_scene_set_builder.argtypes = [C.c_void_p, C.c_int]
+    L.wpt_ipc_counter_create.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
+    L.wpt_ipc_counter_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.wpt_ipc_counter_close.argtypes = [C.c_int, C.c_void_p, C.c_int]
+    L.wpt_ipc_counter_clear.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -74,8 +79,30 @@ def device_count():
     return lib().wpt_device_count()
 
 
+def ipc_counter_create(device):
+    """(device pointer, 64-byte handle) of a pair of work-item counters other processes can open."""
+    p = C.c_void_p()
+    handle = C.create_string_buffer(64)
+    _check(lib().wpt_ipc_counter_create(device, C.byref(p), handle))
+    return p.value, handle.raw
+
+
+def ipc_counter_open(device, handle):
+    p = C.c_void_p()
+    _check(lib().wpt_ipc_counter_open(device, handle, C.byref(p)))
+    return p.value
+
+
+def ipc_counter_close(device, pointer, opened):
+    _check(lib().wpt_ipc_counter_close(device, C.c_void_p(pointer), 1 if opened else 0))
+
+
+def ipc_counter_clear(pointer, stream=None):
+    _check(lib().wpt_ipc_counter_clear(C.c_void_p(pointer), C.c_void_p(stream) if stream else None))
+
+
 def make_opts(traversal=abi.WPT_TRAVERSAL_WIDE, substreams=0, tile_first=0, tile_stride=1,
-              frame_on_device=False, stream=None, pipeline=abi.WPT_PIPELINE_AUTO):
+              frame_on_device=False, stream=None, pipeline=abi.WPT_PIPELINE_AUTO, shared_counter=None):
     o = abi.wpt_render_opts()
     o.pipeline = pipeline
     o.traversal = traversal
@@ -84,6 +111,7 @@ def make_opts(traversal=abi.WPT_TRAVERSAL_WIDE, substreams=0, tile_first=0, tile
     o.tile_stride = tile_stride
     o.frame_on_device = 1 if frame_on_device else 0
     o.stream = stream
+    o.shared_counter = shared_counter
     return o
 
 

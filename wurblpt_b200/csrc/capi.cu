@@ -641,6 +641,65 @@ int wpt_scene_create(const wpt_scene_desc* desc, int device, wpt_scene** out)
     return WPT_OK;
 }
 
+int wpt_ipc_counter_create(int device, void** counters, unsigned char handle[64])
+{
+    if (!counters || !handle)
+        return fail(WPT_E_INVALID, "null argument");
+    int rc = selectDevice(device);
+    if (rc != WPT_OK)
+        return rc;
+    void* p = nullptr;
+    WPT_CUDA(cudaMalloc(&p, 256), "allocate shared counters");
+    WPT_CUDA(cudaMemset(p, 0, 256), "clear shared counters");
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return failCuda(e, "cudaIpcGetMemHandle");
+    }
+    std::memcpy(handle, &h, 64);
+    *counters = p;
+    return WPT_OK;
+}
+
+int wpt_ipc_counter_open(int device, const unsigned char handle[64], void** counters)
+{
+    if (!counters || !handle)
+        return fail(WPT_E_INVALID, "null argument");
+    int rc = selectDevice(device);
+    if (rc != WPT_OK)
+        return rc;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    WPT_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    *counters = p;
+    return WPT_OK;
+}
+
+int wpt_ipc_counter_close(int device, void* counters, int opened)
+{
+    if (!counters)
+        return WPT_OK;
+    int rc = selectDevice(device);
+    if (rc != WPT_OK)
+        return rc;
+    if (opened)
+        WPT_CUDA(cudaIpcCloseMemHandle(counters), "cudaIpcCloseMemHandle");
+    else
+        WPT_CUDA(cudaFree(counters), "free shared counters");
+    return WPT_OK;
+}
+
+int wpt_ipc_counter_clear(void* counter, void* stream)
+{
+    if (!counter)
+        return fail(WPT_E_INVALID, "null counter");
+    WPT_CUDA(cudaMemsetAsync(counter, 0, 8, static_cast<cudaStream_t>(stream)), "clear shared counter");
+    return WPT_OK;
+}
+
 int wpt_scene_device_count(const wpt_scene* s)
 {
     if (!s || s->device == WPT_DEVICE_NONE)
@@ -980,6 +1039,13 @@ static int renderSingle(wpt_scene* s, const wpt_camera_desc* camera, const wpt_s
     WPT_CUDA(cudaMemsetAsync(s->counters.p, 0, wptd::CTR_WORDS * sizeof(unsigned long long), stream), "clear counters");
     P.itemCounter = P.counters + wptd::CTR_ITEM;
     P.blockDone = nullptr;
+    MultiFrame fromOpts;
+    if (!multi && o.shared_counter) {
+        if (o.tile_stride > 1)
+            return fail(WPT_E_INVALID, "shared_counter hands out all work items: tile_stride must be 0 or 1");
+        fromOpts.itemCounter = static_cast<unsigned long long*>(o.shared_counter);
+        multi = &fromOpts;
+    }
     if (multi) {
         /* all devices draw blocks of WAVE_WINDOW work items from one counter; a block holds whole pixels (their
          * sub-streams are consecutive items, at most 128), so this device resolves exactly the pixels of its blocks */

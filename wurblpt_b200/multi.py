@@ -42,6 +42,39 @@ def rank_opts(rank, world, substreams=0, stream=None, traversal=0, frame_on_devi
                           frame_on_device=frame_on_device, stream=stream, pipeline=pipeline)
 
 
+class SharedWork:
+    """Dynamic work distribution over the GPUs of several processes: ONE counter in rank 0's GPU memory that the
+    windows of every rank's kernels draw their blocks of work items from (CUDA IPC handle broadcast once; remote ranks
+    reach it over NVLink). This is the MPICoordinator hand-out (reference mpi.hpp:74-107) without the messages: a GPU
+    that is done early simply draws more. Two counters are used for alternate frames: rank 0 clears the one of the NEXT
+    frame at the start of every frame, which is safe because the frame reduce separates the frames (no rank can
+    start frame k+1 before rank 0 has entered the reduce of frame k, which follows the clear on its stream)."""
+
+    def __init__(self, rank, world, device_index):
+        import torch.distributed as dist
+        self.rank, self.world, self.device = rank, world, device_index
+        self.step = 0
+        box = [None]
+        if rank == 0:
+            self.base, handle = capi.ipc_counter_create(device_index)
+            box[0] = handle
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            self.base = capi.ipc_counter_open(device_index, box[0])
+
+    def begin_frame(self, stream=None):
+        """Counter of this frame (device pointer). Call once per frame on every rank, same number of times."""
+        current = self.base + 128 * (self.step & 1)
+        if self.rank == 0:
+            capi.ipc_counter_clear(self.base + 128 * ((self.step + 1) & 1), stream)
+        self.step += 1
+        return current
+
+    def close(self):
+        capi.ipc_counter_close(self.device, self.base, self.rank != 0)
+        self.base = None
+
+
 def tile_shape(substreams):
     """(tile width, tile height) in pixels: a tile is 32 work items (32 / substreams pixels), or one pixel."""
     w = _TILE_W[substreams]
