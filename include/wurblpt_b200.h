@@ -312,8 +312,10 @@ typedef struct wpt_params {
 enum {
     WPT_TRAVERSAL_WIDE      = 0,    /* 4-wide BVH, near-to-far ordered (default) */
     WPT_TRAVERSAL_REFERENCE = 1,    /* binary BVH walked in the reference's storage order (bvh.hpp:277-311) */
-    WPT_TRAVERSAL_POOL      = 2     /* queries only: the 4-wide walk as the wavefront pipeline's pooled trace kernel runs it
+    WPT_TRAVERSAL_POOL      = 2,    /* queries only: the 4-wide walk as the wavefront pipeline's pooled trace kernel runs it
                                        (scenes without media and animated hitables); renders treat it like WIDE */
+    WPT_TRAVERSAL_PERSISTENT = 3    /* queries only: likewise through the pipeline's persistent per-lane trace kernel (the
+                                       one renders use by default), so that parity tests reach it bit for bit */
 };
 
 enum {

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 REFERENCE = abi.WPT_TRAVERSAL_REFERENCE
 WIDE = abi.WPT_TRAVERSAL_WIDE
 POOL = abi.WPT_TRAVERSAL_POOL
+PERSISTENT = abi.WPT_TRAVERSAL_PERSISTENT
 
 
 @pytest.fixture(scope="module")
@@ -76,23 +77,25 @@ def test_primary_hits_wide_walk(gpu, name):
 
 
 @pytest.mark.parametrize("name", GOLDEN_SCENES)
-def test_pooled_trace_kernel_answers_like_the_wide_walk(gpu, name):
-    """waveTracePoolKernel (the trace kernel of the wavefront pipeline: walk state in shared memory, node and
-    leaf steps run warp-wide from queues) runs the same tests in the same order per query as the per-lane wide
-    walk: ids and distance bits must be identical, ties included."""
+@pytest.mark.parametrize("mode", [PERSISTENT, POOL])
+def test_pipeline_trace_kernels_answer_like_the_wide_walk(gpu, name, mode):
+    """The trace kernels of the wavefront pipeline - waveTracePersistentKernel (lanes refill inside the walk loop, leaf
+    rounds, triangles of a leaf round pooled and tested one per lane) and waveTracePoolKernel (walk state in shared
+    memory, node and leaf passes from queues) - run the same tests in the same order per query as the per-lane wide
+    walk of the query kernel: ids and distance bits must be identical, ties included."""
     g = Golden(name)
     s = device_scene(gpu, g)
     h, w = g.z["hit_ids"].shape
     try:
-        ids, dist = s.primary_hits(g.camera, w, h, g.t0, g.params.min_hit_distance, gpu.make_opts(traversal=POOL))
+        ids, dist = s.primary_hits(g.camera, w, h, g.t0, g.params.min_hit_distance, gpu.make_opts(traversal=mode))
     except gpu.WptError as e:
-        assert e.code == abi.WPT_E_UNSUPPORTED      # media / animated hitables: served by the per-lane kernel
+        assert e.code == abi.WPT_E_UNSUPPORTED      # media / animated hitables: kernel variants with Prng and animation cache
         assert g.desc.n_media > 0 or g.desc.n_animations > 0, name
         return
     wids, wdist = s.primary_hits(g.camera, w, h, g.t0, g.params.min_hit_distance, gpu.make_opts(traversal=WIDE))
     assert np.array_equal(ids, wids)
     assert np.array_equal(dist.view(np.uint32), wdist.view(np.uint32))
-    # and a ragged count of incoherent rays (pool refills, drain, partial passes)
+    # and ragged counts of incoherent rays (refills, drain, partial rounds)
     rng = np.random.default_rng(99)
     for n in (1, 31, 33, 4097, 100003):
         boxes, _, _ = s.binary_nodes()
@@ -100,7 +103,7 @@ def test_pooled_trace_kernel_answers_like_the_wide_walk(gpu, name):
         o = (lo + rng.random((n, 3)) * (hi - lo)).astype(np.float32)
         d = rng.normal(size=(n, 3)).astype(np.float32)
         d = (d / np.sqrt((d ** 2).sum(axis=1, keepdims=True))).astype(np.float32)
-        a_ids, a_dist = s.trace_rays(o, d, g.t0, 1e-4, gpu.make_opts(traversal=POOL))
+        a_ids, a_dist = s.trace_rays(o, d, g.t0, 1e-4, gpu.make_opts(traversal=mode))
         b_ids, b_dist = s.trace_rays(o, d, g.t0, 1e-4, gpu.make_opts(traversal=WIDE))
         assert np.array_equal(a_ids, b_ids), (name, n)
         assert np.array_equal(a_dist.view(np.uint32), b_dist.view(np.uint32)), (name, n)
@@ -125,7 +128,7 @@ def test_secondary_ray_closest_hits_against_live_reference(gpu, ref, name, scale
     d = (d / np.sqrt((d.astype(np.float32) ** 2).sum(axis=1, keepdims=True))).astype(np.float32)
     has_media = r.desc.n_media > 0
     rid, ra = r.trace_rays(o, d, 0.0, 1e-4)
-    for mode in (REFERENCE, WIDE) + (() if has_media else (POOL,)):
+    for mode in (REFERENCE, WIDE) + (() if has_media else (POOL, PERSISTENT)):
         ids, dist = s.trace_rays(o, d, 0.0, 1e-4, gpu.make_opts(traversal=mode))
         if has_media:
             # media hits are random free-flight samples (hitable_medium.hpp:89): compare surfaces only

@@ -972,9 +972,9 @@ static int renderSingle(wpt_scene* s, const wpt_camera_desc* camera, const wpt_s
     P.invHeight = 1.0f / float(sensor->height);
     P.t0 = t0;
     P.t1 = t1;
-    if (o.traversal < WPT_TRAVERSAL_WIDE || o.traversal > WPT_TRAVERSAL_POOL)
+    if (o.traversal < WPT_TRAVERSAL_WIDE || o.traversal > WPT_TRAVERSAL_PERSISTENT)
         return fail(WPT_E_INVALID, "unknown traversal");
-    P.traversal = (o.traversal == WPT_TRAVERSAL_POOL ? WPT_TRAVERSAL_WIDE : o.traversal);
+    P.traversal = (o.traversal >= WPT_TRAVERSAL_POOL ? WPT_TRAVERSAL_WIDE : o.traversal);
     if (P.traversal == WPT_TRAVERSAL_WIDE && !(P.minHit > 0.0f))
         P.traversal = WPT_TRAVERSAL_REFERENCE;  /* the ordered walk needs a positive lower bound */
     if (P.traversal == WPT_TRAVERSAL_WIDE && 3 * s->host.wideDepth + 1 > wptd::wideStackEntries())
@@ -1302,7 +1302,7 @@ static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width,
     }
     P.t0 = P.t1 = time;
     P.minHit = minHit;
-    if (o.traversal < WPT_TRAVERSAL_WIDE || o.traversal > WPT_TRAVERSAL_POOL)
+    if (o.traversal < WPT_TRAVERSAL_WIDE || o.traversal > WPT_TRAVERSAL_PERSISTENT)
         return fail(WPT_E_INVALID, "unknown traversal");
     P.traversal = o.traversal;
     if (o.traversal != WPT_TRAVERSAL_REFERENCE && (!(minHit > 0.0f) || 3 * s->host.wideDepth + 1 > wptd::wideStackEntries()))
@@ -1310,9 +1310,9 @@ static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width,
     if (P.traversal == WPT_TRAVERSAL_REFERENCE && s->host.deviceBuilt)
         return fail(WPT_E_UNSUPPORTED, "this tree was built on the device (WPT_BUILDER_DEVICE_LBVH): the reference-order walk needs the "
                 "host builder's binary tree; it is also what a non-positive minimum hit distance or a very deep tree falls back to");
-    if (P.traversal == WPT_TRAVERSAL_POOL && (!s->d.simpleWalk || counters))
-        return fail(WPT_E_UNSUPPORTED, "WPT_TRAVERSAL_POOL: the pooled trace kernel serves scenes without media and animated "
-                "hitables, and does not count node visits");
+    if (P.traversal >= WPT_TRAVERSAL_POOL && (!s->d.simpleWalk || counters))
+        return fail(WPT_E_UNSUPPORTED, "WPT_TRAVERSAL_POOL / _PERSISTENT: queries through the pipeline's trace kernels are for scenes "
+                "without media and animated hitables, and do not count node visits");
     if (nRays == 0)
         return WPT_OK;
     if (nRays >= (1ull << 31))
@@ -1342,7 +1342,9 @@ static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width,
     const bool queryTiming = std::getenv("WPT_QUERY_TIMING") != nullptr;   /* experiment knob: kernel time to stderr */
     if (queryTiming)
         WPT_CUDA(cudaEventRecord(s->evStart, stream), "cudaEventRecord");
-    if (P.traversal == WPT_TRAVERSAL_POOL) {
+    if (P.traversal >= WPT_TRAVERSAL_POOL) {
+        const bool pooled = (P.traversal == WPT_TRAVERSAL_POOL);
+        P.traversal = WPT_TRAVERSAL_WIDE;
         /* the rays as wavefront slots: rays (wave[2]), answers (wave[5]), trace queue (wave[13]) */
         WPT_CUDA(s->wave[2].reserve(nRays * 2 * sizeof(float4)), "allocate query slots");
         WPT_CUDA(s->wave[5].reserve(nRays * sizeof(uint4)), "allocate query answers");
@@ -1358,7 +1360,7 @@ static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width,
         rc = reservePoolSpill(s, P);
         if (rc != WPT_OK)
             return rc;
-        WPT_CUDA(wptd::launchPoolQuery(dscene, P, s->numSMs, dO, dD, nRays, time, static_cast<int32_t*>(s->qIds.p),
+        WPT_CUDA(wptd::launchPoolQuery(dscene, P, s->numSMs, pooled, dO, dD, nRays, time, static_cast<int32_t*>(s->qIds.p),
                     static_cast<float*>(s->qDist.p), stream), "pooled query launch");
     } else
     WPT_CUDA(wptd::launchQuery(sceneFeatures(s, false), counters != nullptr, dscene, P, dO, dD, nRays, time,

@@ -59,6 +59,12 @@ namespace wptd {
 #ifndef WPT_LEAF_UNIT
 #define WPT_LEAF_UNIT 0     /* 1: a lane tests one primitive per leaf round instead of all primitives of its leaf (up to four); leaf lanes 7 -> 12 of 32 but node lanes 21 -> 18: -3 % on C3 */
 #endif
+#ifndef WPT_LEAF_COOP
+#define WPT_LEAF_COOP 0     /* 1: leaf rounds of triangle leaves pool the triangles of all waiting lanes and test one per lane
+                               (static scenes; see waveTracePersistentKernel). Bit-identical answers; the shuffles, the owner
+                               table and the in-order combine cost what the fuller lanes save: C3 +0.7 %, C1 -3 %, C2 -3 %
+                               (profiles/r2q_coop_ab.txt) */
+#endif
 #ifndef WPT_LEAF_MIN
 #define WPT_LEAF_MIN 12     /* lanes that must be at a leaf before the persistent trace kernel runs a leaf round */
 #endif
@@ -767,10 +773,20 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTraceKernel(c
  * ends, stores the answer and takes the next entry of the trace queue from a ticket counter -- inside the walk
  * loop, so a lane never waits for the longest ray of its warp. One loop iteration handles one inner node or one
  * primitive of a leaf. */
+/* A leaf round can be run cooperatively when every waiting lane's leaf holds triangles only (warp-uniform result). */
+WPT_DEV bool coopLeafRound(unsigned leafMask, bool atLeaf, int32_t cur)
+{
+    const uint32_t type = uint32_t(~cur) >> REF_TYPE_SHIFT;
+    const bool other = atLeaf && !(type == PRIM_TRIANGLE || type == PRIM_TRIANGLE_RUN);
+    return leafMask != 0u && __ballot_sync(0xFFFFFFFFu, other) == 0u;
+}
+
 template<int F>
 __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersistentKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
     extern __shared__ uint2 smStackAll[];
+    __shared__ float4 coopResult[(WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA))) ? (BLOCK / 32) * 128 : 1];
+    __shared__ uint8_t coopOwner[(WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA))) ? (BLOCK / 32) * 128 : 1];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned laneBelow = (1u << lane) - 1u;
     constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -871,8 +887,8 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
         const unsigned leafMask = __ballot_sync(FULL, atLeaf);
         const unsigned innerMask = activeMask & ~leafMask;
         const bool leafRound = (__popc(leafMask) >= WPT_LEAF_MIN) || innerMask == 0u;
-        if (!active)
-            continue;
+        if (!active && !(WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA)) && leafRound))
+            continue;       /* (idle lanes test triangles for the others in a cooperative leaf round) */
 
         if (!leafRound) {
             if (atInner) {
@@ -889,6 +905,71 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
                     cur = popNext(st, best.hit.a);
                 }
             }
+        } else if (WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA)) && coopLeafRound(leafMask, atLeaf, cur)) {
+            /* Cooperative leaf round: a leaf holds 1-4 triangles and only ~10 lanes wait at one, so looping over "my"
+             * triangles runs the (long) triangle test up to four times at a third of the lanes. Instead the triangles of
+             * all waiting lanes are numbered (prefix sum of the counts) and every lane of the warp tests ONE of them for
+             * its owner, whose ray it fetches by shuffle; the owners then take their results in slot order exactly as the
+             * loop would: a later triangle of the run only counts under the distance an earlier one has set. */
+            uint32_t first = 0, cnt = 0;
+            if (atLeaf) {
+                const uint32_t ref = uint32_t(~cur);
+                const bool run = (ref >> REF_TYPE_SHIFT) == PRIM_TRIANGLE_RUN;
+                first = run ? (ref & RUN_SLOT_MASK) : (ref & REF_SLOT_MASK);
+                cnt = run ? ((ref >> RUN_COUNT_SHIFT) & 3u) + 1u : 1u;
+            }
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, inc, off);
+                if (lane >= (unsigned)off)
+                    inc += y;
+            }
+            const uint32_t total = __shfl_sync(FULL, inc, 31);
+            const uint32_t excl = inc - cnt;
+            uint8_t* ownerOf = coopOwner + (threadIdx.x >> 5) * 128;
+            float4* result = coopResult + (threadIdx.x >> 5) * 128;
+            for (uint32_t i = 0; i < cnt; i++)
+                ownerOf[excl + i] = uint8_t(lane);
+            __syncwarp();
+            const uint32_t kpack = uint32_t(h.kx) | (uint32_t(h.ky) << 2) | (uint32_t(h.kz) << 4);
+            for (uint32_t base = 0; base < total; base += 32u) {
+                const uint32_t j = base + lane;
+                const bool valid = j < total;
+                const unsigned own = valid ? ownerOf[j] : 0u;
+                Ray oray;
+                oray.o = f3(__shfl_sync(FULL, ray.o.x, own), __shfl_sync(FULL, ray.o.y, own), __shfl_sync(FULL, ray.o.z, own));
+                oray.d = f3(0.0f);
+                oray.time = 0.0f;
+                RayHelper oh;
+                oh.inv = f3(0.0f);
+                oh.Sx = __shfl_sync(FULL, h.Sx, own);
+                oh.Sy = __shfl_sync(FULL, h.Sy, own);
+                oh.Sz = __shfl_sync(FULL, h.Sz, own);
+                const uint32_t ok = __shfl_sync(FULL, kpack, own);
+                oh.kx = int(ok & 3u); oh.ky = int((ok >> 2) & 3u); oh.kz = int(ok >> 4);
+                const float oamax = __shfl_sync(FULL, best.hit.a, own);
+                const uint32_t ofirst = __shfl_sync(FULL, first, own);
+                const uint32_t oexcl = __shfl_sync(FULL, excl, own);
+                if (valid) {
+                    const float4* tp = S.tri + size_t(ofirst + (j - oexcl)) * 3;
+                    const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                    float ta = 0.0f, U, V, W, det, Ts = 0.0f, da = 0.0f;
+                    const bool found = triangleTest(xyz(t0), xyz(t1), xyz(t2), oray, oh, amin, oamax, true, ta, U, V, W, det, Ts, da);
+                    result[j] = f4(ta, Ts, da, found ? 1.0f : 0.0f);
+                }
+            }
+            __syncwarp();
+            if (atLeaf) {
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const float4 r = result[excl + i];
+                    /* (the test ran under the distance the round started with: redo its upper bound, hitable_triangle.hpp:263-264) */
+                    if (r.w != 0.0f && !(r.y > best.hit.a * r.z))
+                        considerHit(best, (PRIM_TRIANGLE << REF_TYPE_SHIFT) | (first + i), r.x, r.y, r.z);
+                }
+                cur = popNext(st, best.hit.a);
+            }
+            __syncwarp();
         } else if (atLeaf) {
 #if WPT_LEAF_UNIT
             /* one primitive per lane and leaf round; what is left of a run stays this lane's leaf */
@@ -903,7 +984,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
         if (S.prefetchLeaves && cur < 0 && ((!leafRound && atInner) || (leafRound && atLeaf)))
             prefetchLeaf(S, uint32_t(~cur));
 #endif
-        if (cur == EMPTY_CHILD) {
+        if (active && cur == EMPTY_CHILD) {
             reinterpret_cast<uint2*>(P.W.hit)[entry] = make_uint2(__float_as_uint(best.hit.a), best.hit.ref);
             if ((F & F_MEDIA) && !(entry & 1u))
                 P.W.prng[2 * (entry >> 1)] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
@@ -1351,6 +1432,8 @@ __global__ void __launch_bounds__(BLOCK) queryKernel(const __grid_constant__ DSc
     }
 }
 
+static size_t stackBytes();
+
 /* Closest-hit queries through the pooled trace kernel (WPT_TRAVERSAL_POOL): the rays are laid out like wavefront
  * slots, traced by waveTracePoolKernel, and the answers converted to ids. This is how the bit-exact parity
  * tests reach the kernel that renders. */
@@ -1396,13 +1479,23 @@ __global__ void __launch_bounds__(BLOCK) poolQueryFinishKernel(const __grid_cons
     dist[i] = (hw.y != NO_HIT ? __uint_as_float(hw.x) : 0.0f);
 }
 
-cudaError_t launchPoolQuery(const DScene& S, const RenderParams& P, int numSMs, const float* origins, const float* directions,
+cudaError_t launchPoolQuery(const DScene& S, const RenderParams& P, int numSMs, bool pooled, const float* origins, const float* directions,
         unsigned long long nRays, float time, int32_t* ids, float* dist, cudaStream_t stream)
 {
     const unsigned int grid = (unsigned int)((nRays + BLOCK - 1) / BLOCK);
     if (grid == 0)
         return cudaSuccess;
     poolQuerySetupKernel<<<grid, BLOCK, 0, stream>>>(P, origins, directions, nRays, time);
+    if (!pooled) {
+        int perSM = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, waveTracePersistentKernel<0>, BLOCK, stackBytes());
+        if (e != cudaSuccess)
+            return e;
+        unsigned int pgrid = (unsigned int)(numSMs * (perSM < 1 ? 1 : perSM));
+        if (pgrid > grid)
+            pgrid = grid;
+        waveTracePersistentKernel<0><<<pgrid, BLOCK, stackBytes(), stream>>>(S, P);
+    } else
     waveTracePoolKernel<<<poolGridBlocks(numSMs), BLOCK, 0, stream>>>(S, P, P.poolSpill, P.poolSpillPerRay);
     poolQueryFinishKernel<<<grid, BLOCK, 0, stream>>>(S, P, nRays, ids, dist);
     return cudaGetLastError();

@@ -21,9 +21,10 @@ cudaError_t launchQuery(int features, bool count, const DScene& S, const RenderP
         const float* origins, const float* directions, unsigned long long nRays, float time,
         int32_t* ids, float* dist, TraceStats* stats, cudaStream_t stream);
 
-/* The same queries through the pooled trace kernel of the wavefront pipeline (scenes without media / animated hitables):
+/* The same queries through a trace kernel of the wavefront pipeline - pooled, or the persistent per-lane one (scenes without media /
+ * animated hitables):
  * P.W.rayO / rayD / traceQueue / hit must hold nRays slots, P.poolSpill the spill area, P.counters the counters. */
-cudaError_t launchPoolQuery(const DScene& S, const RenderParams& P, int numSMs, const float* origins, const float* directions,
+cudaError_t launchPoolQuery(const DScene& S, const RenderParams& P, int numSMs, bool pooled, const float* origins, const float* directions,
         unsigned long long nRays, float time, int32_t* ids, float* dist, cudaStream_t stream);
 unsigned int poolGridBlocks(int numSMs);
 unsigned int poolRaysPerBlock();
