@@ -273,3 +273,44 @@ def test_noise_textures_equal_the_reference_bit_for_bit(tmp_path):
         outputs.append(subprocess.run([exe], capture_output=True, text=True).stdout)
     assert len(outputs[0].splitlines()) == 1000
     assert outputs[0] == outputs[1]
+
+
+def test_mpi_coordinator_interface_without_mpi(tmp_path):
+    """MPICoordinator (reference mpi.hpp:152-289) keeps the members applications use; there is one process, the world
+    size is the number of GPUs that render a frame, the block interface hands out the image as one block, and the
+    program refuses to run as one of several MPI ranks (every rank would render everything on the same GPUs)."""
+    src = tmp_path / "t.cpp"
+    src.write_text('''
+#include <cstdio>
+#include <wurblpt/wurblpt.hpp>
+using namespace WurblPT;
+int main() {
+    MPICoordinator mpi;
+    unsigned int start = 7, size = 7;
+    float pixels[12];
+    mpi.init(2, 2, pixels, 3);
+    mpi.getBlock(&start, &size);
+    std::printf("%d %d %u %u %u", mpi.mainProcess() ? 1 : 0, mpi.worldSize(), mpi.blockSize(), start, size);
+    mpi.submitBlock(start, size);
+    mpi.getBlock(&start, &size);
+    std::printf(" %u %s\\n", size, mpi.processId());
+    mpi.finish();
+    return 0;
+}
+''')
+    lib = os.path.join(ROOT, "wurblpt_b200", "lib")
+    exe = str(tmp_path / "t")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe,
+                        "-L" + lib, "-lwurblpt_b200", "-Wl,-rpath," + lib], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    env = {k: v for k, v in os.environ.items() if not k.startswith(("OMPI_", "PMI_", "PMIX_", "MV2_"))}
+    r = subprocess.run([exe], capture_output=True, text=True, env=dict(env, WURBLPT_DEVICE="0"))
+    assert r.returncode == 0, r.stderr
+    main, world, block, start, size, size2, *name = r.stdout.split()
+    assert (main, world, block, start, size, size2) == ("1", "1", "4096", "0", "4", "0")   # one device chosen explicitly
+    assert " ".join(name) == "process 0"
+    from wurblpt_b200 import capi
+    r = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and int(r.stdout.split()[1]) == max(1, capi.device_count())     # all GPUs of the box
+    r = subprocess.run([exe], capture_output=True, text=True, env=dict(env, OMPI_COMM_WORLD_SIZE="4", OMPI_COMM_WORLD_RANK="1"))
+    assert r.returncode != 0 and "MPI ranks" in r.stderr
