@@ -40,6 +40,9 @@ constexpr int F_COUNT = 8;      /* count node visits and leaf tests (query kerne
 #ifndef WPT_SM_STACK
 #define WPT_SM_STACK 12
 #endif
+#ifndef WPT_STACK_STRIDE
+#define WPT_STACK_STRIDE 128    /* threads per block of the kernels that walk the tree (kernels.cu BLOCK) */
+#endif
 constexpr int SM_STACK = WPT_SM_STACK;          /* shared-memory stack entries per thread */
 constexpr int LOCAL_STACK = 96 - SM_STACK;      /* spill entries per thread (local memory, touched only when deep) */
 constexpr int BINARY_STACK = 128;   /* BVH::maxTreeDepth, bvh.hpp:230 */
@@ -491,11 +494,14 @@ __device__ Hit traverseReference(const DScene& S, uint32_t root, const Ray& ray,
 #define WPT_SHARED_STACK_PTX 1      /* ld.shared / st.shared instead of generic accesses (same frame, +1 % on C3) */
 #endif
 
+/* The wide walk's stack: SM_STACK entries per thread in shared memory (column `sm`, stride entries apart), deeper ones in
+ * `spill` (local memory). The stack pointer is a plain variable of the caller (a register), not a member: a struct
+ * that also holds the dynamically indexed spill array lives in local memory as a whole. */
 struct WideStack {
     uint2* sm;              /* this thread's column of the shared-memory stack, stride = blockDim.x */
     int stride;
     uint2 spill[LOCAL_STACK];
-    int sp;
+    int sp;                 /* (per-walk functions keep their own copy in a register, see WideWalkStack) */
 
 #if WPT_SHARED_STACK_PTX
     /* The pointer above reaches shared memory through the generic address space (LD.E / ST.E in SASS,
@@ -540,6 +546,35 @@ WPT_DEV int32_t popNext(WideStack& st, float limit)
 {
     while (st.sp > 0) {
         const uint2 e = st.pop();
+        if (__uint_as_float(e.y) <= limit)
+            return int32_t(e.x);
+    }
+    return EMPTY_CHILD;
+}
+
+/* The same stack for the persistent trace kernel: shared-memory base address and spill array are separate variables and
+ * the stack pointer is passed by reference, so that it stays in a register across the walk loop (with the struct above
+ * the compiler keeps `sp` in local memory next to the spill array: an STL / LDL per push and pop). */
+WPT_DEV void stackPush(uint32_t smBase, uint2* spill, int& sp, uint32_t code, uint32_t tminBits)
+{
+    if (sp < SM_STACK)
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(smBase + uint32_t(sp) * uint32_t(WPT_STACK_STRIDE * sizeof(uint2))),
+                "r"(code), "r"(tminBits) : "memory");
+    else
+        spill[sp - SM_STACK] = make_uint2(code, tminBits);
+    sp++;
+}
+
+WPT_DEV int32_t stackPopNext(uint32_t smBase, const uint2* spill, int& sp, float limit)
+{
+    while (sp > 0) {
+        --sp;
+        uint2 e;
+        if (sp < SM_STACK)
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y)
+                    : "r"(smBase + uint32_t(sp) * uint32_t(WPT_STACK_STRIDE * sizeof(uint2))) : "memory");
+        else
+            e = spill[sp - SM_STACK];
         if (__uint_as_float(e.y) <= limit)
             return int32_t(e.x);
     }

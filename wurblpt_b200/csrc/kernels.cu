@@ -419,6 +419,7 @@ constexpr unsigned int SORT_WINDOW = 256;       /* slots per warp */
 constexpr unsigned int TRACE_CLASSES = 8;       /* see waveGenerateKernel */
 constexpr unsigned int SORT_BLOCK = 128;
 static_assert(SORT_BLOCK == BLOCK && SORT_WINDOW == WAVE_WINDOW, "the sort and generate kernels share one launch geometry");
+static_assert(BLOCK == WPT_STACK_STRIDE, "the shared-memory stack columns are BLOCK entries apart");
 
 __global__ void __launch_bounds__(SORT_BLOCK) waveSortKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
@@ -812,10 +813,10 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     best.hit.ref = NO_HIT;
     best.Ts = best.det = 0.0f;
     int32_t cur = EMPTY_CHILD;
-    WideStack st;
-    st.sm = smStackAll + threadIdx.x;
-    st.stride = BLOCK;
-    st.sp = 0;
+    /* the walk's stack: a column of the block's shared-memory array, a local-memory spill, the pointer in a register */
+    const uint32_t smBase = uint32_t(__cvta_generic_to_shared(smStackAll + threadIdx.x));
+    uint2 spill[LOCAL_STACK];
+    int sp = 0;
     const float amin = P.minHit;
 
     /* Tickets are drawn from the global counter a chunk at a time and handed out inside the warp
@@ -867,7 +868,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
                 active = true;
                 best.hit.a = MAXVAL;
                 best.hit.ref = NO_HIT;
-                st.sp = 0;
+                sp = 0;
                 cur = S.root4;
             }
             const unsigned gotMask = __ballot_sync(FULL, got);
@@ -895,14 +896,14 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
                 const NodeKeys nk = nodeKeys(S, cur, ray.o, h.inv, amin, best.hit.a, rows);
                 if (nk.k0 != 0xFFFFFFFFu) {
                     if (nk.k3 != 0xFFFFFFFFu)
-                        st.push(uint32_t(sel4i(nk.ch, nk.k3 & 3u)), __uint_as_float(nk.k3 & ~3u));
+                        stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k3 & 3u)), nk.k3 & ~3u);
                     if (nk.k2 != 0xFFFFFFFFu)
-                        st.push(uint32_t(sel4i(nk.ch, nk.k2 & 3u)), __uint_as_float(nk.k2 & ~3u));
+                        stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k2 & 3u)), nk.k2 & ~3u);
                     if (nk.k1 != 0xFFFFFFFFu)
-                        st.push(uint32_t(sel4i(nk.ch, nk.k1 & 3u)), __uint_as_float(nk.k1 & ~3u));
+                        stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k1 & 3u)), nk.k1 & ~3u);
                     cur = sel4i(nk.ch, nk.k0 & 3u);
                 } else {
-                    cur = popNext(st, best.hit.a);
+                    cur = stackPopNext(smBase, spill, sp, best.hit.a);
                 }
             }
         } else if (WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA)) && coopLeafRound(leafMask, atLeaf, cur)) {
@@ -967,17 +968,17 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
                     if (r.w != 0.0f && !(r.y > best.hit.a * r.z))
                         considerHit(best, (PRIM_TRIANGLE << REF_TYPE_SHIFT) | (first + i), r.x, r.y, r.z);
                 }
-                cur = popNext(st, best.hit.a);
+                cur = stackPopNext(smBase, spill, sp, best.hit.a);
             }
             __syncwarp();
         } else if (atLeaf) {
 #if WPT_LEAF_UNIT
             /* one primitive per lane and leaf round; what is left of a run stays this lane's leaf */
             const uint32_t rest = wideLeafStep<F>(S, uint32_t(~cur), ray, h, amin, P.minHit, ctx, best);
-            cur = (rest != NO_HIT ? int32_t(~rest) : popNext(st, best.hit.a));
+            cur = (rest != NO_HIT ? int32_t(~rest) : stackPopNext(smBase, spill, sp, best.hit.a));
 #else
             wideLeaf<F>(S, uint32_t(~cur), ray, h, amin, P.minHit, ctx, best);
-            cur = popNext(st, best.hit.a);
+            cur = stackPopNext(smBase, spill, sp, best.hit.a);
 #endif
         }
 #if WPT_PREFETCH_LEAF
