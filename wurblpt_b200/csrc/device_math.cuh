@@ -66,7 +66,19 @@ WPT_DEV float3 refract(float3 i, float3 n, float eta)
 WPT_DEV float3 vmin(float3 a, float3 b) { return f3(rmin(a.x, b.x), rmin(a.y, b.y), rmin(a.z, b.z)); }
 WPT_DEV float3 vmax(float3 a, float3 b) { return f3(rmax(a.x, b.x), rmax(a.y, b.y), rmax(a.z, b.z)); }
 WPT_DEV float3 vmix(float3 a, float3 b, float t) { return f3(rmix(a.x, b.x, t), rmix(a.y, b.y, t), rmix(a.z, b.z, t)); }
-WPT_DEV float sel(float3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+/* component k (0..2) of v. Written as two selp: left to itself the compiler turns the ternaries into divergent branches
+ * (six instructions and a reconvergence point per use, nine uses per triangle test). */
+WPT_DEV float sel(float3 v, int k)
+{
+    float r;
+    asm("{\n\t.reg .pred p0, p1;\n\t"
+        "setp.eq.s32 p0, %4, 0;\n\t"
+        "setp.eq.s32 p1, %4, 1;\n\t"
+        "selp.f32 %0, %2, %3, p1;\n\t"
+        "selp.f32 %0, %1, %0, p0;\n\t}"
+        : "=f"(r) : "f"(v.x), "f"(v.y), "f"(v.z), "r"(k));
+    return r;
+}
 WPT_DEV float average(float3 v) { return (1.0f / 3.0f) * (((0.0f + v.x) + v.y) + v.z); }  /* gvm.hpp:1293-1300 */
 
 /* ---- float4 ---- */
