@@ -110,16 +110,16 @@ WPT_DEV float sel(float4 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k ==
 /* component k (0..3) of v with three selects (written as selp so that no branches are generated) */
 WPT_DEV int sel4i(int4 v, uint32_t k)
 {
-    int lo, hi, r;
-    asm("{\n\t.reg .pred p0, p1;\n\t"
-        "and.b32 %1, %7, 1;\n\t"
-        "setp.ne.u32 p0, %1, 0;\n\t"
-        "and.b32 %2, %7, 2;\n\t"
-        "setp.ne.u32 p1, %2, 0;\n\t"
-        "selp.b32 %1, %4, %3, p0;\n\t"
-        "selp.b32 %2, %6, %5, p0;\n\t"
-        "selp.b32 %0, %2, %1, p1;\n\t}"
-        : "=r"(r), "=&r"(lo), "=&r"(hi) : "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(k));
+    int r;
+    asm("{\n\t.reg .pred p0, p1;\n\t.reg .b32 lo, hi;\n\t"
+        "and.b32 lo, %5, 1;\n\t"
+        "setp.ne.u32 p0, lo, 0;\n\t"
+        "and.b32 hi, %5, 2;\n\t"
+        "setp.ne.u32 p1, hi, 0;\n\t"
+        "selp.b32 lo, %2, %1, p0;\n\t"
+        "selp.b32 hi, %4, %3, p0;\n\t"
+        "selp.b32 %0, hi, lo, p1;\n\t}"
+        : "=r"(r) : "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(k));
     return r;
 }
 
