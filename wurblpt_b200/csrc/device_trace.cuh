@@ -494,67 +494,11 @@ __device__ Hit traverseReference(const DScene& S, uint32_t root, const Ray& ray,
 #define WPT_SHARED_STACK_PTX 1      /* ld.shared / st.shared instead of generic accesses (same frame, +1 % on C3) */
 #endif
 
-/* The wide walk's stack: SM_STACK entries per thread in shared memory (column `sm`, stride entries apart), deeper ones in
- * `spill` (local memory). The stack pointer is a plain variable of the caller (a register), not a member: a struct
- * that also holds the dynamically indexed spill array lives in local memory as a whole. */
-struct WideStack {
-    uint2* sm;              /* this thread's column of the shared-memory stack, stride = blockDim.x */
-    int stride;
-    uint2 spill[LOCAL_STACK];
-    int sp;                 /* (per-walk functions keep their own copy in a register, see WideWalkStack) */
-
-#if WPT_SHARED_STACK_PTX
-    /* The pointer above reaches shared memory through the generic address space (LD.E / ST.E in SASS,
-     * profiles/r1_sass_trace_kernel.txt); these two address it as shared memory. */
-    WPT_DEV uint32_t sharedAddress(int entry) const
-    {
-        return uint32_t(__cvta_generic_to_shared(sm)) + uint32_t(entry * stride) * uint32_t(sizeof(uint2));
-    }
-    WPT_DEV void storeShared(int entry, uint2 e) const
-    {
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(sharedAddress(entry)), "r"(e.x), "r"(e.y) : "memory");
-    }
-    WPT_DEV uint2 loadShared(int entry) const
-    {
-        uint2 e;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(sharedAddress(entry)) : "memory");
-        return e;
-    }
-#else
-    WPT_DEV void storeShared(int entry, uint2 e) const { sm[entry * stride] = e; }
-    WPT_DEV uint2 loadShared(int entry) const { return sm[entry * stride]; }
-#endif
-
-    WPT_DEV void push(uint32_t code, float tmin)
-    {
-        uint2 e = make_uint2(code, __float_as_uint(tmin));
-        if (sp < SM_STACK)
-            storeShared(sp, e);
-        else
-            spill[sp - SM_STACK] = e;
-        sp++;
-    }
-    WPT_DEV uint2 pop()
-    {
-        --sp;
-        return sp < SM_STACK ? loadShared(sp) : spill[sp - SM_STACK];
-    }
-};
-
-/* next stack entry that can still contain a hit at or before `limit`; EMPTY_CHILD when the stack is empty */
-WPT_DEV int32_t popNext(WideStack& st, float limit)
-{
-    while (st.sp > 0) {
-        const uint2 e = st.pop();
-        if (__uint_as_float(e.y) <= limit)
-            return int32_t(e.x);
-    }
-    return EMPTY_CHILD;
-}
-
-/* The same stack for the persistent trace kernel: shared-memory base address and spill array are separate variables and
- * the stack pointer is passed by reference, so that it stays in a register across the walk loop (with the struct above
- * the compiler keeps `sp` in local memory next to the spill array: an STL / LDL per push and pop). */
+/* The wide walk's stack: SM_STACK entries per thread in shared memory (a column of the block's array, WPT_STACK_STRIDE
+ * entries apart, addressed as shared memory: ld.shared / st.shared instead of the generic LD.E / ST.E a pointer gives),
+ * deeper entries in `spill` (local memory). Base address, spill array and stack pointer are separate variables of the
+ * walk: in a struct next to the dynamically indexed spill array the stack pointer lives in local memory (an STL / LDL
+ * per push and pop). */
 WPT_DEV void stackPush(uint32_t smBase, uint2* spill, int& sp, uint32_t code, uint32_t tminBits)
 {
     if (sp < SM_STACK)
@@ -754,10 +698,11 @@ __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
     best.hit.a = amax;
     best.hit.ref = NO_HIT;
     best.Ts = best.det = 0.0f;
-    WideStack st;
-    st.sm = smStack;
-    st.stride = smStride;
-    st.sp = 0;
+    /* (smStride is the block size of the calling kernel: WPT_STACK_STRIDE) */
+    const uint32_t smBase = uint32_t(__cvta_generic_to_shared(smStack));
+    uint2 spill[LOCAL_STACK];
+    int sp = 0;
+    (void)smStride;
     int32_t cur = S.root4;                  /* EMPTY_CHILD doubles as "walk finished" */
     const uint32_t rows = octantRows(ray.d);
     for (;;) {
@@ -768,20 +713,20 @@ __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
             if (nk.k0 != 0xFFFFFFFFu) {
                 /* far children go on the stack farthest first, the nearest is visited next */
                 if (nk.k3 != 0xFFFFFFFFu)
-                    st.push(uint32_t(sel4i(nk.ch, nk.k3 & 3u)), __uint_as_float(nk.k3 & ~3u));
+                    stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k3 & 3u)), nk.k3 & ~3u);
                 if (nk.k2 != 0xFFFFFFFFu)
-                    st.push(uint32_t(sel4i(nk.ch, nk.k2 & 3u)), __uint_as_float(nk.k2 & ~3u));
+                    stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k2 & 3u)), nk.k2 & ~3u);
                 if (nk.k1 != 0xFFFFFFFFu)
-                    st.push(uint32_t(sel4i(nk.ch, nk.k1 & 3u)), __uint_as_float(nk.k1 & ~3u));
+                    stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k1 & 3u)), nk.k1 & ~3u);
                 cur = sel4i(nk.ch, nk.k0 & 3u);
             } else {
-                cur = popNext(st, best.hit.a);
+                cur = stackPopNext(smBase, spill, sp, best.hit.a);
             }
         }
         if (cur == EMPTY_CHILD)
             return best.hit;
         wideLeaf<F>(S, uint32_t(~cur), ray, h, amin, minHit, ctx, best);
-        cur = popNext(st, best.hit.a);
+        cur = stackPopNext(smBase, spill, sp, best.hit.a);
     }
 }
 
