@@ -45,6 +45,7 @@ WORKLOADS = {
     "synth_profile": ("synth", 1.0, 960, 540, 4),
     "synth_64spp": ("synth", 1.0, 1920, 1080, 8),
     "cornell_profile": ("cornell", 1.0, 512, 512, 4),
+    "media_profile": ("media", 1.0, 512, 512, 4),
 }
 
 

@@ -36,6 +36,7 @@ SCENES = [
     ("mixed", 1.0, (96, 64), (96, 64, 12)),
     ("synth", 0.004, (128, 72), (96, 54, 8)),
     ("synth360", 0.004, (128, 128), (64, 64, 8)),     # C4: 360 degree top-bottom stereo camera
+    ("imported", 1.0, (96, 72), (80, 60, 12)),        # OBJ/MTL import: the description is the REFERENCE importer's
 ]
 
 

@@ -190,7 +190,8 @@ def render_golden_view(gpu, g, opts=None, spp_sqrt=None):
 # 8x8 box filter the per-pixel noise drops by ~8x; the bound below is ~4 sigma of what two
 # independent reference renders with different seeds differ by (measured here: 2-4 %).
 RENDER_TOL = {"cornell": 0.06, "rtiow": 0.06, "mis": 0.10, "mis_nohot": 0.25, "media": 0.10, "tof": 0.05,
-              "furnace": 0.01, "mixed": 0.12, "synth": 0.25, "synth360": 0.25}
+              "furnace": 0.01, "mixed": 0.12, "synth": 0.25, "synth360": 0.25,
+              "imported": 0.02}    # (the OBJ/MTL scene: two reference renders of it differ by 0.1 %)
 
 
 @pytest.mark.parametrize("name", GOLDEN_SCENES)

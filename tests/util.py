@@ -8,7 +8,7 @@ from wurblpt_b200 import abi
 from wurblpt_b200 import scene_desc as sd
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_SCENES = ["cornell", "rtiow", "mis", "mis_nohot", "media", "tof", "furnace", "mixed", "synth", "synth360"]
+GOLDEN_SCENES = ["cornell", "rtiow", "mis", "mis_nohot", "media", "tof", "furnace", "mixed", "synth", "synth360", "imported"]
 
 
 class Golden:

@@ -65,6 +65,9 @@ namespace wptd {
                                table and the in-order combine cost what the fuller lanes save: C3 +0.7 %, C1 -3 %, C2 -3 %
                                (profiles/r2q_coop_ab.txt) */
 #endif
+#ifndef WPT_ANY_HIT
+#define WPT_ANY_HIT 1       /* shadow queries towards the environment stop at the first hit (persistent trace kernel) */
+#endif
 #ifndef WPT_LEAF_MIN
 #define WPT_LEAF_MIN 12     /* lanes that must be at a leaf before the persistent trace kernel runs a leaf round */
 #endif
@@ -794,7 +797,6 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
     Ctx<F> ctx;
     ctx.nested = 0;
     ctx.nodes = ctx.leaves = 0;
-    unsigned int traced = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {  /* queue lengths of this round (the sort kernel that follows counts them up) */
         for (int c = 0; c < MAT_CLASSES; c++)
             *ctrMaterial(P, c) = 0ull;
@@ -802,6 +804,12 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
 
     const unsigned int nCamera = (unsigned int)*ctrTraceCamera(P);
     const unsigned int nQueued = nCamera + (unsigned int)*ctrTraceOther(P);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nQueued != 0u)       /* statistics: every queued query is answered by this launch */
+        atomicAdd(P.counters + CTR_RAYS, (unsigned long long)nQueued);
+    /* Without hot spots every shadow query S asks whether the environment is visible (wurblpt.hpp:236-251): only
+     * "nothing hit" is read of its answer (consumeShadow), so its walk may stop at the first hit instead of looking for
+     * the closest one. Not with media: their walks draw from the Prng, the draws must not depend on the visiting order. */
+    const bool anyHitScene = WPT_ANY_HIT && !(F & F_MEDIA) && S.nHot == 0u;
     unsigned int entry = 0;             /* slot << 1 | query of the walk in progress */
     bool active = false;
     Ray ray;
@@ -978,7 +986,8 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
             cur = (rest != NO_HIT ? int32_t(~rest) : stackPopNext(smBase, spill, sp, best.hit.a));
 #else
             wideLeaf<F>(S, uint32_t(~cur), ray, h, amin, P.minHit, ctx, best);
-            cur = stackPopNext(smBase, spill, sp, best.hit.a);
+            /* occlusion query: the first hit answers it */
+            cur = (anyHitScene && (entry & 1u) && best.hit.ref != NO_HIT) ? EMPTY_CHILD : stackPopNext(smBase, spill, sp, best.hit.a);
 #endif
         }
 #if WPT_PREFETCH_LEAF
@@ -990,17 +999,11 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
             if ((F & F_MEDIA) && !(entry & 1u))
                 P.W.prng[2 * (entry >> 1)] = make_uint4(ctx.prng.s0, ctx.prng.s1, ctx.prng.s2, ctx.prng.s3);
             active = false;
-            traced++;
         }
     }
-    const unsigned int n = __reduce_add_sync(FULL, traced);
     const unsigned int q = __reduce_add_sync(FULL, ctx.nested);
-    if (lane == 0) {
-        if (n)
-            atomicAdd(P.counters + CTR_RAYS, (unsigned long long)n);
-        if (q)
-            atomicAdd(P.counters + CTR_NESTED, (unsigned long long)q);
-    }
+    if (lane == 0 && q)
+        atomicAdd(P.counters + CTR_NESTED, (unsigned long long)q);
 }
 
 /* Drain: the last rounds of a frame hold few live slots but cost a full round each (five launches that scan or
