@@ -314,8 +314,10 @@ enum {
     WPT_TRAVERSAL_REFERENCE = 1,    /* binary BVH walked in the reference's storage order (bvh.hpp:277-311) */
     WPT_TRAVERSAL_POOL      = 2,    /* queries only: the 4-wide walk as the wavefront pipeline's pooled trace kernel runs it
                                        (scenes without media and animated hitables); renders treat it like WIDE */
-    WPT_TRAVERSAL_PERSISTENT = 3    /* queries only: likewise through the pipeline's persistent per-lane trace kernel (the
-                                       one renders use by default), so that parity tests reach it bit for bit */
+    WPT_TRAVERSAL_PERSISTENT = 3,   /* queries only: likewise through the pipeline's persistent per-lane trace kernel, so that
+                                       parity tests reach it bit for bit */
+    WPT_TRAVERSAL_QUAD      = 4     /* queries only: likewise through the pipeline's quad trace kernel (four lanes per query:
+                                       one child of a wide node / one triangle of a leaf each) */
 };
 
 enum {

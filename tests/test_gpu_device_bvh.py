@@ -61,7 +61,7 @@ def test_device_and_host_built_trees_answer_alike(gpu, name):
     d = rng.normal(size=(n, 3)).astype(np.float32)
     d = (d / np.sqrt((d ** 2).sum(axis=1, keepdims=True))).astype(np.float32)
     hid, hdist = host.trace_rays(o, d, g.t0, 1e-4)
-    modes = [abi.WPT_TRAVERSAL_WIDE] + ([abi.WPT_TRAVERSAL_POOL, abi.WPT_TRAVERSAL_PERSISTENT] if g.desc.n_animations == 0 else [])
+    modes = [abi.WPT_TRAVERSAL_WIDE] + ([abi.WPT_TRAVERSAL_POOL, abi.WPT_TRAVERSAL_PERSISTENT, abi.WPT_TRAVERSAL_QUAD] if g.desc.n_animations == 0 else [])
     for mode in modes:
         did, ddist = dev.trace_rays(o, d, g.t0, 1e-4, gpu.make_opts(traversal=mode))
         c = compare_hits(did, ddist, hid, hdist)

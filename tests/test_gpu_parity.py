@@ -16,6 +16,7 @@ REFERENCE = abi.WPT_TRAVERSAL_REFERENCE
 WIDE = abi.WPT_TRAVERSAL_WIDE
 POOL = abi.WPT_TRAVERSAL_POOL
 PERSISTENT = abi.WPT_TRAVERSAL_PERSISTENT
+QUAD = abi.WPT_TRAVERSAL_QUAD
 
 
 @pytest.fixture(scope="module")
@@ -77,11 +78,12 @@ def test_primary_hits_wide_walk(gpu, name):
 
 
 @pytest.mark.parametrize("name", GOLDEN_SCENES)
-@pytest.mark.parametrize("mode", [PERSISTENT, POOL])
+@pytest.mark.parametrize("mode", [PERSISTENT, POOL, QUAD])
 def test_pipeline_trace_kernels_answer_like_the_wide_walk(gpu, name, mode):
     """The trace kernels of the wavefront pipeline - waveTracePersistentKernel (lanes refill inside the walk loop, leaf
-    rounds, triangles of a leaf round pooled and tested one per lane) and waveTracePoolKernel (walk state in shared
-    memory, node and leaf passes from queues) - run the same tests in the same order per query as the per-lane wide
+    rounds, triangles of a leaf round pooled and tested one per lane), waveTracePoolKernel (walk state in shared
+    memory, node and leaf passes from queues) and waveTraceQuadKernel (four lanes per query: one child of a wide node /
+    one triangle of a leaf each) - run the same tests in the same order per query as the per-lane wide
     walk of the query kernel: ids and distance bits must be identical, ties included."""
     g = Golden(name)
     s = device_scene(gpu, g)
@@ -128,7 +130,7 @@ def test_secondary_ray_closest_hits_against_live_reference(gpu, ref, name, scale
     d = (d / np.sqrt((d.astype(np.float32) ** 2).sum(axis=1, keepdims=True))).astype(np.float32)
     has_media = r.desc.n_media > 0
     rid, ra = r.trace_rays(o, d, 0.0, 1e-4)
-    for mode in (REFERENCE, WIDE) + (() if has_media else (POOL, PERSISTENT)):
+    for mode in (REFERENCE, WIDE) + (() if has_media else (POOL, PERSISTENT, QUAD)):
         ids, dist = s.trace_rays(o, d, 0.0, 1e-4, gpu.make_opts(traversal=mode))
         if has_media:
             # media hits are random free-flight samples (hitable_medium.hpp:89): compare surfaces only

@@ -27,7 +27,7 @@ WPT_ENV_NONE, WPT_ENV_EQUIRECT, WPT_ENV_CUBE = range(3)
 WPT_SURROUND_OFF, WPT_SURROUND_180, WPT_SURROUND_360 = range(3)
 WPT_DISTORTION_NONE, WPT_DISTORTION_RADIAL_AND_PLANAR, WPT_DISTORTION_RADIAL_ONLY, WPT_DISTORTION_OPENCV = range(4)
 WPT_SENSOR_RGB, WPT_SENSOR_TOF_AMCW = range(2)
-WPT_TRAVERSAL_WIDE, WPT_TRAVERSAL_REFERENCE, WPT_TRAVERSAL_POOL, WPT_TRAVERSAL_PERSISTENT = range(4)
+WPT_TRAVERSAL_WIDE, WPT_TRAVERSAL_REFERENCE, WPT_TRAVERSAL_POOL, WPT_TRAVERSAL_PERSISTENT, WPT_TRAVERSAL_QUAD = range(5)
 WPT_PIPELINE_AUTO, WPT_PIPELINE_MEGAKERNEL, WPT_PIPELINE_WAVEFRONT = range(3)
 
 f32, i32, u32, u64 = C.c_float, C.c_int32, C.c_uint32, C.c_uint64

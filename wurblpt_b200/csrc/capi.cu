@@ -133,7 +133,7 @@ struct wpt_scene {
     DeviceBuf animations, keyframes, envM, envMs, envMcs, envGuide;
     int envGuideBits = 0;
     /* per updateBVH */
-    DeviceBuf node4, bnode, tri, triShade, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs, triClass, sphClass, medClass;
+    DeviceBuf node4, node4c, bnode, tri, triShade, sph, med, triGlobal, sphGlobal, medGlobal, hotRefs, triClass, sphClass, medClass;
     /* per call scratch */
     DeviceBuf counters, camKeys, frame, partials, wave[17], qOrigins, qDirections, qIds, qDist, qStats, gtImages, gtMaterialIds, animTable, poolSpill, sharedCounter, blockDone, peerStage;
     /* device builder: inputs in hitable order, scratch */
@@ -159,7 +159,7 @@ struct wpt_scene {
     uint64_t deviceBytes() const
     {
         const DeviceBuf* all[] = { &materials, &instances, &meshes, &vertices, &indices, &textures, &texels,
-            &animations, &keyframes, &envM, &envMs, &envMcs, &envGuide, &node4, &bnode, &tri, &triShade, &sph, &med,
+            &animations, &keyframes, &envM, &envMs, &envMcs, &envGuide, &node4, &node4c, &bnode, &tri, &triShade, &sph, &med,
             &triGlobal, &sphGlobal, &medGlobal, &hotRefs, &triClass, &sphClass, &medClass };
         uint64_t n = 0;
         for (const DeviceBuf* b : all)
@@ -268,6 +268,7 @@ void refreshDeviceScene(wpt_scene* s)
     wptd::DScene& d = s->d;
     const wpt::HostScene& h = s->host;
     d.node4 = s->node4.as<float4>();
+    d.node4c = s->node4c.as<float4>();
     d.bnode = s->bnode.as<float4>();
     d.tri = s->tri.as<float4>();
     d.triShade = s->triShade.as<uint4>();
@@ -714,6 +715,8 @@ static int uploadBvh(wpt_scene* s)
     auto start = std::chrono::steady_clock::now();
     const wpt::HostScene& h = s->host;
     WPT_CUDA(s->node4.upload(h.nodes4.data(), h.nodes4.size() * sizeof(wpt::Node4)), "upload wide nodes");
+    WPT_CUDA(s->node4c.reserve(h.nodes4.size() * sizeof(wpt::Node4)), "allocate wide nodes (child-major)");
+    WPT_CUDA(wptd::launchNodeTranspose(s->node4.as<float4>(), static_cast<float4*>(s->node4c.p), uint32_t(h.nodes4.size()), 0), "wide nodes child by child");
     WPT_CUDA(s->bnode.upload(h.bnodes.data(), h.bnodes.size() * sizeof(wpt::BNode)), "upload binary nodes");
     WPT_CUDA(s->tri.upload(h.triData.data(), h.triData.size() * sizeof(float)), "upload triangles");
     WPT_CUDA(s->triShade.upload(h.triShade.data(), h.triShade.size() * sizeof(uint32_t)), "upload triangle shading records");
@@ -783,6 +786,9 @@ static int buildOnDevice(wpt_scene* s, uint32_t* wideNodes, uint32_t* depth, uin
     io.hotRefs = static_cast<uint32_t*>(s->hotRefs.p);
     WPT_CUDA(wptd::launchDeviceBuild(io, s->bScratch.p, h.wideLeafTriangles, 0, wideNodes, depth, triangles), "device tree build");
     WPT_CUDA(cudaDeviceSynchronize(), "device tree build");
+    WPT_CUDA(s->node4c.reserve(size_t(*wideNodes) * sizeof(wpt::Node4)), "allocate wide nodes (child-major)");
+    WPT_CUDA(wptd::launchNodeTranspose(s->node4.as<float4>(), static_cast<float4*>(s->node4c.p), *wideNodes, 0), "wide nodes child by child");
+    WPT_CUDA(cudaDeviceSynchronize(), "wide nodes child by child");
     s->uploadSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     return WPT_OK;
 }
@@ -972,7 +978,7 @@ static int renderSingle(wpt_scene* s, const wpt_camera_desc* camera, const wpt_s
     P.invHeight = 1.0f / float(sensor->height);
     P.t0 = t0;
     P.t1 = t1;
-    if (o.traversal < WPT_TRAVERSAL_WIDE || o.traversal > WPT_TRAVERSAL_PERSISTENT)
+    if (o.traversal < WPT_TRAVERSAL_WIDE || o.traversal > WPT_TRAVERSAL_QUAD)
         return fail(WPT_E_INVALID, "unknown traversal");
     P.traversal = (o.traversal >= WPT_TRAVERSAL_POOL ? WPT_TRAVERSAL_WIDE : o.traversal);
     if (P.traversal == WPT_TRAVERSAL_WIDE && !(P.minHit > 0.0f))
@@ -1302,7 +1308,7 @@ static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width,
     }
     P.t0 = P.t1 = time;
     P.minHit = minHit;
-    if (o.traversal < WPT_TRAVERSAL_WIDE || o.traversal > WPT_TRAVERSAL_PERSISTENT)
+    if (o.traversal < WPT_TRAVERSAL_WIDE || o.traversal > WPT_TRAVERSAL_QUAD)
         return fail(WPT_E_INVALID, "unknown traversal");
     P.traversal = o.traversal;
     if (o.traversal != WPT_TRAVERSAL_REFERENCE && (!(minHit > 0.0f) || 3 * s->host.wideDepth + 1 > wptd::wideStackEntries()))
@@ -1344,6 +1350,7 @@ static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width,
         WPT_CUDA(cudaEventRecord(s->evStart, stream), "cudaEventRecord");
     if (P.traversal >= WPT_TRAVERSAL_POOL) {
         const bool pooled = (P.traversal == WPT_TRAVERSAL_POOL);
+        const int mode = pooled ? 1 : (P.traversal == WPT_TRAVERSAL_QUAD ? 2 : 0);
         P.traversal = WPT_TRAVERSAL_WIDE;
         /* the rays as wavefront slots: rays (wave[2]), answers (wave[5]), trace queue (wave[13]) */
         WPT_CUDA(s->wave[2].reserve(nRays * 2 * sizeof(float4)), "allocate query slots");
@@ -1360,7 +1367,7 @@ static int runQuery(wpt_scene* s, const wpt_camera_desc* camera, uint32_t width,
         rc = reservePoolSpill(s, P);
         if (rc != WPT_OK)
             return rc;
-        WPT_CUDA(wptd::launchPoolQuery(dscene, P, s->numSMs, pooled, dO, dD, nRays, time, static_cast<int32_t*>(s->qIds.p),
+        WPT_CUDA(wptd::launchPoolQuery(dscene, P, s->numSMs, mode, dO, dD, nRays, time, static_cast<int32_t*>(s->qIds.p),
                     static_cast<float*>(s->qDist.p), stream), "pooled query launch");
     } else
     WPT_CUDA(wptd::launchQuery(sceneFeatures(s, false), counters != nullptr, dscene, P, dO, dD, nRays, time,

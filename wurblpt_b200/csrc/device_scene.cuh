@@ -45,6 +45,8 @@ struct DTexture {
 
 struct DScene {
     const float4* node4;
+    const float4* node4c;       /* the same wide nodes child by child (32 B per child: lo.xyz hi.x | hi.yz child pad): what the
+                                   quad trace kernel reads, one child per lane */
     const float4* bnode;
     const float4* tri;
     const uint4* triShade;      /* per triangle slot: float offsets of the 3 vertex attribute blocks in `vertices`, mesh flags */

@@ -1006,6 +1006,289 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
         atomicAdd(P.counters + CTR_NESTED, (unsigned long long)q);
 }
 
+/* ------------------------------------------------------------ quad trace kernel */
+
+#ifndef WPT_TRACE_QUAD_DEFAULT
+#define WPT_TRACE_QUAD_DEFAULT 0    /* 1: static scenes without media are traced by waveTraceQuadKernel (WPT_TRACE_QUAD=0/1 overrides) */
+#endif
+#ifndef WPT_QUAD_STACK
+#define WPT_QUAD_STACK 40       /* shared-memory stack entries per quad (deeper entries: local memory) */
+#endif
+#ifndef WPT_QUAD_REFILL_MIN
+#define WPT_QUAD_REFILL_MIN 12  /* idle LANES (3 quads) that must have gathered before new queries are fetched */
+#endif
+#ifndef WPT_QUAD_LEAF_MIN
+#define WPT_QUAD_LEAF_MIN 12    /* LANES (3 quads) that must wait at a leaf before a leaf round runs */
+#endif
+#ifndef WPT_QUAD_MIN_BLOCKS
+#define WPT_QUAD_MIN_BLOCKS 8
+#endif
+constexpr int QUAD_STACK = WPT_QUAD_STACK;
+constexpr int QUAD_SPILL = 96 - QUAD_STACK;         /* same capacity as the per-lane walk: wideStackEntries() */
+constexpr int QUADS_PER_BLOCK = BLOCK / 4;
+constexpr int QUAD_STRIDE = QUADS_PER_BLOCK + 1;    /* entries of one stack level are QUAD_STRIDE apart: the +1 spreads the
+                                                       levels that the lanes of one quad push together over the banks */
+static_assert(SM_STACK + LOCAL_STACK == QUAD_STACK + QUAD_SPILL, "both walks have the stack capacity capi.cu checks against");
+
+static size_t quadStackBytes()
+{
+    return size_t(QUAD_STACK) * QUAD_STRIDE * sizeof(uint2);
+}
+
+/* The wide nodes child by child: node4 holds one 128-byte node as six rows of four child planes plus the child row (what
+ * a lane that tests all four children wants); node4c holds the same 128 bytes as four 32-byte child records
+ * (lo.x lo.y lo.z hi.x | hi.y hi.z child 0), what a lane that tests ONE child wants: two 128-bit loads. */
+__global__ void __launch_bounds__(256) nodeTransposeKernel(const float4* __restrict__ node4, float4* __restrict__ node4c, uint32_t nNodes)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;     /* (node, child) */
+    if (i >= nNodes * 4u)
+        return;
+    const uint32_t node = i >> 2, k = i & 3u;
+    const float* src = reinterpret_cast<const float*>(node4 + size_t(node) * 8);
+    const float lox = src[0 + k], hix = src[4 + k], loy = src[8 + k], hiy = src[12 + k], loz = src[16 + k], hiz = src[20 + k];
+    const float child = src[24 + k];
+    node4c[size_t(node) * 8 + 2 * k] = f4(lox, loy, loz, hix);
+    node4c[size_t(node) * 8 + 2 * k + 1] = f4(hiy, hiz, child, 0.0f);
+}
+
+cudaError_t launchNodeTranspose(const float4* node4, float4* node4c, uint32_t nNodes, cudaStream_t stream)
+{
+    if (nNodes == 0)
+        return cudaSuccess;
+    nodeTransposeKernel<<<(nNodes * 4u + 255u) / 256u, 256, 0, stream>>>(node4, node4c, nNodes);
+    return cudaGetLastError();
+}
+
+WPT_DEV void quadStackStore(uint32_t smBase, int pos, uint32_t code, uint32_t tminBits)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(smBase + uint32_t(pos) * uint32_t(QUAD_STRIDE * sizeof(uint2))),
+            "r"(code), "r"(tminBits) : "memory");
+}
+
+/* Next stack entry whose entry distance is still under `limit` (all four lanes of a quad run this with the same
+ * arguments and read the same entries: broadcasts). */
+WPT_DEV int32_t quadStackPopNext(uint32_t smBase, const uint2* spill, int& sp, float limit)
+{
+    while (sp > 0) {
+        --sp;
+        uint2 e;
+        if (sp < QUAD_STACK)
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y)
+                    : "r"(smBase + uint32_t(sp) * uint32_t(QUAD_STRIDE * sizeof(uint2))) : "memory");
+        else
+            e = spill[sp - QUAD_STACK];
+        if (__uint_as_float(e.y) <= limit)
+            return int32_t(e.x);
+    }
+    return EMPTY_CHILD;
+}
+
+/* Trace, quad form (static scenes without media: F == 0). Four neighbouring lanes walk the tree for ONE query:
+ *
+ *   inner node   lane j of the quad fetches child j of the node (two 128-bit loads from node4c: the four lanes read
+ *                the node's 128-byte line once per load, where the per-lane walk reads it seven times, one row per
+ *                load) and runs the one slab test; the four keys are exchanged by three shuffles, every lane ranks
+ *                its child among the hit ones, pushes it at its place of the quad's stack (farthest first) or, if
+ *                it is the nearest, hands it to the quad as the next node;
+ *   leaf         lane j tests triangle j of the leaf's run (a leaf holds 1-4 triangles; the per-lane walk loops over
+ *                them at a third of the lanes); the results are taken in slot order exactly as that loop would, a later
+ *                triangle only under the distance an earlier one has set. Spheres are tested by all four lanes alike.
+ *
+ * The state of a walk (ray, best hit, current node, stack pointer) is replicated in the quad's four lanes and every
+ * branch on it is uniform across the quad. The arithmetic of the slab, triangle and sphere tests and the order in which
+ * hits are considered are those of the per-lane walk: the answers are bit-identical (tests/test_gpu_parity.py). Queue
+ * tickets, refill of idle quads inside the walk loop, node rounds vs. leaf rounds: as in waveTracePersistentKernel. */
+template<int F>
+__global__ void __launch_bounds__(BLOCK, WPT_QUAD_MIN_BLOCKS) waveTraceQuadKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+{
+    static_assert(!(F & (F_MEDIA | F_ANIM)), "the quad walk is for static scenes without media");
+    extern __shared__ uint2 smStackAll[];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned laneBelow = (1u << lane) - 1u;
+    const unsigned j = lane & 3u;                   /* my child / my triangle */
+    const unsigned qshift = lane & ~3u;             /* first lane of my quad */
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    Ctx<F> ctx;
+    ctx.nested = 0;
+    ctx.nodes = ctx.leaves = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  /* queue lengths of this round (the sort kernel that follows counts them up) */
+        for (int c = 0; c < MAT_CLASSES; c++)
+            *ctrMaterial(P, c) = 0ull;
+    }
+    const unsigned int nCamera = (unsigned int)*ctrTraceCamera(P);
+    const unsigned int nQueued = nCamera + (unsigned int)*ctrTraceOther(P);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nQueued != 0u)
+        atomicAdd(P.counters + CTR_RAYS, (unsigned long long)nQueued);
+    const bool anyHitScene = WPT_ANY_HIT && S.nHot == 0u;      /* see waveTracePersistentKernel */
+    unsigned int entry = 0;
+    bool active = false;
+    Ray ray;
+    ray.o = f3(0.0f); ray.d = f3(0.0f, 0.0f, 1.0f); ray.time = 0.0f;
+    RayHelper h = makeRayHelper(ray);
+    uint32_t rows = 0;
+    WideBest best;
+    best.hit.a = MAXVAL;
+    best.hit.ref = NO_HIT;
+    best.Ts = best.det = 0.0f;
+    int32_t cur = EMPTY_CHILD;
+    const uint32_t smBase = uint32_t(__cvta_generic_to_shared(smStackAll + (threadIdx.x >> 2)));
+    uint2 spill[QUAD_SPILL];
+    int sp = 0;
+    const float amin = P.minHit;
+
+    const unsigned int perWarp = nQueued / (gridDim.x * (BLOCK / 32u));
+    const unsigned int CHUNK = perWarp >= 512u ? 64u : perWarp >= 128u ? 32u : perWarp >= 32u ? 16u : 8u;    /* queries per ticket */
+    unsigned int warpNext = 0, warpEnd = 0;
+    bool drained = false;
+    unsigned exhaustedMask = 0u;
+    for (;;) {
+        const unsigned busyMask = __ballot_sync(FULL, active);
+        const unsigned wantMask = ~busyMask & ~exhaustedMask;
+        unsigned activeMask = busyMask;
+        const int refillMin = (warpNext < warpEnd && warpNext < nCamera) ? 32 : WPT_QUAD_REFILL_MIN;
+        if (wantMask != 0u && (__popc(wantMask) >= refillMin || busyMask == 0u)) {
+            if (warpNext >= warpEnd && !drained) {
+                unsigned int base = 0;
+                if (lane == 0)
+                    base = (unsigned int)atomicAdd(ctrTicket(P), (unsigned long long)CHUNK);
+                base = __shfl_sync(FULL, base, 0);
+                warpNext = base;
+                warpEnd = min(base + CHUNK, nQueued);
+                if (base >= nQueued) {
+                    drained = true;
+                    warpNext = warpEnd = 0;
+                }
+            }
+            const unsigned int avail = warpEnd - warpNext;
+            const unsigned int rank = __popc(wantMask & laneBelow) >> 2;       /* idle quads before mine */
+            const bool got = ((wantMask >> lane) & 1u) && rank < avail;
+            if (got) {
+                const unsigned int e = traceQueueEntry(P, warpNext + rank, nCamera);
+                const unsigned int s = e >> 1, which = e & 1u;
+                const float4 o = P.W.rayO[2 * s], d = (which ? P.W.shD[2 * s] : P.W.rayD[2 * s]);
+                ray.o = xyz(o); ray.time = o.w; ray.d = xyz(d);
+                h = makeRayHelper(ray);
+                rows = octantRows(ray.d);
+                entry = e;
+                active = true;
+                best.hit.a = MAXVAL;
+                best.hit.ref = NO_HIT;
+                sp = 0;
+                cur = S.root4;
+            }
+            const unsigned gotMask = __ballot_sync(FULL, got);
+            activeMask |= gotMask;
+            if (drained)
+                exhaustedMask |= wantMask & ~gotMask;
+            warpNext += min((unsigned int)__popc(wantMask) >> 2, avail);
+        }
+        if (exhaustedMask == FULL)
+            break;
+        const bool atLeaf = active && cur < 0;
+        const bool atInner = active && cur >= 0 && cur != EMPTY_CHILD;
+        const unsigned leafMask = __ballot_sync(FULL, atLeaf);
+        const unsigned innerMask = activeMask & ~leafMask;
+        const bool leafRound = (__popc(leafMask) >= WPT_QUAD_LEAF_MIN) || innerMask == 0u;
+
+        /* Both kinds of round are entered by the whole warp (leafRound is warp-uniform) and every shuffle / ballot below
+         * runs with all 32 lanes converged: quads that have nothing to do in the round take part with a key of "missed" /
+         * "not found". (Sub-warp masks would do, but nvcc guards every *_sync with a run-time mask by MATCH / REDUX / a
+         * divergence check.) */
+        if (!leafRound) {
+            /* my child's record */
+            uint32_t key = 0xFFFFFFFFu;
+            int32_t child = EMPTY_CHILD;
+            if (atInner) {
+                const float4* n = S.node4c + size_t(cur) * 8 + 2u * j;
+                const float4 ra = __ldg(n), rb = __ldg(n + 1);
+                child = __float_as_int(rb.z);
+                const bool sx = rows & 1u, sy = rows & 2u, sz = rows & 4u;
+                key = childKeyNearFar(sx ? ra.w : ra.x, sx ? ra.x : ra.w, sy ? rb.x : ra.y, sy ? ra.y : rb.x,
+                        sz ? rb.y : ra.z, sz ? ra.z : rb.y, ray.o, h.inv, amin, best.hit.a, j);
+                if (child == EMPTY_CHILD)
+                    key = 0xFFFFFFFFu;
+            }
+            const uint32_t k1 = __shfl_xor_sync(FULL, key, 1), k2 = __shfl_xor_sync(FULL, key, 2), k3 = __shfl_xor_sync(FULL, key, 3);
+            const bool hit = key != 0xFFFFFFFFu;
+            const int nHit = int(hit) + int(k1 != 0xFFFFFFFFu) + int(k2 != 0xFFFFFFFFu) + int(k3 != 0xFFFFFFFFu);
+            /* keys of hit children differ in their low bits: `rank` numbers them by entry distance, 0 = nearest */
+            const int rank = int(k1 < key) + int(k2 < key) + int(k3 < key);
+            const uint32_t nearest = min(min(key, k1), min(k2, k3));
+            const int32_t nearestChild = __shfl_sync(FULL, child, int(qshift + (nearest & 3u)));
+            const int newSp = sp + (nHit > 0 ? nHit - 1 : 0);
+            const bool deep = newSp > QUAD_STACK;       /* (rare) the push reaches into the local-memory part of the stack */
+            if (__any_sync(FULL, deep)) {
+                /* every lane of a quad keeps a copy of the local-memory part: the entries are handed round */
+                for (int r = 3; r >= 1; r--) {
+                    const unsigned m = (__ballot_sync(FULL, hit && rank == r) >> qshift) & 0xFu;
+                    const int src = int(qshift) + (m ? __ffs(int(m)) - 1 : 0);
+                    const uint32_t c = __shfl_sync(FULL, uint32_t(child), src), t = __shfl_sync(FULL, key & ~3u, src);
+                    if (deep && r <= nHit - 1) {
+                        const int pos = sp + (nHit - 1 - r);
+                        if (pos < QUAD_STACK) {
+                            if (j == 0u)
+                                quadStackStore(smBase, pos, c, t);
+                        } else {
+                            spill[pos - QUAD_STACK] = make_uint2(c, t);
+                        }
+                    }
+                }
+            }
+            if (atInner) {
+                if (nHit == 0) {
+                    cur = quadStackPopNext(smBase, spill, sp, best.hit.a);
+                } else {
+                    if (!deep && hit && rank >= 1)      /* farthest first: the nearest of the pushed ones ends up on top */
+                        quadStackStore(smBase, sp + (nHit - 1 - rank), uint32_t(child), key & ~3u);
+                    sp = newSp;
+                    cur = nearestChild;
+                }
+            }
+        } else {
+            const uint32_t ref = uint32_t(~cur);
+            const uint32_t type = ref >> REF_TYPE_SHIFT;
+            const bool triLeaf = atLeaf && (type == PRIM_TRIANGLE_RUN || type == PRIM_TRIANGLE);
+            const bool run = (type == PRIM_TRIANGLE_RUN);
+            const uint32_t first = run ? (ref & RUN_SLOT_MASK) : (ref & REF_SLOT_MASK);
+            const uint32_t cnt = run ? ((ref >> RUN_COUNT_SHIFT) & 3u) + 1u : 1u;
+            float ta = 0.0f, Ts = 0.0f, da = 0.0f;
+            bool found = false;
+            if (triLeaf && j < cnt) {
+                const float4* tp = S.tri + size_t(first + j) * 3;
+                const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                float U, V, W, det;
+                found = triangleTest(xyz(t0), xyz(t1), xyz(t2), ray, h, amin, best.hit.a, true, ta, U, V, W, det, Ts, da);
+            }
+            const unsigned foundAll = __ballot_sync(FULL, found);
+            const unsigned foundBits = (foundAll >> qshift) & 0xFu;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {       /* in slot order */
+                if (foundAll & (0x11111111u << i)) {    /* (warp-uniform) some quad's triangle i was hit */
+                    const int src = int(qshift) + i;
+                    const float ia = __shfl_sync(FULL, ta, src), iTs = __shfl_sync(FULL, Ts, src), ida = __shfl_sync(FULL, da, src);
+                    /* (the test ran under the distance the round started with: redo its upper bound, hitable_triangle.hpp:263-264) */
+                    if (((foundBits >> i) & 1u) && !(iTs > best.hit.a * ida))
+                        considerHit(best, (PRIM_TRIANGLE << REF_TYPE_SHIFT) | (first + uint32_t(i)), ia, iTs, ida);
+                }
+            }
+            if (atLeaf) {
+                if (!triLeaf)       /* a sphere: all four lanes alike */
+                    wideLeaf<F>(S, ref, ray, h, amin, P.minHit, ctx, best);
+                cur = (anyHitScene && (entry & 1u) && best.hit.ref != NO_HIT) ? EMPTY_CHILD : quadStackPopNext(smBase, spill, sp, best.hit.a);
+            }
+        }
+#if WPT_PREFETCH_LEAF
+        if (S.prefetchLeaves && cur < 0 && ((!leafRound && atInner) || (leafRound && atLeaf)))
+            prefetchLeaf(S, uint32_t(~cur));
+#endif
+        if (active && cur == EMPTY_CHILD) {
+            if (j == 0u)
+                reinterpret_cast<uint2*>(P.W.hit)[entry] = make_uint2(__float_as_uint(best.hit.a), best.hit.ref);
+            active = false;
+        }
+    }
+}
+
 /* Drain: the last rounds of a frame hold few live slots but cost a full round each (five launches that scan or
  * stride over all slots, ~70 us). Once the work items have run out and few slots are alive, this kernel finishes
  * every one of them in a thread of its own: the slot's pending queries, the rest of its path, the remaining samples
@@ -1483,14 +1766,25 @@ __global__ void __launch_bounds__(BLOCK) poolQueryFinishKernel(const __grid_cons
     dist[i] = (hw.y != NO_HIT ? __uint_as_float(hw.x) : 0.0f);
 }
 
-cudaError_t launchPoolQuery(const DScene& S, const RenderParams& P, int numSMs, bool pooled, const float* origins, const float* directions,
+cudaError_t launchPoolQuery(const DScene& S, const RenderParams& P, int numSMs, int mode, const float* origins, const float* directions,
         unsigned long long nRays, float time, int32_t* ids, float* dist, cudaStream_t stream)
 {
     const unsigned int grid = (unsigned int)((nRays + BLOCK - 1) / BLOCK);
     if (grid == 0)
         return cudaSuccess;
+    const bool pooled = (mode == 1);
     poolQuerySetupKernel<<<grid, BLOCK, 0, stream>>>(P, origins, directions, nRays, time);
-    if (!pooled) {
+    if (mode == 2) {
+        int perSM = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, waveTraceQuadKernel<0>, BLOCK, quadStackBytes());
+        if (e != cudaSuccess)
+            return e;
+        unsigned int pgrid = (unsigned int)(numSMs * (perSM < 1 ? 1 : perSM));
+        const unsigned int needed = (unsigned int)((nRays + BLOCK / 4 - 1) / (BLOCK / 4));     /* a block walks BLOCK / 4 queries at a time */
+        if (pgrid > needed)
+            pgrid = needed;
+        waveTraceQuadKernel<0><<<pgrid, BLOCK, quadStackBytes(), stream>>>(S, P);
+    } else if (!pooled) {
         int perSM = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, waveTracePersistentKernel<0>, BLOCK, stackBytes());
         if (e != cudaSuccess)
@@ -1659,6 +1953,14 @@ static size_t stackBytes()
     return size_t(SM_STACK) * BLOCK * sizeof(uint2);
 }
 
+/* The quad trace kernel (waveTraceQuadKernel) renders static scenes without media unless WPT_TRACE_QUAD=0. */
+static bool waveQuadTrace(const DScene& S)
+{
+    const char* e = std::getenv("WPT_TRACE_QUAD");
+    const bool on = e ? (e[0] != '0') : (WPT_TRACE_QUAD_DEFAULT != 0);
+    return on && S.simpleWalk && S.node4c != nullptr;
+}
+
 static cudaError_t launchResolve(const RenderParams& P, cudaStream_t stream)
 {
     if (P.substreams == 1)
@@ -1820,6 +2122,22 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
     }
     const bool persistent = (P.traversal == WPT_TRAVERSAL_WIDE) && !wavePlainTrace();
     const bool pool = wavePool(S, P);
+    bool quad = false;
+    int quadPerSM = 0;
+    if constexpr (F == 0) {
+        quad = persistent && !pool && waveQuadTrace(S);
+        if (quad) {
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&quadPerSM, waveTraceQuadKernel<0>, BLOCK, quadStackBytes());
+            if (e != cudaSuccess)
+                return e;
+            if (const char* ev = std::getenv("WPT_TRACE_CTAS")) {
+                const int v = std::atoi(ev);
+                if (v >= 1 && v < quadPerSM)
+                    quadPerSM = v;
+            }
+            perSM = quadPerSM;
+        }
+    }
     const unsigned int poolGrid = poolGridBlocks(numSMs);
     unsigned long long drainSlots = 32768;      /* live slots at which waveDrainKernel takes over (0: never); C1 +6 %,
                                                    media +2 %, larger values cost media up to 6 % (profiles/r2h_ab.txt) */
@@ -1868,7 +2186,10 @@ static cudaError_t launchWavefrontT(const DScene& S, const RenderParams& P, int 
                 if (persistent && pool)
                     waveTracePoolKernel<<<poolGrid, BLOCK, 0, st[g]>>>(S, R,
                             P.poolSpill + size_t(g) * poolGrid * poolRaysPerBlock() * P.poolSpillPerRay, P.poolSpillPerRay);
-                else if (persistent)
+                else if (quad) {
+                    if constexpr (F == 0)
+                        waveTraceQuadKernel<0><<<pgrid[g], BLOCK, quadStackBytes(), st[g]>>>(S, R);
+                } else if (persistent)
                     waveTracePersistentKernel<F><<<pgrid[g], BLOCK, stackBytes(), st[g]>>>(S, R);
                 else
                     waveTraceKernel<F><<<pgrid[g], BLOCK, stackBytes(), st[g]>>>(S, R);

@@ -24,9 +24,11 @@ cudaError_t launchQuery(int features, bool count, const DScene& S, const RenderP
 /* The same queries through a trace kernel of the wavefront pipeline - pooled, or the persistent per-lane one (scenes without media /
  * animated hitables):
  * P.W.rayO / rayD / traceQueue / hit must hold nRays slots, P.poolSpill the spill area, P.counters the counters. */
-cudaError_t launchPoolQuery(const DScene& S, const RenderParams& P, int numSMs, bool pooled, const float* origins, const float* directions,
+cudaError_t launchPoolQuery(const DScene& S, const RenderParams& P, int numSMs, int mode /* 0 persistent per-lane, 1 pooled, 2 quad */, const float* origins, const float* directions,
         unsigned long long nRays, float time, int32_t* ids, float* dist, cudaStream_t stream);
 unsigned int poolGridBlocks(int numSMs);
+/* node4c from node4 (see DScene): nNodes wide nodes, child by child */
+cudaError_t launchNodeTranspose(const float4* node4, float4* node4c, uint32_t nNodes, cudaStream_t stream);
 unsigned int poolRaysPerBlock();
 unsigned int poolStackEntries();
 unsigned int wideStackEntries();     /* capacity of the per-lane walk's stack (shared memory + local spill) */
