@@ -525,6 +525,22 @@ WPT_DEV int32_t stackPopNext(uint32_t smBase, const uint2* spill, int& sp, float
     return EMPTY_CHILD;
 }
 
+#ifndef WPT_PUSH_PREDICATED
+#define WPT_PUSH_PREDICATED 0   /* 1: the far children of a node are pushed by predicated stores (no branch per child) while the
+                                   stack is in shared memory. Most nodes have one or two children hit and the branches skip
+                                   the work of the others: -1.5 % on C3 (profiles/r2y_trace_micro_ab.txt) */
+#endif
+
+/* st.shared of one stack entry under the predicate key != 0xFFFFFFFF (a child the ray enters) */
+WPT_DEV void stackStoreIfHit(uint32_t addr, uint32_t code, uint32_t key)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+        "setp.ne.u32 p, %2, 0xffffffff;\n\t"
+        "and.b32 t, %2, 0xfffffffc;\n\t"
+        "@p st.shared.v2.u32 [%0], {%1, t};\n\t}"
+        :: "r"(addr), "r"(code), "r"(key) : "memory");
+}
+
 WPT_DEV void sort2(uint32_t& a, uint32_t& b)
 {
     uint32_t lo = min(a, b), hi = max(a, b);
@@ -597,6 +613,32 @@ WPT_DEV NodeKeys nodeKeys(const DScene& S, int32_t cur, float3 o, float3 inv, fl
     /* 5-comparator sorting network, ascending */
     sort2(r.k0, r.k1); sort2(r.k2, r.k3); sort2(r.k0, r.k2); sort2(r.k1, r.k3); sort2(r.k1, r.k2);
     return r;
+}
+
+/* The far children of a node whose nearest child is visited next: k1..k3 of the sorted keys, farthest first (the hit
+ * ones are a prefix of the sorted order: k3 hit implies k2 and k1 hit). */
+WPT_DEV void pushFarChildren(uint32_t smBase, uint2* spill, int& sp, const NodeKeys& nk)
+{
+#if WPT_PUSH_PREDICATED
+    if (sp <= SM_STACK - 3) {
+        constexpr uint32_t STRIDE = uint32_t(WPT_STACK_STRIDE * sizeof(uint2));
+        const uint32_t p3 = (nk.k3 != 0xFFFFFFFFu), p2 = (nk.k2 != 0xFFFFFFFFu), p1 = (nk.k1 != 0xFFFFFFFFu);
+        const uint32_t a3 = smBase + uint32_t(sp) * STRIDE;
+        const uint32_t a2 = a3 + p3 * STRIDE;
+        const uint32_t a1 = a2 + p2 * STRIDE;
+        stackStoreIfHit(a3, uint32_t(sel4i(nk.ch, nk.k3 & 3u)), nk.k3);
+        stackStoreIfHit(a2, uint32_t(sel4i(nk.ch, nk.k2 & 3u)), nk.k2);
+        stackStoreIfHit(a1, uint32_t(sel4i(nk.ch, nk.k1 & 3u)), nk.k1);
+        sp += int(p3 + p2 + p1);
+        return;
+    }
+#endif
+    if (nk.k3 != 0xFFFFFFFFu)
+        stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k3 & 3u)), nk.k3 & ~3u);
+    if (nk.k2 != 0xFFFFFFFFu)
+        stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k2 & 3u)), nk.k2 & ~3u);
+    if (nk.k1 != 0xFFFFFFFFu)
+        stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k1 & 3u)), nk.k1 & ~3u);
 }
 
 /* bit 0/1/2: the ray direction's x/y/z is negative (sign bit; -0 counts, its inverse is -inf) */
@@ -712,12 +754,7 @@ __device__ Hit traverseWide(const DScene& S, const Ray& ray, const RayHelper& h,
             const NodeKeys nk = nodeKeys(S, cur, ray.o, h.inv, amin, best.hit.a, rows);
             if (nk.k0 != 0xFFFFFFFFu) {
                 /* far children go on the stack farthest first, the nearest is visited next */
-                if (nk.k3 != 0xFFFFFFFFu)
-                    stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k3 & 3u)), nk.k3 & ~3u);
-                if (nk.k2 != 0xFFFFFFFFu)
-                    stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k2 & 3u)), nk.k2 & ~3u);
-                if (nk.k1 != 0xFFFFFFFFu)
-                    stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k1 & 3u)), nk.k1 & ~3u);
+                pushFarChildren(smBase, spill, sp, nk);
                 cur = sel4i(nk.ch, nk.k0 & 3u);
             } else {
                 cur = stackPopNext(smBase, spill, sp, best.hit.a);

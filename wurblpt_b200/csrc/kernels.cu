@@ -36,7 +36,7 @@ namespace wptd {
 #define WPT_MIN_BLOCKS 8
 #endif
 #ifndef WPT_TRACE_MIN_BLOCKS
-#define WPT_TRACE_MIN_BLOCKS 8
+#define WPT_TRACE_MIN_BLOCKS 9      /* 56 registers: +1.5 % on C3 over 8 blocks (63 registers), profiles/r2x_ab.txt */
 #endif
 #ifndef WPT_SHADE_MIN_BLOCKS
 #define WPT_SHADE_MIN_BLOCKS 4
@@ -67,6 +67,13 @@ namespace wptd {
 #endif
 #ifndef WPT_ANY_HIT
 #define WPT_ANY_HIT 1       /* shadow queries towards the environment stop at the first hit (persistent trace kernel) */
+#endif
+#ifndef WPT_NODE_REPEAT
+#define WPT_NODE_REPEAT 1       /* node steps per node round of the persistent trace kernel (1 = one step per loop iteration;
+                                   2: +0.6 % on C3, -0.7 % on C2: noise level, profiles/r2y_trace_micro_ab.txt) */
+#endif
+#ifndef WPT_NODE_REPEAT_MIN
+#define WPT_NODE_REPEAT_MIN 16  /* lanes that must still be at an inner node for another step of the same round */
 #endif
 #ifndef WPT_LEAF_MIN
 #define WPT_LEAF_MIN 12     /* lanes that must be at a leaf before the persistent trace kernel runs a leaf round */
@@ -892,27 +899,37 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
          * those lanes test their primitives together. Without this, the few lanes that are at a leaf in
          * any given iteration make the whole warp pay for the leaf code every time. */
         const bool atLeaf = active && cur < 0;
-        const bool atInner = active && cur >= 0 && cur != EMPTY_CHILD;   /* (EMPTY_CHILD: the root of an empty scene) */
         const unsigned leafMask = __ballot_sync(FULL, atLeaf);
         const unsigned innerMask = activeMask & ~leafMask;
         const bool leafRound = (__popc(leafMask) >= WPT_LEAF_MIN) || innerMask == 0u;
-        if (!active && !(WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA)) && leafRound))
-            continue;       /* (idle lanes test triangles for the others in a cooperative leaf round) */
+        if (!active && leafRound && !(WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA))))
+            continue;       /* (idle lanes take part in the ballots of a node round, and test triangles for the others
+                               in a cooperative leaf round) */
 
         if (!leafRound) {
-            if (atInner) {
-                const NodeKeys nk = nodeKeys(S, cur, ray.o, h.inv, amin, best.hit.a, rows);
-                if (nk.k0 != 0xFFFFFFFFu) {
-                    if (nk.k3 != 0xFFFFFFFFu)
-                        stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k3 & 3u)), nk.k3 & ~3u);
-                    if (nk.k2 != 0xFFFFFFFFu)
-                        stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k2 & 3u)), nk.k2 & ~3u);
-                    if (nk.k1 != 0xFFFFFFFFu)
-                        stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k1 & 3u)), nk.k1 & ~3u);
-                    cur = sel4i(nk.ch, nk.k0 & 3u);
-                } else {
-                    cur = stackPopNext(smBase, spill, sp, best.hit.a);
+            /* A node round runs up to WPT_NODE_REPEAT node steps while at least WPT_NODE_REPEAT_MIN lanes are still at
+             * an inner node: the bookkeeping at the top and the bottom of the loop (~55 instructions: refill and
+             * leaf-round decisions, three ballots) is then paid once for several steps. Lanes that arrive at a leaf or
+             * finish in the first step wait for the next iteration. A lane's own walk is the same sequence either way. */
+#pragma unroll 1
+            for (int rep = 0;; rep++) {
+                if (active && cur >= 0 && cur != EMPTY_CHILD) {
+                    const NodeKeys nk = nodeKeys(S, cur, ray.o, h.inv, amin, best.hit.a, rows);
+                    if (nk.k0 != 0xFFFFFFFFu) {
+                        pushFarChildren(smBase, spill, sp, nk);
+                        cur = sel4i(nk.ch, nk.k0 & 3u);
+                    } else {
+                        cur = stackPopNext(smBase, spill, sp, best.hit.a);
+                    }
+#if WPT_PREFETCH_LEAF
+                    if (S.prefetchLeaves && cur < 0)
+                        prefetchLeaf(S, uint32_t(~cur));
+#endif
                 }
+                if (rep + 1 >= WPT_NODE_REPEAT)
+                    break;
+                if (__popc(__ballot_sync(FULL, active && cur >= 0 && cur != EMPTY_CHILD)) < WPT_NODE_REPEAT_MIN)
+                    break;
             }
         } else if (WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA)) && coopLeafRound(leafMask, atLeaf, cur)) {
             /* Cooperative leaf round: a leaf holds 1-4 triangles and only ~10 lanes wait at one, so looping over "my"
@@ -991,7 +1008,7 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
 #endif
         }
 #if WPT_PREFETCH_LEAF
-        if (S.prefetchLeaves && cur < 0 && ((!leafRound && atInner) || (leafRound && atLeaf)))
+        if (S.prefetchLeaves && cur < 0 && leafRound && atLeaf)
             prefetchLeaf(S, uint32_t(~cur));
 #endif
         if (active && cur == EMPTY_CHILD) {
