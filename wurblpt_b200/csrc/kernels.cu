@@ -36,7 +36,11 @@ namespace wptd {
 #define WPT_MIN_BLOCKS 8
 #endif
 #ifndef WPT_TRACE_MIN_BLOCKS
-#define WPT_TRACE_MIN_BLOCKS 9      /* 56 registers: +1.5 % on C3 over 8 blocks (63 registers), profiles/r2x_ab.txt */
+#define WPT_TRACE_MIN_BLOCKS 8
+#endif
+#ifndef WPT_TRACE_MIN_BLOCKS_STATIC
+#define WPT_TRACE_MIN_BLOCKS_STATIC 9   /* persistent trace kernel of static scenes without media (F == 0): 56 registers, +1.8 % on
+                                           C3 over 8 blocks (63 registers), profiles/r2x_quad_kernel_ab.txt */
 #endif
 #ifndef WPT_SHADE_MIN_BLOCKS
 #define WPT_SHADE_MIN_BLOCKS 4
@@ -793,7 +797,7 @@ WPT_DEV bool coopLeafRound(unsigned leafMask, bool atLeaf, int32_t cur)
 }
 
 template<int F>
-__global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersistentKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
+__global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC : WPT_TRACE_MIN_BLOCKS)) waveTracePersistentKernel(const __grid_constant__ DScene S, const __grid_constant__ RenderParams P)
 {
     extern __shared__ uint2 smStackAll[];
     __shared__ float4 coopResult[(WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA))) ? (BLOCK / 32) * 128 : 1];
@@ -902,10 +906,29 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
         const unsigned leafMask = __ballot_sync(FULL, atLeaf);
         const unsigned innerMask = activeMask & ~leafMask;
         const bool leafRound = (__popc(leafMask) >= WPT_LEAF_MIN) || innerMask == 0u;
+#if WPT_NODE_REPEAT > 1
         if (!active && leafRound && !(WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA))))
             continue;       /* (idle lanes take part in the ballots of a node round, and test triangles for the others
                                in a cooperative leaf round) */
+#else
+        const bool atInner = active && cur >= 0 && cur != EMPTY_CHILD;   /* (EMPTY_CHILD: the root of an empty scene) */
+        if (!active && !(WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA)) && leafRound))
+            continue;       /* (idle lanes test triangles for the others in a cooperative leaf round) */
+#endif
 
+#if WPT_NODE_REPEAT <= 1
+        if (!leafRound) {
+            if (atInner) {
+                const NodeKeys nk = nodeKeys(S, cur, ray.o, h.inv, amin, best.hit.a, rows);
+                if (nk.k0 != 0xFFFFFFFFu) {
+                    pushFarChildren(smBase, spill, sp, nk);
+                    cur = sel4i(nk.ch, nk.k0 & 3u);
+                } else {
+                    cur = stackPopNext(smBase, spill, sp, best.hit.a);
+                }
+            }
+        } else
+#else
         if (!leafRound) {
             /* A node round runs up to WPT_NODE_REPEAT node steps while at least WPT_NODE_REPEAT_MIN lanes are still at
              * an inner node: the bookkeeping at the top and the bottom of the loop (~55 instructions: refill and
@@ -931,7 +954,9 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
                 if (__popc(__ballot_sync(FULL, active && cur >= 0 && cur != EMPTY_CHILD)) < WPT_NODE_REPEAT_MIN)
                     break;
             }
-        } else if (WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA)) && coopLeafRound(leafMask, atLeaf, cur)) {
+        } else
+#endif
+        if (WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA)) && coopLeafRound(leafMask, atLeaf, cur)) {
             /* Cooperative leaf round: a leaf holds 1-4 triangles and only ~10 lanes wait at one, so looping over "my"
              * triangles runs the (long) triangle test up to four times at a third of the lanes. Instead the triangles of
              * all waiting lanes are numbered (prefix sum of the counts) and every lane of the warp tests ONE of them for
@@ -1008,7 +1033,11 @@ __global__ void __launch_bounds__(BLOCK, WPT_TRACE_MIN_BLOCKS) waveTracePersiste
 #endif
         }
 #if WPT_PREFETCH_LEAF
+#if WPT_NODE_REPEAT > 1
         if (S.prefetchLeaves && cur < 0 && leafRound && atLeaf)
+#else
+        if (S.prefetchLeaves && cur < 0 && ((!leafRound && atInner) || (leafRound && atLeaf)))
+#endif
             prefetchLeaf(S, uint32_t(~cur));
 #endif
         if (active && cur == EMPTY_CHILD) {
