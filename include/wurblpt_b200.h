@@ -504,7 +504,9 @@ int wpt_get_ground_truth(wpt_scene* scene, const wpt_camera_desc* camera, uint32
         const wpt_render_opts* opts, const wpt_ground_truth* out);
 
 /* Closest-hit queries for caller-supplied rays (origin xyz, unit direction xyz per ray;
- * host pointers). Used to check BVH::hit() parity on secondary-ray distributions. */
+ * host pointers). Used to check BVH::hit() parity on secondary-ray distributions.
+ * A ray with a non-finite origin or a direction whose squared length is not within 1e-5 of 1 (what the reference's Ray
+ * constructor asserts, ray.hpp:47-49) is refused with WPT_E_INVALID before anything runs. */
 int wpt_trace_rays(wpt_scene* scene, const float* origins, const float* directions, uint64_t n_rays,
         float time, float min_hit_distance, const wpt_render_opts* opts, int32_t* ids, float* a, uint64_t* counters);
 

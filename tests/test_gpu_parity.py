@@ -369,3 +369,27 @@ def test_more_animations_than_cache_entries_with_motion_blur(gpu):
         s.close()
     assert np.isfinite(frames[0]).all() and frames[0].mean() > 0
     assert np.array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_trace_rays_refuses_rays_the_reference_would_assert_on(gpu):
+    """Ray's constructor asserts a finite, unit-length direction (ray.hpp:47-49); wpt_trace_rays returns WPT_E_INVALID
+    for such input instead of walking the tree with it (the boxes of unused child slots are only out of reach of
+    unit directions)."""
+    g = Golden("cornell")
+    s = device_scene(gpu, g)
+    o = np.zeros((4, 3), dtype=np.float32)
+    d = np.tile(np.array([0.0, 0.0, -1.0], dtype=np.float32), (4, 1))
+    ids, dist = s.trace_rays(o, d, g.t0, 1e-4)
+    assert ids.shape == (4,)
+    for bad in (np.array([10.0, 10.0, 10.0]), np.array([0.0, 0.0, 0.0]), np.array([np.nan, 0.0, 1.0])):
+        d2 = d.copy()
+        d2[2] = bad
+        with pytest.raises(gpu.WptError) as e:
+            s.trace_rays(o, d2, g.t0, 1e-4)
+        assert e.value.code == abi.WPT_E_INVALID
+    o2 = o.copy()
+    o2[1, 0] = np.inf
+    with pytest.raises(gpu.WptError) as e:
+        s.trace_rays(o2, d, g.t0, 1e-4)
+    assert e.value.code == abi.WPT_E_INVALID

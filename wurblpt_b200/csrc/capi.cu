@@ -1501,6 +1501,17 @@ int wpt_get_ground_truth(wpt_scene* s, const wpt_camera_desc* camera, uint32_t w
 int wpt_trace_rays(wpt_scene* s, const float* origins, const float* directions, uint64_t nRays,
         float time, float minHitDistance, const wpt_render_opts* opts, int32_t* ids, float* a, uint64_t* counters)
 {
+    /* Ray's contract (ray.hpp:47-49, constants.hpp:42): a finite direction of unit length. The walks rely on it:
+     * |1 / d| >= 1 keeps the boxes of unused child slots (all planes at FLT_MAX) out of every ray's reach. */
+    if (origins && directions) {
+        for (uint64_t i = 0; i < nRays; i++) {
+            const float* d = directions + 3 * i;
+            const float* o = origins + 3 * i;
+            const float len2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            if (!(std::fabs(len2 - 1.0f) < 0.00001f) || !std::isfinite(o[0]) || !std::isfinite(o[1]) || !std::isfinite(o[2]))
+                return fail(WPT_E_INVALID, "ray " + std::to_string(i) + ": origin not finite or direction not of unit length (ray.hpp:47-49)");
+        }
+    }
     return runQuery(s, nullptr, 0, 0, origins, directions, nRays, time, minHitDistance, opts, ids, a, counters);
 }
 
