@@ -580,6 +580,18 @@ WPT_DEV uint32_t childKeyNearFar(float nx, float fx, float ny, float fy, float n
 }
 
 /* The four child keys of a wide node, sorted ascending (nearest entry distance first; 0xFFFFFFFF = missed). */
+#ifndef WPT_NODE_FAST
+#define WPT_NODE_FAST 0     /* 1: the persistent trace kernel forms the node's row addresses and child keys with nodeKeysFast();
+                               2: and marks missed children by the sign bit of the key */
+#endif
+WPT_DEV bool keyMissed(uint32_t k)
+{
+#if WPT_NODE_FAST >= 2
+    return int32_t(k) < 0;      /* 0xFFFFFFFF or any key with the sign bit set (hit keys are bits of a positive distance) */
+#else
+    return k == 0xFFFFFFFFu;
+#endif
+}
 struct NodeKeys {
     uint32_t k0, k1, k2, k3;
     int4 ch;
@@ -615,6 +627,101 @@ WPT_DEV NodeKeys nodeKeys(const DScene& S, int32_t cur, float3 o, float3 inv, fl
     return r;
 }
 
+/* Index of the near row inside each axis' pair of rows (lo row, hi row): 1 when the ray direction's component is
+ * negative (sign bit; -0 counts, its inverse is -inf), else 0. Per ray, kept in registers by the persistent trace kernel. */
+struct RowOffsets {
+    uint32_t x, y, z;
+};
+
+WPT_DEV RowOffsets rowOffsets(float3 d)
+{
+    RowOffsets r;
+    r.x = __float_as_uint(d.x) >> 31;
+    r.y = __float_as_uint(d.y) >> 31;
+    r.z = __float_as_uint(d.z) >> 31;
+    return r;
+}
+
+/* node + row * 16 bytes as ONE 64-bit multiply-add (IMAD.WIDE.U32, FMA pipe) instead of the shift / mask /
+ * add-with-carry sequence the compiler makes of an index expression (ALU pipe, the busier one in the trace kernel). */
+WPT_DEV const float4* rowAddress(const float4* node, uint32_t row)
+{
+    const float4* p;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(p) : "r"(row), "l"(node));
+    return p;
+}
+
+/* The other row of a pair: the address with bit 4 flipped (nodes are 128-byte aligned, a pair of rows 32-byte aligned),
+ * one logic operation on the low word. */
+WPT_DEV const float4* otherRow(const float4* row)
+{
+    const float4* p;
+    asm("{\n\t.reg .b32 lo, hi;\n\t"
+        "mov.b64 {lo, hi}, %1;\n\t"
+        "xor.b32 lo, lo, 16;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}"
+        : "=l"(p) : "l"(row));
+    return p;
+}
+
+/* tmin <= tmax ? (bits of tmin with the child number in the two low bits) : 0xFFFFFFFF, as compare + predicated
+ * three-input logic operation (the select of the plain form is one more ALU instruction per child). */
+template<uint32_t K>
+WPT_DEV uint32_t childKeyBits(float tmin, float tmax)
+{
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.le.f32 p, %1, %2;\n\t"
+        "mov.b32 %0, 0xffffffff;\n\t"
+        "@p lop3.b32 %0, %1, 0xfffffffc, %3, 0xEA;\n\t}"
+        : "=r"(r) : "f"(tmin), "f"(tmax), "n"(K));
+    return r;
+}
+
+template<uint32_t K>
+WPT_DEV uint32_t childKeyFast(float nx, float fx, float ny, float fy, float nz, float fz, float3 o, float3 inv, float amin, float amax)
+{
+    /* the products and the min / max of childKeyNearFar() */
+    const float tnx = (nx - o.x) * inv.x, tfx = (fx - o.x) * inv.x;
+    const float tny = (ny - o.y) * inv.y, tfy = (fy - o.y) * inv.y;
+    const float tnz = (nz - o.z) * inv.z, tfz = (fz - o.z) * inv.z;
+    const float tmin = fmaxf(fmaxf(amin, tnx), fmaxf(tny, tnz));
+    const float tmax = fminf(fminf(amax, tfx), fminf(tfy, tfz));
+#if WPT_NODE_FAST >= 2
+    /* A missed child is marked by the SIGN BIT of its key instead of the value 0xFFFFFFFF (keyMissed() accepts both):
+     * tmax - tmin is negative exactly when tmin > tmax (no flush to zero: a difference of two different floats is not
+     * zero; equal values give +0), tmin >= amin > 0 has a clear sign bit. One subtraction on the FMA pipe and one logic
+     * operation replace a compare and a select on the ALU pipe. */
+    const float d = tmax - tmin;
+    uint32_t t, key;
+    asm("lop3.b32 %0, %1, 0xfffffffc, %2, 0xEA;" : "=r"(t) : "f"(tmin), "n"(K));
+    asm("lop3.b32 %0, %1, %2, 0x80000000, 0xF8;" : "=r"(key) : "r"(t), "f"(d));
+    return key;
+#else
+    return childKeyBits<K>(tmin, tmax);
+#endif
+}
+
+/* nodeKeys() for a walk that keeps the ray's row offsets: same loads, same arithmetic, same keys. */
+WPT_DEV NodeKeys nodeKeysFast(const DScene& S, int32_t cur, float3 o, float3 inv, float amin, float amax, RowOffsets off)
+{
+    NodeKeys r;
+    const float4* n = S.node4 + size_t(cur) * 8;
+    const float4* px = rowAddress(n, off.x);
+    const float4* py = rowAddress(n, off.y);
+    const float4* pz = rowAddress(n, off.z);
+    const float4 nx = __ldg(px), fx = __ldg(otherRow(px));
+    const float4 ny = __ldg(py + 2), fy = __ldg(otherRow(py) + 2);
+    const float4 nz = __ldg(pz + 4), fz = __ldg(otherRow(pz) + 4);
+    r.ch = __ldg(reinterpret_cast<const int4*>(n + 6));
+    r.k0 = childKeyFast<0>(nx.x, fx.x, ny.x, fy.x, nz.x, fz.x, o, inv, amin, amax);
+    r.k1 = childKeyFast<1>(nx.y, fx.y, ny.y, fy.y, nz.y, fz.y, o, inv, amin, amax);
+    r.k2 = childKeyFast<2>(nx.z, fx.z, ny.z, fy.z, nz.z, fz.z, o, inv, amin, amax);
+    r.k3 = childKeyFast<3>(nx.w, fx.w, ny.w, fy.w, nz.w, fz.w, o, inv, amin, amax);
+    sort2(r.k0, r.k1); sort2(r.k2, r.k3); sort2(r.k0, r.k2); sort2(r.k1, r.k3); sort2(r.k1, r.k2);
+    return r;
+}
+
 /* The far children of a node whose nearest child is visited next: k1..k3 of the sorted keys, farthest first (the hit
  * ones are a prefix of the sorted order: k3 hit implies k2 and k1 hit). */
 WPT_DEV void pushFarChildren(uint32_t smBase, uint2* spill, int& sp, const NodeKeys& nk)
@@ -633,12 +740,65 @@ WPT_DEV void pushFarChildren(uint32_t smBase, uint2* spill, int& sp, const NodeK
         return;
     }
 #endif
-    if (nk.k3 != 0xFFFFFFFFu)
+    if (!keyMissed(nk.k3))
         stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k3 & 3u)), nk.k3 & ~3u);
-    if (nk.k2 != 0xFFFFFFFFu)
+    if (!keyMissed(nk.k2))
         stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k2 & 3u)), nk.k2 & ~3u);
-    if (nk.k1 != 0xFFFFFFFFu)
+    if (!keyMissed(nk.k1))
         stackPush(smBase, spill, sp, uint32_t(sel4i(nk.ch, nk.k1 & 3u)), nk.k1 & ~3u);
+}
+
+#ifndef WPT_STACK_TOS
+#define WPT_STACK_TOS 0     /* 1: the persistent trace kernel keeps the youngest stack entry in registers */
+#endif
+
+/* The youngest entry of the walk's stack in registers (code == EMPTY_CHILD: the stack is empty). A pop hands it out and
+ * asks shared memory for the entry below it, which is not needed before the NEXT pop: the load's latency (the wait at
+ * `tmin <= limit`, 6 % of the trace kernel's stall samples) is off the critical path. */
+struct StackTop {
+    uint32_t code, tmin;
+};
+
+WPT_DEV void stackPushTop(uint32_t smBase, uint2* spill, int& sp, StackTop& top, uint32_t code, uint32_t tminBits)
+{
+    if (top.code != uint32_t(EMPTY_CHILD))
+        stackPush(smBase, spill, sp, top.code, top.tmin);
+    top.code = code;
+    top.tmin = tminBits;
+}
+
+WPT_DEV int32_t stackPopNextTop(uint32_t smBase, const uint2* spill, int& sp, StackTop& top, float limit)
+{
+    while (top.code != uint32_t(EMPTY_CHILD)) {
+        const uint32_t code = top.code;
+        const float tmin = __uint_as_float(top.tmin);
+        if (sp > 0) {
+            --sp;
+            uint2 e;
+            if (sp < SM_STACK)
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y)
+                        : "r"(smBase + uint32_t(sp) * uint32_t(WPT_STACK_STRIDE * sizeof(uint2))) : "memory");
+            else
+                e = spill[sp - SM_STACK];
+            top.code = e.x;
+            top.tmin = e.y;
+        } else {
+            top.code = uint32_t(EMPTY_CHILD);
+        }
+        if (tmin <= limit)
+            return int32_t(code);
+    }
+    return EMPTY_CHILD;
+}
+
+WPT_DEV void pushFarChildrenTop(uint32_t smBase, uint2* spill, int& sp, StackTop& top, const NodeKeys& nk)
+{
+    if (!keyMissed(nk.k3))
+        stackPushTop(smBase, spill, sp, top, uint32_t(sel4i(nk.ch, nk.k3 & 3u)), nk.k3 & ~3u);
+    if (!keyMissed(nk.k2))
+        stackPushTop(smBase, spill, sp, top, uint32_t(sel4i(nk.ch, nk.k2 & 3u)), nk.k2 & ~3u);
+    if (!keyMissed(nk.k1))
+        stackPushTop(smBase, spill, sp, top, uint32_t(sel4i(nk.ch, nk.k1 & 3u)), nk.k1 & ~3u);
 }
 
 /* bit 0/1/2: the ray direction's x/y/z is negative (sign bit; -0 counts, its inverse is -inf) */

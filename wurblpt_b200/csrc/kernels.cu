@@ -54,6 +54,10 @@ namespace wptd {
 #ifndef WPT_PREFETCH_LEAF
 #define WPT_PREFETCH_LEAF 1
 #endif
+#ifndef WPT_PREFETCH_NODE
+#define WPT_PREFETCH_NODE 0     /* 1: the persistent trace kernel asks for the next inner node (one 128-byte line) the moment it is
+                                   chosen or popped, a loop-top's worth of instructions before its rows are loaded */
+#endif
 #ifndef WPT_CAMERA_REFILL_MIN
 #define WPT_CAMERA_REFILL_MIN 32
 #endif
@@ -826,7 +830,11 @@ __global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC :
     Ray ray;
     ray.o = f3(0.0f); ray.d = f3(0.0f, 0.0f, 1.0f); ray.time = 0.0f;
     RayHelper h = makeRayHelper(ray);
+#if WPT_NODE_FAST
+    RowOffsets rows = rowOffsets(ray.d);
+#else
     uint32_t rows = 0;                  /* octantRows(ray.d); only used with WPT_OCTANT_ROWS */
+#endif
     WideBest best;
     best.hit.a = MAXVAL;
     best.hit.ref = NO_HIT;
@@ -836,6 +844,16 @@ __global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC :
     const uint32_t smBase = uint32_t(__cvta_generic_to_shared(smStackAll + threadIdx.x));
     uint2 spill[LOCAL_STACK];
     int sp = 0;
+#if WPT_STACK_TOS
+    StackTop top;
+    top.code = uint32_t(EMPTY_CHILD);
+    top.tmin = 0u;
+#define WPT_PUSH_FAR(nk) pushFarChildrenTop(smBase, spill, sp, top, nk)
+#define WPT_POP_NEXT() stackPopNextTop(smBase, spill, sp, top, best.hit.a)
+#else
+#define WPT_PUSH_FAR(nk) pushFarChildren(smBase, spill, sp, nk)
+#define WPT_POP_NEXT() stackPopNext(smBase, spill, sp, best.hit.a)
+#endif
     const float amin = P.minHit;
 
     /* Tickets are drawn from the global counter a chunk at a time and handed out inside the warp
@@ -882,12 +900,19 @@ __global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC :
                 }
                 animationCacheInit<F>(S, ctx, ray.time);
                 h = makeRayHelper(ray);
+#if WPT_NODE_FAST
+                rows = rowOffsets(ray.d);
+#else
                 rows = octantRows(ray.d);
+#endif
                 entry = e;
                 active = true;
                 best.hit.a = MAXVAL;
                 best.hit.ref = NO_HIT;
                 sp = 0;
+#if WPT_STACK_TOS
+                top.code = uint32_t(EMPTY_CHILD);
+#endif
                 cur = S.root4;
             }
             const unsigned gotMask = __ballot_sync(FULL, got);
@@ -919,12 +944,16 @@ __global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC :
 #if WPT_NODE_REPEAT <= 1
         if (!leafRound) {
             if (atInner) {
+#if WPT_NODE_FAST
+                const NodeKeys nk = nodeKeysFast(S, cur, ray.o, h.inv, amin, best.hit.a, rows);
+#else
                 const NodeKeys nk = nodeKeys(S, cur, ray.o, h.inv, amin, best.hit.a, rows);
-                if (nk.k0 != 0xFFFFFFFFu) {
-                    pushFarChildren(smBase, spill, sp, nk);
+#endif
+                if (!keyMissed(nk.k0)) {
+                    WPT_PUSH_FAR(nk);
                     cur = sel4i(nk.ch, nk.k0 & 3u);
                 } else {
-                    cur = stackPopNext(smBase, spill, sp, best.hit.a);
+                    cur = WPT_POP_NEXT();
                 }
             }
         } else
@@ -937,12 +966,16 @@ __global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC :
 #pragma unroll 1
             for (int rep = 0;; rep++) {
                 if (active && cur >= 0 && cur != EMPTY_CHILD) {
+#if WPT_NODE_FAST
+                    const NodeKeys nk = nodeKeysFast(S, cur, ray.o, h.inv, amin, best.hit.a, rows);
+#else
                     const NodeKeys nk = nodeKeys(S, cur, ray.o, h.inv, amin, best.hit.a, rows);
-                    if (nk.k0 != 0xFFFFFFFFu) {
-                        pushFarChildren(smBase, spill, sp, nk);
+#endif
+                    if (!keyMissed(nk.k0)) {
+                        WPT_PUSH_FAR(nk);
                         cur = sel4i(nk.ch, nk.k0 & 3u);
                     } else {
-                        cur = stackPopNext(smBase, spill, sp, best.hit.a);
+                        cur = WPT_POP_NEXT();
                     }
 #if WPT_PREFETCH_LEAF
                     if (S.prefetchLeaves && cur < 0)
@@ -1018,18 +1051,18 @@ __global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC :
                     if (r.w != 0.0f && !(r.y > best.hit.a * r.z))
                         considerHit(best, (PRIM_TRIANGLE << REF_TYPE_SHIFT) | (first + i), r.x, r.y, r.z);
                 }
-                cur = stackPopNext(smBase, spill, sp, best.hit.a);
+                cur = WPT_POP_NEXT();
             }
             __syncwarp();
         } else if (atLeaf) {
 #if WPT_LEAF_UNIT
             /* one primitive per lane and leaf round; what is left of a run stays this lane's leaf */
             const uint32_t rest = wideLeafStep<F>(S, uint32_t(~cur), ray, h, amin, P.minHit, ctx, best);
-            cur = (rest != NO_HIT ? int32_t(~rest) : stackPopNext(smBase, spill, sp, best.hit.a));
+            cur = (rest != NO_HIT ? int32_t(~rest) : WPT_POP_NEXT());
 #else
             wideLeaf<F>(S, uint32_t(~cur), ray, h, amin, P.minHit, ctx, best);
             /* occlusion query: the first hit answers it */
-            cur = (anyHitScene && (entry & 1u) && best.hit.ref != NO_HIT) ? EMPTY_CHILD : stackPopNext(smBase, spill, sp, best.hit.a);
+            cur = (anyHitScene && (entry & 1u) && best.hit.ref != NO_HIT) ? EMPTY_CHILD : WPT_POP_NEXT();
 #endif
         }
 #if WPT_PREFETCH_LEAF
@@ -1039,6 +1072,10 @@ __global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC :
         if (S.prefetchLeaves && cur < 0 && ((!leafRound && atInner) || (leafRound && atLeaf)))
 #endif
             prefetchLeaf(S, uint32_t(~cur));
+#endif
+#if WPT_PREFETCH_NODE && WPT_NODE_REPEAT <= 1
+        if (S.prefetchLeaves && cur >= 0 && cur != EMPTY_CHILD && ((!leafRound && atInner) || (leafRound && atLeaf)))
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(S.node4 + size_t(cur) * 8));
 #endif
         if (active && cur == EMPTY_CHILD) {
             reinterpret_cast<uint2*>(P.W.hit)[entry] = make_uint2(__float_as_uint(best.hit.a), best.hit.ref);
@@ -1051,6 +1088,8 @@ __global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC :
     if (lane == 0 && q)
         atomicAdd(P.counters + CTR_NESTED, (unsigned long long)q);
 }
+#undef WPT_PUSH_FAR
+#undef WPT_POP_NEXT
 
 /* ------------------------------------------------------------ quad trace kernel */
 
