@@ -832,6 +832,99 @@ WPT_DEV void considerHit(WideBest& best, uint32_t ref, float a, float Ts, float 
     }
 }
 
+#ifndef WPT_MEDIUM_COOP
+#define WPT_MEDIUM_COOP 1   /* the persistent trace kernel tests small triangle boundaries of media with the whole warp */
+#endif
+
+/* HitableMedium::hit (hitable_medium.hpp:69-98) for the lanes of a warp whose walk waits at a medium whose boundary is a
+ * small triangle mesh (`run` != 0: first triangle slot | count << 26, count <= 32; scene_host.cpp). Called by ALL lanes
+ * of the warp. The per-lane form (mediumTest) walks the nested tree twice per medium - some thousand instructions at
+ * the handful of lanes that wait at a medium, while the rest of the warp idles. Here the lanes that wait are served one
+ * after the other: the owner's ray goes to all lanes by shuffle, lane j runs the watertight test of boundary triangle j
+ * ONCE without bounds (a triangle's distance along the line does not depend on them), and the two closest-hit queries of
+ * the reference (first crossing on the whole line, next crossing behind it) are replayed over the triangles that were
+ * hit, in slot order = the order the nested walk meets them, with the very comparisons of the bounded test
+ * (hitable_triangle.hpp:263-264) against the shrinking upper bound (bvh.hpp:292-295). What the box tests of the nested
+ * walk would have culled fails those comparisons as well, so the two distances are the nested walk's. The owner then
+ * samples the free flight from its own Prng exactly as mediumTest does. Scenes without animated hitables only (the
+ * corners are read for the owner's time). */
+template<int F>
+WPT_DEV void mediumRoundCoop(const DScene& S, uint32_t run, uint32_t mediumRef, const Ray& ray, const RayHelper& h,
+        float amin, float minHit, Ctx<F>& ctx, WideBest& best)
+{
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned waiting = __ballot_sync(FULL, run != 0u);
+    const uint32_t kpack = uint32_t(h.kx) | (uint32_t(h.ky) << 2) | (uint32_t(h.kz) << 4);
+    while (waiting != 0u) {
+        const int owner = __ffs(waiting) - 1;
+        waiting &= waiting - 1u;
+        Ray oray;
+        oray.o = f3(__shfl_sync(FULL, ray.o.x, owner), __shfl_sync(FULL, ray.o.y, owner), __shfl_sync(FULL, ray.o.z, owner));
+        oray.d = f3(0.0f);
+        oray.time = 0.0f;
+        RayHelper oh;
+        oh.inv = f3(0.0f);
+        oh.Sx = __shfl_sync(FULL, h.Sx, owner);
+        oh.Sy = __shfl_sync(FULL, h.Sy, owner);
+        oh.Sz = __shfl_sync(FULL, h.Sz, owner);
+        const uint32_t ok = __shfl_sync(FULL, kpack, owner);
+        oh.kx = int(ok & 3u); oh.ky = int((ok >> 2) & 3u); oh.kz = int(ok >> 4);
+        const uint32_t orun = __shfl_sync(FULL, run, owner);
+        const uint32_t first = orun & ((1u << 26) - 1u), count = orun >> 26;
+        float ta = 0.0f, Ts = 0.0f, da = 0.0f;
+        bool found = false;
+        if (lane < count) {
+            const float4* tp = S.tri + size_t(first + lane) * 3;
+            const float4 t0 = __ldg(tp + 0), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+            float U, V, W, det;
+            found = triangleTest(xyz(t0), xyz(t1), xyz(t2), oray, oh, 0.0f, 0.0f, false, ta, U, V, W, det, Ts, da);
+        }
+        unsigned hits = __ballot_sync(FULL, found);
+        /* first query: (-maxval, maxval); second query: (a1 + minHitDistance, maxval) */
+        float a1 = MAXVAL, a2 = MAXVAL;
+        bool have1 = false, have2 = false;
+        for (unsigned m = hits; m != 0u; m &= m - 1u) {
+            const int j = __ffs(m) - 1;
+            const float Tj = __shfl_sync(FULL, Ts, j), dj = __shfl_sync(FULL, da, j), aj = __shfl_sync(FULL, ta, j);
+            if (!(Tj < -MAXVAL * dj || Tj > a1 * dj)) {
+                a1 = aj;
+                have1 = true;
+            }
+        }
+        if (have1) {
+            const float lo = a1 + minHit;
+            for (unsigned m = hits; m != 0u; m &= m - 1u) {
+                const int j = __ffs(m) - 1;
+                const float Tj = __shfl_sync(FULL, Ts, j), dj = __shfl_sync(FULL, da, j), aj = __shfl_sync(FULL, ta, j);
+                if (!(Tj < lo * dj || Tj > a2 * dj)) {
+                    a2 = aj;
+                    have2 = true;
+                }
+            }
+        }
+        if (int(lane) == owner) {
+            ctx.nested += have1 ? 2u : 1u;
+            if (have1 && have2) {
+                const float amax = best.hit.a;
+                if (a1 < amin)
+                    a1 = amin;
+                if (a2 > amax)
+                    a2 = amax;
+                if (a1 < a2) {
+                    if (a1 < 0.0f)
+                        a1 = 0.0f;
+                    const float inside = a2 - a1;
+                    const float density = __ldg(S.med + (mediumRef & REF_SLOT_MASK)).x;
+                    const float freeFlight = -(1.0f / density) * logf(in01(ctx.prng));
+                    if (freeFlight < inside)
+                        considerHit(best, mediumRef, a1 + freeFlight, 0.0f, 0.0f);
+                }
+            }
+        }
+    }
+}
+
 /* A leaf of the wide tree: one hitable, or a run of up to four consecutive triangle slots. */
 template<int F>
 WPT_DEV void wideLeaf(const DScene& S, uint32_t ref, const Ray& ray, const RayHelper& h,

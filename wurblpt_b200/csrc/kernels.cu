@@ -825,6 +825,8 @@ __global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC :
      * "nothing hit" is read of its answer (consumeShadow), so its walk may stop at the first hit instead of looking for
      * the closest one. Not with media: their walks draw from the Prng, the draws must not depend on the visiting order. */
     const bool anyHitScene = WPT_ANY_HIT && !(F & F_MEDIA) && S.nHot == 0u;
+    /* media bounded by a small triangle mesh are tested by the whole warp in leaf rounds (mediumRoundCoop) */
+    constexpr bool MEDIUM_COOP = WPT_MEDIUM_COOP && (F & F_MEDIA) && !(F & F_ANIM);
     unsigned int entry = 0;             /* slot << 1 | query of the walk in progress */
     bool active = false;
     Ray ray;
@@ -932,15 +934,28 @@ __global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC :
         const unsigned innerMask = activeMask & ~leafMask;
         const bool leafRound = (__popc(leafMask) >= WPT_LEAF_MIN) || innerMask == 0u;
 #if WPT_NODE_REPEAT > 1
-        if (!active && leafRound && !(WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA))))
+        if (!active && leafRound && !(WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA))) && !MEDIUM_COOP)
             continue;       /* (idle lanes take part in the ballots of a node round, and test triangles for the others
                                in a cooperative leaf round) */
 #else
         const bool atInner = active && cur >= 0 && cur != EMPTY_CHILD;   /* (EMPTY_CHILD: the root of an empty scene) */
-        if (!active && !(WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA)) && leafRound))
+        if (!active && !(((WPT_LEAF_COOP && !(F & (F_ANIM | F_MEDIA))) || MEDIUM_COOP) && leafRound))
             continue;       /* (idle lanes test triangles for the others in a cooperative leaf round) */
 #endif
 
+        bool mediumDone = false;
+        if (MEDIUM_COOP && leafRound) {
+            uint32_t run = 0u;
+            if (atLeaf && (uint32_t(~cur) >> REF_TYPE_SHIFT) == PRIM_MEDIUM)
+                run = __float_as_uint(__ldg(S.med + (uint32_t(~cur) & REF_SLOT_MASK)).w);
+            if (__any_sync(FULL, run != 0u)) {
+                mediumRoundCoop<F>(S, run, uint32_t(~cur), ray, h, amin, P.minHit, ctx, best);
+                if (run != 0u) {
+                    cur = WPT_POP_NEXT();
+                    mediumDone = true;
+                }
+            }
+        }
 #if WPT_NODE_REPEAT <= 1
         if (!leafRound) {
             if (atInner) {
@@ -1054,7 +1069,7 @@ __global__ void __launch_bounds__(BLOCK, (F == 0 ? WPT_TRACE_MIN_BLOCKS_STATIC :
                 cur = WPT_POP_NEXT();
             }
             __syncwarp();
-        } else if (atLeaf) {
+        } else if (atLeaf && !mediumDone) {
 #if WPT_LEAF_UNIT
             /* one primitive per lane and leaf round; what is left of a run stays this lane's leaf */
             const uint32_t rest = wideLeafStep<F>(S, uint32_t(~cur), ray, h, amin, P.minHit, ctx, best);

@@ -715,6 +715,13 @@ int HostScene::updateBvh(float t0, float t1)
         for (uint64_t i = 0; i < topLevelNodes; i++)
             if (bnodes[i].leaf != INNER)
                 assignSlot(bnodes[i].leaf);
+    /* the hitables that bound a medium, in the order the nested tree stores them: a medium whose boundary is a small
+     * triangle mesh then owns a run of consecutive triangle slots in the order the nested walk meets them (medData) */
+    for (size_t m = 0; m < media.size(); m++)
+        if (nestedBase[m] != NO_NODE)
+            for (uint64_t i = nestedBase[m]; i < uint64_t(nestedBase[m]) + 2 * uint64_t(media[m].boundary_count) - 1; i++)
+                if (bnodes[i].leaf != INNER)
+                    assignSlot(bnodes[i].leaf);
     for (uint32_t id = 0; id < prims.size(); id++)
         assignSlot(id);
     if (!topLevel.empty() || !media.empty()) {
@@ -777,7 +784,32 @@ int HostScene::updateBvh(float t0, float t1)
         d[0] = media[mi].density;
         d[1] = bits(uint32_t(media[mi].material));
         d[2] = bits(mediumRoot[mi]);
-        d[3] = 0.0f;
+        /* boundary = up to 32 triangles in consecutive slots (the nested tree's storage order, see above): first slot |
+         * count << 26 for the trace kernel's warp-wide boundary test; 0 = walk the nested tree */
+        uint32_t run = 0;
+        const uint32_t count = media[mi].boundary_count;
+        if (mediumRoot[mi] != NO_NODE && count >= 1 && count <= 32) {
+            bool ok = true;
+            uint32_t first = 0xFFFFFFFFu, next = 0;
+            for (uint64_t i = mediumRoot[mi]; ok && i < uint64_t(mediumRoot[mi]) + 2 * uint64_t(count) - 1; i++) {
+                if (bnodes[i].leaf == INNER)
+                    continue;
+                const uint32_t ref = bnodes[i].leaf;        /* already a slot reference */
+                if ((ref >> REF_TYPE_SHIFT) != PRIM_TRIANGLE) {
+                    ok = false;
+                } else if (first == 0xFFFFFFFFu) {
+                    first = ref & REF_SLOT_MASK;
+                    next = first + 1;
+                } else if ((ref & REF_SLOT_MASK) == next) {
+                    next++;
+                } else {
+                    ok = false;
+                }
+            }
+            if (ok && first != 0xFFFFFFFFu && next - first == count && first < (1u << 26))
+                run = first | (count << 26);
+        }
+        d[3] = bits(run);
     }
     hotSpotRefs.clear();
     for (uint32_t id : hotSpotIds)
