@@ -362,7 +362,8 @@ typedef struct wpt_scene_info {
     uint64_t wide_nodes;
     uint32_t binary_depth, wide_depth;
     uint32_t hot_spots;
-    uint32_t _pad;
+    uint32_t warp_tested_media; /* media whose boundary (a mesh of up to 32 triangles) the trace kernel tests with a whole
+                                   warp instead of walking the nested boundary tree per lane (hitable_medium.hpp:69-98) */
     uint64_t device_bytes;
     double build_seconds;       /* host SAH build + collapse */
     double upload_seconds;

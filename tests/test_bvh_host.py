@@ -76,3 +76,19 @@ def test_single_hitable_tree(capi):
     s = capi.Scene(g.desc, device=-1).update_bvh()
     boxes, link, leaf = s.binary_nodes()
     assert s.info().hitables == 1 and len(leaf) == 1 and leaf[0] == 0
+
+
+def test_small_triangle_boundaries_of_media_are_marked_for_the_warp_wide_test(capi):
+    """HitableMedium::hit (hitable_medium.hpp:69-98) asks the boundary's BVH twice. A boundary that is a mesh of up to 32
+    triangles gets consecutive triangle slots in the nested tree's storage order and is tested by a whole warp of the
+    trace kernel; other boundaries keep the nested walk. The media fixture has one of each: the icosahedron around the
+    dense medium and the sphere around the thin one."""
+    g = Golden("media")
+    assert g.desc.n_media == 2
+    s = capi.Scene(g.desc, device=-1).update_bvh(g.t0, g.t1)
+    info = s.info()
+    assert info.media == 2
+    assert info.warp_tested_media == 1
+    # scenes without media: nothing to mark
+    c = capi.Scene(Golden("cornell").desc, device=-1).update_bvh()
+    assert c.info().warp_tested_media == 0

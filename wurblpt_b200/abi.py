@@ -140,7 +140,7 @@ class wpt_stats(C.Structure):
 class wpt_scene_info(C.Structure):
     _fields_ = [("hitables", u64), ("triangles", u64), ("spheres", u64), ("media", u64),
                 ("binary_nodes", u64), ("wide_nodes", u64),
-                ("binary_depth", u32), ("wide_depth", u32), ("hot_spots", u32), ("_pad", u32),
+                ("binary_depth", u32), ("wide_depth", u32), ("hot_spots", u32), ("warp_tested_media", u32),
                 ("device_bytes", u64), ("build_seconds", C.c_double), ("upload_seconds", C.c_double)]
 
 

@@ -860,6 +860,11 @@ int wpt_scene_get_info(const wpt_scene* s, wpt_scene_info* info)
     info->binary_depth = h.binaryDepth;
     info->wide_depth = h.wideDepth;
     info->hot_spots = uint32_t(h.hotSpotIds.size());
+    for (size_t m = 0; m < h.medGlobal.size(); m++) {
+        uint32_t run;
+        std::memcpy(&run, &h.medData[m * 4 + 3], sizeof(run));
+        info->warp_tested_media += (run != 0u);
+    }
     info->device_bytes = s->deviceBytes();
     info->build_seconds = h.buildSeconds;
     info->upload_seconds = s->uploadSeconds;
