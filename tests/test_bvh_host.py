@@ -90,5 +90,6 @@ def test_small_triangle_boundaries_of_media_are_marked_for_the_warp_wide_test(ca
     assert info.media == 2
     assert info.warp_tested_media == 1
     # scenes without media: nothing to mark
-    c = capi.Scene(Golden("cornell").desc, device=-1).update_bvh()
+    cornell = Golden("cornell")     # (keeps the arrays behind the description alive)
+    c = capi.Scene(cornell.desc, device=-1).update_bvh()
     assert c.info().warp_tested_media == 0
