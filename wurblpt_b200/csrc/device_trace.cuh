@@ -395,15 +395,60 @@ WPT_DEV bool mediumTest(const DScene& S, uint32_t slot, const Ray& ray, const Ra
     const uint32_t root = __float_as_uint(m.z);
     if (root == NO_NODE)
         return false;
-    ctx.nested++;
-    Hit hr1 = traverseReference<F, false>(S, root, ray, h, -MAXVAL, MAXVAL, minHit, ctx);
-    if (hr1.ref == NO_HIT)
-        return false;
-    ctx.nested++;
-    Hit hr2 = traverseReference<F, false>(S, root, ray, h, hr1.a + minHit, MAXVAL, minHit, ctx);
-    if (hr2.ref == NO_HIT)
-        return false;
-    float a1 = hr1.a, a2 = hr2.a;
+    float a1, a2;
+    const uint32_t run = (F & F_ANIM) ? 0u : __float_as_uint(m.w);     /* (animated scenes: nested walks in every kernel) */
+    if (run != 0u) {
+        /* The boundary is a small triangle mesh in consecutive slots, in the nested tree's storage order (scene_host.cpp).
+         * The persistent trace kernel tests such a boundary with a whole warp (mediumRoundCoop): every triangle once
+         * without bounds, then the reference's two queries replayed over the hit triangles with the bounded test's own
+         * comparisons. This is the same computation for one thread - same tests, same comparisons, same order - so that a
+         * query gets the same answer bit for bit whichever kernel serves it (frames do not depend on which slots the drain
+         * kernel finishes, nor on the number of GPUs). The box tests of the nested walk are left out: what they cull
+         * fails the comparisons too. */
+        const uint32_t first = run & ((1u << 26) - 1u), count = run >> 26;
+        bool have1 = false, have2 = false;
+        a1 = a2 = MAXVAL;
+        ctx.nested++;
+        for (uint32_t j = 0; j < count; j++) {
+            float3 v0, v1, v2;
+            uint32_t inst, tri, anim;
+            triangleCorners<F>(S, first + j, ctx, v0, v1, v2, inst, tri, anim);
+            float ta, U, V, W, det, Ts, da;
+            if (triangleTest(v0, v1, v2, ray, h, 0.0f, 0.0f, false, ta, U, V, W, det, Ts, da)
+                    && !(Ts < -MAXVAL * da || Ts > a1 * da)) {
+                a1 = ta;
+                have1 = true;
+            }
+        }
+        if (!have1)
+            return false;
+        ctx.nested++;
+        const float lo = a1 + minHit;
+        for (uint32_t j = 0; j < count; j++) {
+            float3 v0, v1, v2;
+            uint32_t inst, tri, anim;
+            triangleCorners<F>(S, first + j, ctx, v0, v1, v2, inst, tri, anim);
+            float ta, U, V, W, det, Ts, da;
+            if (triangleTest(v0, v1, v2, ray, h, 0.0f, 0.0f, false, ta, U, V, W, det, Ts, da)
+                    && !(Ts < lo * da || Ts > a2 * da)) {
+                a2 = ta;
+                have2 = true;
+            }
+        }
+        if (!have2)
+            return false;
+    } else {
+        ctx.nested++;
+        Hit hr1 = traverseReference<F, false>(S, root, ray, h, -MAXVAL, MAXVAL, minHit, ctx);
+        if (hr1.ref == NO_HIT)
+            return false;
+        ctx.nested++;
+        Hit hr2 = traverseReference<F, false>(S, root, ray, h, hr1.a + minHit, MAXVAL, minHit, ctx);
+        if (hr2.ref == NO_HIT)
+            return false;
+        a1 = hr1.a;
+        a2 = hr2.a;
+    }
     if (a1 < amin)
         a1 = amin;
     if (a2 > amax)
