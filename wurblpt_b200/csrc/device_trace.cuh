@@ -900,6 +900,8 @@ WPT_DEV void mediumRoundCoop(const DScene& S, uint32_t run, uint32_t mediumRef, 
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;
     unsigned waiting = __ballot_sync(FULL, run != 0u);
+    float myA1 = 0.0f, myA2 = 0.0f;     /* this lane's two boundary distances, if it is an owner and both queries hit */
+    bool myBoth = false;
     const uint32_t kpack = uint32_t(h.kx) | (uint32_t(h.ky) << 2) | (uint32_t(h.kz) << 4);
     while (waiting != 0u) {
         const int owner = __ffs(waiting) - 1;
@@ -950,22 +952,27 @@ WPT_DEV void mediumRoundCoop(const DScene& S, uint32_t run, uint32_t mediumRef, 
         }
         if (int(lane) == owner) {
             ctx.nested += have1 ? 2u : 1u;
-            if (have1 && have2) {
-                const float amax = best.hit.a;
-                if (a1 < amin)
-                    a1 = amin;
-                if (a2 > amax)
-                    a2 = amax;
-                if (a1 < a2) {
-                    if (a1 < 0.0f)
-                        a1 = 0.0f;
-                    const float inside = a2 - a1;
-                    const float density = __ldg(S.med + (mediumRef & REF_SLOT_MASK)).x;
-                    const float freeFlight = -(1.0f / density) * logf(in01(ctx.prng));
-                    if (freeFlight < inside)
-                        considerHit(best, mediumRef, a1 + freeFlight, 0.0f, 0.0f);
-                }
-            }
+            myA1 = a1;
+            myA2 = a2;
+            myBoth = have1 && have2;
+        }
+    }
+    /* the owners sample their free flights together (hitable_medium.hpp:83-95) */
+    if (myBoth) {
+        float a1 = myA1, a2 = myA2;
+        const float amax = best.hit.a;
+        if (a1 < amin)
+            a1 = amin;
+        if (a2 > amax)
+            a2 = amax;
+        if (a1 < a2) {
+            if (a1 < 0.0f)
+                a1 = 0.0f;
+            const float inside = a2 - a1;
+            const float density = __ldg(S.med + (mediumRef & REF_SLOT_MASK)).x;
+            const float freeFlight = -(1.0f / density) * logf(in01(ctx.prng));
+            if (freeFlight < inside)
+                considerHit(best, mediumRef, a1 + freeFlight, 0.0f, 0.0f);
         }
     }
 }
