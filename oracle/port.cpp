@@ -112,8 +112,9 @@ struct Prim {
     int32_t id;         /* global hitable id */
 };
 
-/* hitable_triangle.hpp:189-271 (distance only) */
-inline bool hitTriangle(const Prim& p, const Ray& r, const Helper& h, float amin, float amax, float& a)
+/* hitable_triangle.hpp:189-262: the watertight test on the ray's whole line. On a hit: Ts = T with the sign of det
+ * folded in, ds = |det| (:263 compares these with the bounds), a = the distance (:266-267). */
+inline bool triangleOnLine(const Prim& p, const Ray& r, const Helper& h, float& Ts, float& ds, float& a)
 {
     const V3 A = p.v0 - r.o, B = p.v1 - r.o, C = p.v2 - r.o;
     const float Ax = at(A, h.kx) - h.Sx * at(A, h.kz), Ay = at(A, h.ky) - h.Sy * at(A, h.kz);
@@ -133,10 +134,21 @@ inline bool hitTriangle(const Prim& p, const Ray& r, const Helper& h, float amin
         return false;
     const float Az = h.Sz * at(A, h.kz), Bz = h.Sz * at(B, h.kz), Cz = h.Sz * at(C, h.kz);
     const float T = U * Az + V * Bz + W * Cz;
-    const float Ts = std::signbit(det) ? -T : T, ds = std::signbit(det) ? -det : det;   /* xorf with the sign mask */
+    Ts = std::signbit(det) ? -T : T;        /* xorf with the sign mask */
+    ds = std::signbit(det) ? -det : det;
+    a = (1.0f / det) * T;
+    return true;
+}
+
+/* hitable_triangle.hpp:189-271 (distance only) */
+inline bool hitTriangle(const Prim& p, const Ray& r, const Helper& h, float amin, float amax, float& a)
+{
+    float Ts, ds, dist;
+    if (!triangleOnLine(p, r, h, Ts, ds, dist))
+        return false;
     if (Ts < amin * ds || Ts > amax * ds)
         return false;
-    a = (1.0f / det) * T;
+    a = dist;
     return true;
 }
 
@@ -411,6 +423,119 @@ int port_trace_rays(const wpt_scene_desc* desc, const float* origins, const floa
         a[i] = dist;
     }
     return 0;
+}
+
+/* The hitables that bound medium `medium` (static triangles only) as a Tree: HitableMedium::updateBVH
+ * (hitable_medium.hpp:59-62) builds the same kind of BVH over them as the scene does over its hitables. */
+int buildBoundaryTree(const wpt_scene_desc* d, uint32_t medium, Tree& t)
+{
+    if (medium >= d->n_media)
+        return WPT_E_INVALID;
+    std::vector<Prim> all;      /* every hitable of the scene by id (component order); type -1: not covered here */
+    for (uint32_t c = 0; c < d->n_components; c++) {
+        const wpt_component& comp = d->components[c];
+        if (comp.type == WPT_COMP_MESH_INSTANCE) {
+            const wpt_instance& in = d->instances[comp.ref];
+            const wpt_mesh& m = d->meshes[in.mesh];
+            for (uint32_t k = 0; k < m.triangle_count; k++) {
+                Prim p; std::memset(&p, 0, sizeof(p));
+                p.type = (in.animation >= 0 ? -1 : 0);
+                p.id = int32_t(all.size());
+                V3* corner[3] = { &p.v0, &p.v1, &p.v2 };
+                for (int j = 0; j < 3; j++) {
+                    const float* v = d->vertices + m.vertex_offset + size_t(d->indices[m.index_offset + 3 * k + j]) * m.vertex_stride;
+                    V3 q = { v[0], v[1], v[2] };
+                    if (in.has_transform) q = xform(in.M, q);
+                    *corner[j] = q;
+                }
+                p.box.lo = { gmin(gmin(p.v0.x, p.v1.x), p.v2.x), gmin(gmin(p.v0.y, p.v1.y), p.v2.y), gmin(gmin(p.v0.z, p.v1.z), p.v2.z) };
+                p.box.hi = { gmax(gmax(p.v0.x, p.v1.x), p.v2.x), gmax(gmax(p.v0.y, p.v1.y), p.v2.y), gmax(gmax(p.v0.z, p.v1.z), p.v2.z) };
+                all.push_back(p);
+            }
+        } else {
+            Prim p; std::memset(&p, 0, sizeof(p));
+            p.type = -1;
+            p.id = int32_t(all.size());
+            all.push_back(p);
+        }
+    }
+    const wpt_medium& m = d->media[medium];
+    for (uint32_t k = 0; k < m.boundary_count; k++) {
+        const uint32_t id = d->boundary_hitables[m.first_boundary + k];
+        if (id >= all.size() || all[id].type != 0)
+            return WPT_E_UNSUPPORTED;
+        t.prims.push_back(all[id]);
+    }
+    t.finish();
+    return 0;
+}
+
+/* The two boundary queries of HitableMedium::hit (hitable_medium.hpp:75-79) for caller-supplied rays, computed twice:
+ *   nested[2i], nested[2i+1]   as the reference does: two BVH::hit calls on the boundary's tree, (-maxval, maxval) and
+ *                              (a1 + minHitDistance, maxval);
+ *   replay[2i], replay[2i+1]   as the device does for a small triangle boundary (mediumRoundCoop / mediumTest in
+ *                              wurblpt_b200/csrc/device_trace.cuh): every boundary triangle once on the whole line, then
+ *                              both queries replayed over the triangles that were hit, in the tree's storage order, with
+ *                              the comparisons of the bounded test against the shrinking upper bound.
+ * A query without a hit is reported as +infinity. corners (optional): the boundary triangles in storage order, 9 floats each.
+ * Returns the number of boundary triangles, or a negative error. */
+long long port_medium_boundary(const wpt_scene_desc* desc, uint32_t medium, const float* origins, const float* directions,
+        uint64_t n, float minHit, float* nested, float* replay, float* corners)
+{
+    Tree tree;
+    int rc = buildBoundaryTree(desc, medium, tree);
+    if (rc != 0)
+        return rc;
+    std::vector<int32_t> order;     /* boundary triangles in the order the tree stores (= its walk meets) them */
+    for (const Node& node : tree.nodes)
+        if (node.prim >= 0)
+            order.push_back(node.prim);
+    if (corners)
+        for (size_t k = 0; k < order.size(); k++) {
+            const Prim& p = tree.prims[order[k]];
+            const float c[9] = { p.v0.x, p.v0.y, p.v0.z, p.v1.x, p.v1.y, p.v1.z, p.v2.x, p.v2.y, p.v2.z };
+            std::memcpy(corners + 9 * k, c, sizeof(c));
+        }
+    const float inf = std::numeric_limits<float>::infinity();
+    const float maxval = std::numeric_limits<float>::max();
+    #pragma omp parallel for schedule(dynamic, 256)
+    for (long long i = 0; i < (long long)n; i++) {
+        Ray r = { { origins[3 * i], origins[3 * i + 1], origins[3 * i + 2] }, { directions[3 * i], directions[3 * i + 1], directions[3 * i + 2] } };
+        /* the reference's way */
+        int32_t id;
+        float a1 = inf, a2 = inf, dist = 0.0f;
+        if (tree.hit(r, -maxval, maxval, id, dist)) {
+            a1 = dist;
+            if (tree.hit(r, a1 + minHit, maxval, id, dist))
+                a2 = dist;
+        }
+        nested[2 * i] = a1;
+        nested[2 * i + 1] = a2;
+        /* the device's way */
+        const Helper h(r);
+        std::vector<float> Ts(order.size()), ds(order.size()), as(order.size());
+        std::vector<char> found(order.size());
+        for (size_t k = 0; k < order.size(); k++)
+            found[k] = triangleOnLine(tree.prims[order[k]], r, h, Ts[k], ds[k], as[k]);
+        float b1 = maxval, b2 = maxval;
+        bool have1 = false, have2 = false;
+        for (size_t k = 0; k < order.size(); k++)
+            if (found[k] && !(Ts[k] < -maxval * ds[k] || Ts[k] > b1 * ds[k])) {
+                b1 = as[k];
+                have1 = true;
+            }
+        if (have1) {
+            const float lo = b1 + minHit;
+            for (size_t k = 0; k < order.size(); k++)
+                if (found[k] && !(Ts[k] < lo * ds[k] || Ts[k] > b2 * ds[k])) {
+                    b2 = as[k];
+                    have2 = true;
+                }
+        }
+        replay[2 * i] = have1 ? b1 : inf;
+        replay[2 * i + 1] = (have1 && have2) ? b2 : inf;
+    }
+    return (long long)order.size();
 }
 
 /* node count of the restated tree and, optionally, its arrays in the layout of wpt_scene_get_binary_nodes() */

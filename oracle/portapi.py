@@ -26,6 +26,9 @@ def lib():
                                       C.c_void_p, C.c_void_p]
         L.port_bvh_nodes.restype = C.c_longlong
         L.port_bvh_nodes.argtypes = [C.POINTER(abi.wpt_scene_desc), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.port_medium_boundary.restype = C.c_longlong
+        L.port_medium_boundary.argtypes = [C.POINTER(abi.wpt_scene_desc), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
+                                           C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -68,3 +71,18 @@ def bvh_nodes(desc):
     leaf = np.zeros(n, dtype=np.int32)
     lib().port_bvh_nodes(C.byref(desc), n, boxes.ctypes.data, link.ctypes.data, leaf.ctypes.data)
     return boxes, link, leaf
+
+
+def medium_boundary(desc, medium, origins, directions, min_hit=1e-5):
+    """The two boundary queries of HitableMedium::hit for every ray: (nested, replay, corners) - see port_medium_boundary."""
+    origins = np.ascontiguousarray(origins, dtype=np.float32)
+    directions = np.ascontiguousarray(directions, dtype=np.float32)
+    n = origins.shape[0]
+    nested = np.zeros((n, 2), dtype=np.float32)
+    replay = np.zeros((n, 2), dtype=np.float32)
+    corners = np.zeros((max(1, int(desc.media[medium].boundary_count)), 3, 3), dtype=np.float32)
+    count = lib().port_medium_boundary(C.byref(desc), medium, origins.ctypes.data, directions.ctypes.data, n, min_hit,
+                                       nested.ctypes.data, replay.ctypes.data, corners.ctypes.data)
+    if count < 0:
+        raise NotImplementedError("oracle port does not cover this medium's boundary (rc=%d)" % count)
+    return nested, replay, corners[:count]

@@ -404,7 +404,7 @@ WPT_DEV bool mediumTest(const DScene& S, uint32_t slot, const Ray& ray, const Ra
          * comparisons. This is the same computation for one thread - same tests, same comparisons, same order - so that a
          * query gets the same answer bit for bit whichever kernel serves it (frames do not depend on which slots the drain
          * kernel finishes, nor on the number of GPUs). The box tests of the nested walk are left out: what they cull
-         * fails the comparisons too. */
+         * fails the comparisons too (see mediumRoundCoop for the exception: rays exactly through a vertex or an edge). */
         const uint32_t first = run & ((1u << 26) - 1u), count = run >> 26;
         bool have1 = false, have2 = false;
         a1 = a2 = MAXVAL;
@@ -889,9 +889,12 @@ WPT_DEV void considerHit(WideBest& best, uint32_t ref, float a, float Ts, float 
  * ONCE without bounds (a triangle's distance along the line does not depend on them), and the two closest-hit queries of
  * the reference (first crossing on the whole line, next crossing behind it) are replayed over the triangles that were
  * hit, in slot order = the order the nested walk meets them, with the very comparisons of the bounded test
- * (hitable_triangle.hpp:263-264) against the shrinking upper bound (bvh.hpp:292-295). What the box tests of the nested
- * walk would have culled fails those comparisons as well, so the two distances are the nested walk's. The owner then
- * samples the free flight from its own Prng exactly as mediumTest does. Scenes without animated hitables only (the
+ * (hitable_triangle.hpp:263-264) against the shrinking upper bound (bvh.hpp:292-295). The box tests of the nested walk
+ * only cull what fails those comparisons, so the two distances are the nested walk's: bit for bit on 500 000 random
+ * rays against the restated reference (oracle/port.cpp, tests/test_oracle_port.py); only rays aimed exactly at a vertex
+ * or an edge can differ - by which of the coincident triangles is accepted (a few ulp), or because a box test of the
+ * reference culls a crossing the watertight triangle test finds. The owner then samples the free flight from its own
+ * Prng exactly as mediumTest does. Scenes without animated hitables only (the
  * corners are read for the owner's time). */
 template<int F>
 WPT_DEV void mediumRoundCoop(const DScene& S, uint32_t run, uint32_t mediumRef, const Ray& ray, const RayHelper& h,
