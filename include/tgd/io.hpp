@@ -8,10 +8,13 @@
  *   *.pfm            portable float map (1 or 3 float32 components)
  *   *.ppm / *.pgm / *.pnm   binary netpbm (3 or 1 uint8 components)
  *   *.png            PNG, 8 bit, 1 to 4 components (png.hpp: valid but uncompressed)
+ *   *.hdr / *.pic    Radiance RGBE picture (3 float32 components; hdr.hpp)
  *   anything else    "WPTARRAY" container: one text header line
  *                    "WPTARRAY <type> <components> <ndims> <dim0> <dim1> ...\n"
  *                    followed by the raw little-endian data (readable with numpy).
- * load() understands these four; PNG files may come from anywhere (non-interlaced, 8 or 16 bit).
+ * load() understands these five; PNG and Radiance files may come from anywhere (PNG: non-interlaced, 8 or 16 bit;
+ * Radiance: RGBE in the usual orientations, run-length coded or flat). A header can never make load() allocate more
+ * than the file could fill.
  */
 #pragma once
 
@@ -20,6 +23,7 @@
 
 #include "array.hpp"
 #include "png.hpp"
+#include "hdr.hpp"
 
 namespace TGD {
 
@@ -66,6 +70,24 @@ inline const char* typeName(Type t)
     return names[int(t)];
 }
 
+/* true if `count` elements of `size` bytes fit into `available` bytes (no overflow) */
+inline bool fits(size_t available, size_t count, size_t size)
+{
+    return size != 0 && count <= available / size;
+}
+
+inline size_t product(const std::vector<size_t>& dims, size_t components, bool& overflow)
+{
+    size_t n = components;
+    overflow = false;
+    for (size_t d : dims) {
+        if (d != 0 && n > size_t(-1) / d)
+            overflow = true;
+        n *= d;
+    }
+    return n;
+}
+
 inline bool typeFromName(const std::string& n, Type& t)
 {
     for (int i = 0; i <= int(float64); i++) {
@@ -106,6 +128,9 @@ inline Error save(const ArrayContainer& array, const std::string& fileName, bool
     } else if (detail::endsWith(fileName, ".png") && twoD && array.componentType() == uint8
             && array.componentCount() >= 1 && array.componentCount() <= 4) {
         ok = png::write(f, array);
+    } else if ((detail::endsWith(fileName, ".hdr") || detail::endsWith(fileName, ".pic")) && twoD
+            && array.componentType() == float32 && array.componentCount() == 3) {
+        ok = hdr::write(f, array);
     } else {
         std::fprintf(f, "WPTARRAY %s %zu %zu", detail::typeName(array.componentType()),
                 array.componentCount(), array.dimensionCount());
@@ -128,6 +153,12 @@ inline ArrayContainer load(const std::string& fileName, const TagList& /* hints 
     } else {
         char magic[16] = { 0 };
         unsigned char first = 0;
+        size_t fileSize = 0;
+        if (std::fseek(f, 0, SEEK_END) == 0) {
+            long end = std::ftell(f);
+            fileSize = (end > 0 ? size_t(end) : 0);
+        }
+        std::rewind(f);
         if (std::fread(&first, 1, 1, f) == 1 && first == 0x89) {
             /* PNG: read the whole file */
             std::vector<unsigned char> bytes(1, first);
@@ -140,6 +171,15 @@ inline ArrayContainer load(const std::string& fileName, const TagList& /* hints 
                 e = ErrorFeaturesUnsupported;
         } else if (std::fseek(f, 0, SEEK_SET) != 0 || std::fscanf(f, "%15s", magic) != 1) {
             e = ErrorInvalidData;
+        } else if (std::string(magic).rfind("#?RADIANCE", 0) == 0 || std::string(magic).rfind("#?RGBE", 0) == 0) {
+            std::rewind(f);
+            std::vector<unsigned char> bytes(fileSize);
+            if (std::fread(bytes.data(), 1, fileSize, f) != fileSize) {
+                e = ErrorSysErrno;
+            } else {
+                int rc = hdr::read(bytes, result);
+                e = (rc == 0 ? ErrorNone : rc == 1 ? ErrorFeaturesUnsupported : ErrorInvalidData);
+            }
         } else if (std::string(magic) == "WPTARRAY") {
             char tname[16] = { 0 };
             size_t comps = 0, ndims = 0;
@@ -152,6 +192,11 @@ inline ArrayContainer load(const std::string& fileName, const TagList& /* hints 
                 for (size_t d = 0; d < ndims && e == ErrorNone; d++)
                     if (std::fscanf(f, "%zu", &dims[d]) != 1)
                         e = ErrorInvalidData;
+                bool overflow = false;
+                const size_t elements = detail::product(dims, comps, overflow);
+                static const size_t typeSizes[] = { 1, 1, 2, 2, 4, 4, 8, 8, 4, 8 };
+                if (e == ErrorNone && (overflow || comps == 0 || !detail::fits(fileSize, elements, typeSizes[int(type)])))
+                    e = ErrorInvalidData;       /* more data announced than the file holds */
                 if (e == ErrorNone && std::fgetc(f) == '\n') {
                     result = ArrayContainer(dims, comps, type);
                     if (std::fread(result.data(), 1, result.dataSize(), f) != result.dataSize())
@@ -165,6 +210,9 @@ inline ArrayContainer load(const std::string& fileName, const TagList& /* hints 
             float scale = 0.0f;
             if (std::fscanf(f, "%zu %zu %f", &w, &h, &scale) != 3 || scale >= 0.0f || std::fgetc(f) != '\n') {
                 e = (scale >= 0.0f ? ErrorFeaturesUnsupported : ErrorInvalidData);
+            } else if (w == 0 || h == 0 || !detail::fits(fileSize, w, 4 * (magic[1] == 'F' ? 3 : 1))
+                    || !detail::fits(fileSize / (w * 4 * (magic[1] == 'F' ? 3 : 1)), h, 1)) {
+                e = ErrorInvalidData;
             } else {
                 result = ArrayContainer({ w, h }, magic[1] == 'F' ? 3 : 1, float32);
                 if (std::fread(result.data(), 1, result.dataSize(), f) != result.dataSize())
@@ -174,6 +222,9 @@ inline ArrayContainer load(const std::string& fileName, const TagList& /* hints 
             size_t w = 0, h = 0, maxval = 0;
             if (std::fscanf(f, "%zu %zu %zu", &w, &h, &maxval) != 3 || maxval != 255 || std::fgetc(f) != '\n') {
                 e = ErrorFeaturesUnsupported;
+            } else if (w == 0 || h == 0 || !detail::fits(fileSize, w, magic[1] == '6' ? 3 : 1)
+                    || !detail::fits(fileSize / (w * (magic[1] == '6' ? 3 : 1)), h, 1)) {
+                e = ErrorInvalidData;
             } else {
                 result = ArrayContainer({ w, h }, magic[1] == '6' ? 3 : 1, uint8);
                 size_t rowSize = w * result.elementSize();
